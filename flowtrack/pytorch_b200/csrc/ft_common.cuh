@@ -1,0 +1,50 @@
+// ft_common.cuh -- shared helpers for libflowtrack_b200 (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../../include/flowtrack_b200.h"
+
+namespace ft {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+// Returns 0 if the last launch was accepted, else records the CUDA error and returns 1.
+int check_launch(const char* what);
+
+#define FT_REQUIRE(cond, ...)              \
+    do {                                   \
+        if (!(cond)) {                     \
+            ft::set_error(__VA_ARGS__);    \
+            return 2;                      \
+        }                                  \
+    } while (0)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// ---- split-fp16 value helpers -------------------------------------------------------------------
+// v = float(hi) + float(lo).  hi is clamped to the finite fp16 range so an out-of-range activation
+// saturates instead of turning the whole downstream tensor into inf/NaN.
+__device__ __forceinline__ void split_f32(float v, __half& hi, __half& lo) {
+    float c = fminf(fmaxf(v, -65504.f), 65504.f);
+    hi = __float2half_rn(c);
+    lo = __float2half_rn(c - __half2float(hi));
+}
+
+__device__ __forceinline__ float join_f16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
+
+struct alignas(16) Half8 {
+    __half2 v[4];
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    if (act == FT_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == FT_ACT_LEAKY) return v > 0.f ? v : v * slope;
+    return v;
+}
+
+}  // namespace ft

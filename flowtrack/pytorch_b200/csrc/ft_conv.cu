@@ -1,0 +1,582 @@
+// ft_conv.cu -- fused convolution / k4s2p1 transposed convolution as an implicit GEMM on the
+// Blackwell tensor cores (tcgen05.mma, accumulators in TMEM), sm_100a only.
+//
+//   out[m, co] = act( (sum_k A[m,k] * Wt[co,k]) * scale[co] + shift[co] (+ res[m,co]) )
+//     m  = output pixel (batch folded in: n*Qh*Qw + qy*Qw + qx; 128 rows per tile, tiles may straddle
+//          image rows / images so the 8x6 maps of layer4 fill tiles as well as the 64x48 ones)
+//     k  = tap * Cin_p + ci   (implicit im2col: the A tile is gathered on the fly, never materialised)
+//
+// CTA = 9 warps, persistent over output tiles (static round-robin):
+//   warps 0-3  epilogue : tcgen05.ld the 128 x BN fp32 accumulator (lane = pixel row), scale/shift
+//                         (folded BN or bias), residual, ReLU/LeakyReLU, re-split to fp16 hi/lo, store NHWC
+//                         (or fp32 NCHW for network outputs).  Double-buffered TMEM accumulator, so the
+//                         epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 4-7  producers: gather the A tile (128 pixels x 64 k) with 16-byte cp.async into the
+//                         128B-swizzled K-major smem image tcgen05 expects; out-of-image taps and the
+//                         M/K tails are zero-filled by cp.async's src-size operand.  One of them also
+//                         issues the bulk copy (cp.async.bulk -> UBLKCP) of the pre-swizzled weight tile.
+//   warp 8     MMA      : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) four
+//                         times per 64-wide k-block -- three times that in split mode:
+//                         acc += A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  (fp16 hi/lo pairs carry 22 significant
+//                         bits, which is what the 1e-3 heat-map parity gate needs).
+//   mbarriers: full[s] (producers + weight bytes -> MMA), empty[s] (tcgen05.commit -> producers),
+//              acc_full[a] (tcgen05.commit -> epilogue), acc_empty[a] (epilogue -> MMA).
+//
+// The SIMT kernel at the bottom computes the same thing with fp32 FMAs on the same data formats; it is
+// the on-GPU cross-check used by the tests (FT_IMPL_SIMT), not a fallback: ft_conv2d_fprop never
+// switches implementation on its own.
+#include "ft_common.cuh"
+
+namespace ft {
+
+struct ConvK {
+    const __half* in_hi;
+    const __half* in_lo;
+    __half* out_hi;
+    __half* out_lo;
+    float* out_f32;
+    const __half* res_hi;
+    const __half* res_lo;
+    const uint8_t* w_tile;
+    const float* w_gemm;
+    const float* scale;
+    const float* shift;
+    int N, H, W, in_ld, in_coff, cin_p, cpt;
+    int Qh, Qw, Ho, Wo, out_ld, out_coff, cout, cout_p8, cout_pad;
+    int res_ld, res_coff;
+    int in_stride, out_mul;
+    int n_phase, taps, k_blocks, k_pad;
+    int M, m_tiles, n_tiles, num_tiles;
+    int act;
+    float slope;
+    int8_t tap_dy[4][64];
+    int8_t tap_dx[4][64];
+    int8_t ph_oy[4];
+    int8_t ph_ox[4];
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug becomes a trapped launch (reported through ft_last_error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s at 2 GHz
+    }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; both operands K-major, fp16 in, fp32 accumulate
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address  [0,14)
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                             // descriptor version 1 (sm_100)
+    d |= (uint64_t)2 << 61;                             // layout: SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B fp16, K-major both, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t f16_idesc(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+
+#define TMEM_LD_32(taddr, v)                                                                                                      \
+    asm volatile(                                                                                                                 \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"  \
+        "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                                       \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), \
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),    \
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),    \
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                                      \
+        : "r"(taddr))
+#define TMEM_LD_16(taddr, v)                                                                                                      \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"         \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),    \
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                       \
+                 : "r"(taddr))
+
+// ------------------------------------------------------------------------------------------------
+// Tile geometry shared by host and device
+// ------------------------------------------------------------------------------------------------
+constexpr int BM = 128;              // pixels per tile (UMMA M)
+constexpr int BK = 64;               // fp16 per k-block = one 128-byte swizzle row
+constexpr int A_TILE = BM * BK * 2;  // 16 KiB
+constexpr int NUM_THREADS = 288;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+template <int BN, bool SPLIT>
+struct Geo {
+    static constexpr int B_TILE = BN * BK * 2;
+    static constexpr int STAGE = (SPLIT ? 2 : 1) * (A_TILE + B_TILE);
+    static constexpr int STAGES = (SMEM_BUDGET / STAGE) > 8 ? 8 : (SMEM_BUDGET / STAGE);
+    static constexpr int LAG = STAGES >= 3 ? 2 : 1;       // cp.async groups a producer keeps in flight
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(STAGES >= 2, "tile too large for shared memory");
+};
+
+struct TileCoord {
+    int phase, mt, nt;
+};
+__device__ __forceinline__ TileCoord tile_coord(const ConvK& p, int tile) {
+    TileCoord t;
+    t.nt = tile % p.n_tiles;               // consecutive CTAs share the A tile (L2 reuse), differ in weights
+    const int r = tile / p.n_tiles;
+    t.mt = r % p.m_tiles;
+    t.phase = r / p.m_tiles;
+    return t;
+}
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvK p) {
+    using G = Geo<BN, SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + G::STAGES * G::STAGE;
+    // barrier slots (8 bytes each): full[STAGES] | empty[STAGES] | acc_full[2] | acc_empty[2] | tmem ptr
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (G::STAGES + s); };
+    auto accf_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + a); };
+    auto acce_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * G::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G::STAGES; ++s) {
+            mbar_init(full_bar(s), 128 + 1);   // 128 producer arrivals + 1 arrive.expect_tx for the weight bytes
+            mbar_init(empty_bar(s), 1);        // one tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(accf_bar(a), 1);
+            mbar_init(acce_bar(a), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)G::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp >= 4 && warp < 8) {
+        // =========================== A / weight producers ===========================
+        const int ptid = threadIdx.x - 128;
+        const int j = ptid & 7;             // 16-byte chunk (8 channels) inside the 64-wide k-block
+        const int r0 = ptid >> 3;           // rows r0 + 16*i
+        const uint32_t row_off = (uint32_t)r0 * 128u + (uint32_t)((j ^ (r0 & 7)) << 4);   // 128B swizzle: chunk ^= row%8
+        int it = 0;                         // k-block iterations issued (across tiles)
+        int arrived = 0;                    // iterations whose full-barrier arrival has been made
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const TileCoord tc = tile_coord(p, tile);
+            int pix[8], iy0[8], ix0[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = tc.mt * BM + r0 + 16 * i;
+                if (m < p.M) {
+                    const int qx = m % p.Qw, t2 = m / p.Qw;
+                    const int qy = t2 % p.Qh, n = t2 / p.Qh;
+                    iy0[i] = qy * p.in_stride;
+                    ix0[i] = qx * p.in_stride;
+                    pix[i] = (n * p.H + iy0[i]) * p.W + ix0[i];
+                } else {
+                    iy0[i] = -(1 << 20);    // fails every bounds test -> zero fill
+                    ix0[i] = 0;
+                    pix[i] = 0;
+                }
+            }
+            const uint8_t* wsrc = p.w_tile + ((size_t)(tc.phase * p.n_tiles + tc.nt) * p.k_blocks) * (size_t)(2 * G::B_TILE);
+            for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+                const int s = it % G::STAGES;
+                mbar_wait(empty_bar(s), ((it / G::STAGES) & 1) ^ 1);
+                const uint32_t stage = smem_base + s * G::STAGE;
+                if (ptid == 0) {
+                    constexpr uint32_t wbytes = (SPLIT ? 2 : 1) * G::B_TILE;
+                    mbar_arrive_expect_tx(full_bar(s), wbytes);
+                    bulk_g2s(stage + (SPLIT ? 2 : 1) * A_TILE, wsrc + (size_t)kb * (2 * G::B_TILE), wbytes, full_bar(s));
+                }
+                const int g = kb * 8 + j;            // global 8-channel chunk index along K
+                const int tap = g / p.cpt;
+                const int c8 = g - tap * p.cpt;
+                const bool tap_ok = tap < p.taps;
+                const int dy = tap_ok ? p.tap_dy[tc.phase][tap] : 0;
+                const int dx = tap_ok ? p.tap_dx[tc.phase][tap] : 0;
+                const int doff = dy * p.W + dx;
+                const int coff = p.in_coff + c8 * 8;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int iy = iy0[i] + dy, ix = ix0[i] + dx;
+                    const bool ok = tap_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                    const size_t off = ok ? ((size_t)(pix[i] + doff) * p.in_ld + coff) : 0;
+                    const uint32_t dst = stage + row_off + (uint32_t)i * (16u * 128u);
+                    cp_async16(dst, p.in_hi + off, ok ? 16u : 0u);
+                    if (SPLIT) cp_async16(dst + A_TILE, p.in_lo + off, ok ? 16u : 0u);
+                }
+                cp_async_commit();
+                if (it - arrived >= G::LAG) {
+                    cp_async_wait<G::LAG>();
+                    fence_proxy_async();
+                    mbar_arrive(full_bar(arrived % G::STAGES));
+                    ++arrived;
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (; arrived < it; ++arrived) mbar_arrive(full_bar(arrived % G::STAGES));
+    } else if (warp == 8) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            constexpr uint32_t idesc = f16_idesc(BM, BN);
+            int it = 0, local = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+                const int a = local & 1;
+                mbar_wait(acce_bar(a), ((local >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+                for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+                    const int s = it % G::STAGES;
+                    mbar_wait(full_bar(s), (it / G::STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_base + s * G::STAGE;
+                    const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * A_TILE;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = sw128_desc(a_hi + k * 32), db = sw128_desc(b_hi + k * 32);
+                        tc_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
+                        if (SPLIT) {
+                            const uint64_t dal = sw128_desc(a_hi + A_TILE + k * 32), dbl = sw128_desc(b_hi + G::B_TILE + k * 32);
+                            tc_mma_f16(d_tmem, dal, db, idesc, 1);
+                            tc_mma_f16(d_tmem, da, dbl, idesc, 1);
+                        }
+                    }
+                    tc_commit(empty_bar(s));          // smem slot reusable once these MMAs retire
+                }
+                tc_commit(accf_bar(a));               // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // =========================== epilogue ===========================
+        constexpr int CW = BN >= 32 ? 32 : 16;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+            const TileCoord tc = tile_coord(p, tile);
+            const int a = local & 1;
+            const int row = warp * 32 + lane;
+            const int m = tc.mt * BM + row;
+            const bool valid = m < p.M;
+            size_t opix = 0;
+            int n = 0, oy = 0, ox = 0;
+            if (valid) {
+                const int qx = m % p.Qw, t2 = m / p.Qw;
+                const int qy = t2 % p.Qh;
+                n = t2 / p.Qh;
+                oy = qy * p.out_mul + p.ph_oy[tc.phase];
+                ox = qx * p.out_mul + p.ph_ox[tc.phase];
+                opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
+            }
+            mbar_wait(accf_bar(a), (local >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN);
+#pragma unroll 1
+            for (int cc = 0; cc < BN / CW; ++cc) {
+                uint32_t v[CW];
+                if (CW == 32) {
+                    TMEM_LD_32(t_row + cc * CW, v);
+                } else {
+                    TMEM_LD_16(t_row + cc * CW, v);
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc == BN / CW - 1) {
+                    // every column of this accumulator stage is now in registers: hand TMEM back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(acce_bar(a));
+                }
+                if (!valid) continue;
+                const int cbase = tc.nt * BN + cc * CW;
+#pragma unroll
+                for (int g8 = 0; g8 < CW / 8; ++g8) {
+                    const int c0 = cbase + g8 * 8;
+                    if (c0 >= p.cout_p8) break;
+                    float o[8];
+                    const float4 sc0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0)), sc1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+                    const float4 sh0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0)), sh1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+                    const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                    const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] = fmaf(__uint_as_float(v[g8 * 8 + k]), scv[k], shv[k]);
+                    if (p.res_hi) {
+                        const size_t roff = opix * p.res_ld + p.res_coff + c0;
+                        const Half8 rh = *reinterpret_cast<const Half8*>(p.res_hi + roff);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 f = __half22float2(rh.v[k]);
+                            o[2 * k] += f.x, o[2 * k + 1] += f.y;
+                        }
+                        if (p.res_lo) {
+                            const Half8 rl = *reinterpret_cast<const Half8*>(p.res_lo + roff);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 f = __half22float2(rl.v[k]);
+                                o[2 * k] += f.x, o[2 * k + 1] += f.y;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] = apply_act(o[k], p.act, p.slope);
+                    if (p.out_hi) {
+                        Half8 hi, lo;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            __half h0, l0, h1, l1;
+                            split_f32(o[2 * k], h0, l0);
+                            split_f32(o[2 * k + 1], h1, l1);
+                            hi.v[k] = __halves2half2(h0, h1);
+                            lo.v[k] = __halves2half2(l0, l1);
+                        }
+                        const size_t ooff = opix * p.out_ld + p.out_coff + c0;
+                        *reinterpret_cast<Half8*>(p.out_hi + ooff) = hi;
+                        if (p.out_lo) *reinterpret_cast<Half8*>(p.out_lo + ooff) = lo;
+                    }
+                    if (p.out_f32) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (c0 + k < p.cout) p.out_f32[(((size_t)n * p.cout + c0 + k) * p.Ho + oy) * p.Wo + ox] = o[k];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT cross-check kernel: same inputs, same outputs, fp32 FMAs.
+// ------------------------------------------------------------------------------------------------
+__global__ void conv_simt_kernel(const __grid_constant__ ConvK p) {
+    const size_t total = (size_t)p.n_phase * p.M * p.cout_p8;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int co = (int)(idx % p.cout_p8);
+        const size_t r = idx / p.cout_p8;
+        const int m = (int)(r % p.M), ph = (int)(r / p.M);
+        const int qx = m % p.Qw, t2 = m / p.Qw;
+        const int qy = t2 % p.Qh, n = t2 / p.Qh;
+        float acc = 0.f;
+        const float* wp = p.w_gemm + (size_t)ph * p.k_pad * p.cout_pad + co;
+        for (int t = 0; t < p.taps; ++t) {
+            const int iy = qy * p.in_stride + p.tap_dy[ph][t], ix = qx * p.in_stride + p.tap_dx[ph][t];
+            if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
+            const size_t off = ((size_t)(n * p.H + iy) * p.W + ix) * p.in_ld + p.in_coff;
+            const float* wt = wp + (size_t)t * p.cin_p * p.cout_pad;
+            for (int ci = 0; ci < p.cin_p; ++ci) {
+                float a = __half2float(p.in_hi[off + ci]);
+                if (p.in_lo) a += __half2float(p.in_lo[off + ci]);
+                acc = fmaf(a, __ldg(wt + (size_t)ci * p.cout_pad), acc);
+            }
+        }
+        const int oy = qy * p.out_mul + p.ph_oy[ph], ox = qx * p.out_mul + p.ph_ox[ph];
+        const size_t opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
+        float o = fmaf(acc, p.scale[co], p.shift[co]);
+        if (p.res_hi) {
+            o += __half2float(p.res_hi[opix * p.res_ld + p.res_coff + co]);
+            if (p.res_lo) o += __half2float(p.res_lo[opix * p.res_ld + p.res_coff + co]);
+        }
+        o = apply_act(o, p.act, p.slope);
+        if (p.out_hi) {
+            __half h, l;
+            split_f32(o, h, l);
+            p.out_hi[opix * p.out_ld + p.out_coff + co] = h;
+            if (p.out_lo) p.out_lo[opix * p.out_ld + p.out_coff + co] = l;
+        }
+        if (p.out_f32 && co < p.cout) p.out_f32[(((size_t)n * p.cout + co) * p.Ho + oy) * p.Wo + ox] = o;
+    }
+}
+
+template <int BN, bool SPLIT>
+static int launch_tc(const ConvK& k, cudaStream_t s) {
+    using G = Geo<BN, SPLIT>;
+    static bool attr_set = false;   // per (BN,SPLIT) instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e != cudaSuccess) {
+            set_error("conv_tc_kernel<%d,%d>: cannot opt in to %d B of shared memory: %s", BN, (int)SPLIT, G::SMEM, cudaGetErrorString(e));
+            return 1;
+        }
+        attr_set = true;
+    }
+    int sms = 148;
+    const int grid = k.num_tiles < sms ? k.num_tiles : sms;
+    conv_tc_kernel<BN, SPLIT><<<grid, NUM_THREADS, G::SMEM, s>>>(k);
+    return check_launch("conv_tc_kernel");
+}
+
+static int check_view(const ft_act& a, const char* name) {
+    FT_REQUIRE(a.c % 8 == 0 && a.ld % 8 == 0 && a.coff % 8 == 0 && a.c > 0, "%s: c/ld/coff must be positive multiples of 8 (c=%d ld=%d coff=%d)", name, a.c, a.ld, a.coff);
+    FT_REQUIRE(a.coff + a.c <= a.ld, "%s: view exceeds pixel stride", name);
+    FT_REQUIRE(((uintptr_t)a.hi & 15) == 0 && ((uintptr_t)a.lo & 15) == 0, "%s: planes must be 16-byte aligned", name);
+    FT_REQUIRE(a.n > 0 && a.h > 0 && a.w > 0, "%s: empty tensor", name);
+    return 0;
+}
+
+}  // namespace ft
+
+using namespace ft;
+
+extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
+    FT_REQUIRE(d, "conv2d: null descriptor");
+    FT_REQUIRE(d->in.hi, "conv2d: null input");
+    if (int e = check_view(d->in, "conv2d.in")) return e;
+    FT_REQUIRE(d->out.hi || d->out_f32, "conv2d: no output requested");
+    FT_REQUIRE(d->scale && d->shift, "conv2d: scale/shift are required");
+    FT_REQUIRE(d->cout > 0 && d->cout_pad >= d->cout && d->cout_pad % 8 == 0, "conv2d: bad cout/cout_pad (%d/%d)", d->cout, d->cout_pad);
+    FT_REQUIRE(d->precision == FT_PREC_SPLIT || d->precision == FT_PREC_FAST, "conv2d: bad precision %d", d->precision);
+    FT_REQUIRE(d->precision == FT_PREC_FAST || d->in.lo, "conv2d: split precision needs the input lo plane");
+
+    ConvK k = {};
+    k.in_hi = (const __half*)d->in.hi;
+    k.in_lo = d->precision == FT_PREC_SPLIT ? (const __half*)d->in.lo : nullptr;
+    k.N = d->in.n, k.H = d->in.h, k.W = d->in.w;
+    k.in_ld = d->in.ld, k.in_coff = d->in.coff, k.cin_p = d->in.c, k.cpt = d->in.c / 8;
+    if (d->kind == FT_CONV) {
+        FT_REQUIRE(d->kh > 0 && d->kw > 0 && d->kh * d->kw <= 64 && d->stride > 0 && d->pad >= 0, "conv2d: unsupported window %dx%d s%d p%d", d->kh, d->kw, d->stride, d->pad);
+        k.n_phase = 1, k.taps = d->kh * d->kw;
+        k.Ho = (k.H + 2 * d->pad - d->kh) / d->stride + 1;
+        k.Wo = (k.W + 2 * d->pad - d->kw) / d->stride + 1;
+        k.Qh = k.Ho, k.Qw = k.Wo, k.in_stride = d->stride, k.out_mul = 1;
+        for (int r = 0; r < d->kh; ++r)
+            for (int s = 0; s < d->kw; ++s) {
+                k.tap_dy[0][r * d->kw + s] = (int8_t)(r - d->pad);
+                k.tap_dx[0][r * d->kw + s] = (int8_t)(s - d->pad);
+            }
+    } else if (d->kind == FT_DECONV_K4S2P1) {
+        // out[oy] += in[iy]*w[ky], oy = 2*iy - 1 + ky.  Output parity py sees ky = 1 - py + 2a (a = 0,1) at iy = qy + py - a.
+        k.n_phase = 4, k.taps = 4;
+        k.Ho = 2 * k.H, k.Wo = 2 * k.W, k.Qh = k.H, k.Qw = k.W, k.in_stride = 1, k.out_mul = 2;
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                const int ph = py * 2 + px;
+                k.ph_oy[ph] = (int8_t)py, k.ph_ox[ph] = (int8_t)px;
+                for (int a = 0; a < 2; ++a)
+                    for (int b = 0; b < 2; ++b) {
+                        k.tap_dy[ph][a * 2 + b] = (int8_t)(py - a);
+                        k.tap_dx[ph][a * 2 + b] = (int8_t)(px - b);
+                    }
+            }
+    } else {
+        FT_REQUIRE(false, "conv2d: unknown kind %d", d->kind);
+    }
+    FT_REQUIRE(k.Ho > 0 && k.Wo > 0, "conv2d: empty output");
+    k.k_pad = d->k_pad;
+    FT_REQUIRE(k.k_pad % BK == 0 && k.k_pad >= k.taps * k.cin_p && k.k_pad < k.taps * k.cin_p + BK, "conv2d: k_pad %d does not match taps*cin_p = %d", k.k_pad, k.taps * k.cin_p);
+    k.k_blocks = k.k_pad / BK;
+    k.cout = d->cout, k.cout_p8 = round_up(d->cout, 8), k.cout_pad = d->cout_pad;
+    k.scale = d->scale, k.shift = d->shift, k.act = d->act, k.slope = d->slope;
+    k.w_tile = (const uint8_t*)d->w_tile, k.w_gemm = d->w_gemm;
+    if (d->out.hi) {
+        if (int e = check_view(d->out, "conv2d.out")) return e;
+        FT_REQUIRE(d->out.n == k.N && d->out.h == k.Ho && d->out.w == k.Wo, "conv2d: output view is %dx%dx%d, expected %dx%dx%d", d->out.n, d->out.h, d->out.w, k.N, k.Ho, k.Wo);
+        FT_REQUIRE(d->out.c >= k.cout_p8, "conv2d: output view has %d channels, need %d", d->out.c, k.cout_p8);
+        k.out_hi = (__half*)d->out.hi, k.out_lo = (__half*)d->out.lo, k.out_ld = d->out.ld, k.out_coff = d->out.coff;
+    }
+    k.out_f32 = d->out_f32;
+    if (d->res.hi) {
+        if (int e = check_view(d->res, "conv2d.res")) return e;
+        FT_REQUIRE(d->res.n == k.N && d->res.h == k.Ho && d->res.w == k.Wo && d->res.c >= k.cout_p8, "conv2d: residual shape mismatch");
+        k.res_hi = (const __half*)d->res.hi, k.res_lo = (const __half*)d->res.lo, k.res_ld = d->res.ld, k.res_coff = d->res.coff;
+    }
+    const long long M = (long long)k.N * k.Qh * k.Qw;
+    FT_REQUIRE(M * 4 < (1ll << 31) && (long long)k.N * k.H * k.W < (1ll << 31), "conv2d: tensor too large for 32-bit pixel indices");
+    k.M = (int)M;
+    cudaStream_t s = (cudaStream_t)stream;
+
+    if (d->impl == FT_IMPL_SIMT) {
+        FT_REQUIRE(d->w_gemm, "conv2d: SIMT implementation needs w_gemm");
+        const size_t total = (size_t)k.n_phase * k.M * k.cout_p8;
+        size_t g = (total + 255) / 256;
+        if (g > 148 * 32) g = 148 * 32;
+        conv_simt_kernel<<<(int)g, 256, 0, s>>>(k);
+        return check_launch("conv_simt_kernel");
+    }
+    FT_REQUIRE(d->impl == FT_IMPL_TCGEN05, "conv2d: unknown impl %d", d->impl);
+    FT_REQUIRE(d->w_tile && ((uintptr_t)d->w_tile & 15) == 0, "conv2d: tcgen05 implementation needs a 16-byte aligned w_tile");
+    FT_REQUIRE(d->cout_pad % d->block_n == 0, "conv2d: cout_pad %d is not a multiple of block_n %d", d->cout_pad, d->block_n);
+    k.m_tiles = ceil_div(k.M, BM);
+    k.n_tiles = d->cout_pad / d->block_n;
+    k.num_tiles = k.n_phase * k.m_tiles * k.n_tiles;
+    const bool split = d->precision == FT_PREC_SPLIT;
+    switch (d->block_n) {
+#define FT_CASE(BN_)                                                       \
+    case BN_:                                                              \
+        return split ? launch_tc<BN_, true>(k, s) : launch_tc<BN_, false>(k, s);
+        FT_CASE(16)
+        FT_CASE(32)
+        FT_CASE(64)
+        FT_CASE(128)
+        FT_CASE(256)
+#undef FT_CASE
+        default:
+            FT_REQUIRE(false, "conv2d: block_n must be 16, 32, 64, 128 or 256 (got %d)", d->block_n);
+    }
+    return 0;
+}

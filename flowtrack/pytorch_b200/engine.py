@@ -1,0 +1,266 @@
+"""Host side of the conv stack: weight pre-transformation, split-fp16 NHWC activation buffers, and
+per-layer dispatch through the C ABI (include/flowtrack_b200.h).
+
+Nothing here computes network arithmetic on the host: the transforms are one-off layout/folding steps
+at weight-load time (eval-mode BatchNorm folded into a per-channel scale/shift; the
+k4 s2 p1 transposed convolution split into its four output-parity 2x2 sub-convolutions, SURVEY.md
+7.3 item 5), and every forward step is a kernel launch in libflowtrack_b200.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FtAct, FtConvDesc
+
+BK = 64  # k-block (fp16 elements) = one 128-byte swizzle row
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def pad8(c):
+    return round_up(c, 8)
+
+
+# --------------------------------------------------------------------------------------------------
+# weight transforms (host, numpy) -- exercised on CPU by tests/test_engine_cpu.py
+# --------------------------------------------------------------------------------------------------
+def fold_bn(bn):
+    """Eval-mode BatchNorm2d -> (scale, shift): y = x*scale + shift."""
+    s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    t = bn.bias.detach().double() - bn.running_mean.detach().double() * s
+    return s.float().cpu().numpy(), t.float().cpu().numpy()
+
+
+def gemm_weights_conv(weight, cin_p):
+    """Conv2d weight [Cout,Cin,kh,kw] -> [1, k_pad, Cout] with k = (r*kw+s)*cin_p + ci."""
+    w = weight.detach().float().cpu().numpy()
+    cout, cin, kh, kw = w.shape
+    k = kh * kw * cin_p
+    g = np.zeros((1, round_up(k, BK), cout), np.float32)
+    g[0, :k].reshape(kh * kw, cin_p, cout)[:, :cin] = w.transpose(2, 3, 1, 0).reshape(kh * kw, cin, cout)
+    return g
+
+
+def gemm_weights_deconv(weight, cin_p):
+    """ConvTranspose2d(k4,s2,p1) weight [Cin,Cout,4,4] -> [4, k_pad, Cout].
+    out[oy] += in[iy]*w[ky] with oy = 2*iy - 1 + ky, so output parity py only sees ky = 1 - py + 2a (a=0,1), read at
+    iy = qy + py - a.  phase = py*2+px, k = (a*2+b)*cin_p + ci  (matches the tap table in ft_conv2d_fprop)."""
+    w = weight.detach().float().cpu().numpy()
+    cin, cout = w.shape[:2]
+    assert w.shape[2:] == (4, 4)
+    k = 4 * cin_p
+    g = np.zeros((4, round_up(k, BK), cout), np.float32)
+    for py in range(2):
+        for px in range(2):
+            v = g[py * 2 + px, :k].reshape(4, cin_p, cout)
+            for a in range(2):
+                for b in range(2):
+                    v[a * 2 + b, :cin] = w[:, :, 1 - py + 2 * a, 1 - px + 2 * b]
+    return g
+
+
+def normalise_columns(g, scale):
+    """Scale every output channel by a power of two so max|w| lands in [1024, 2048): keeps the fp16 `lo`
+    halves out of the subnormal range.  Exact (powers of two), undone through `scale`."""
+    m = np.abs(g).max(axis=(0, 1))
+    e = np.where(m > 0, 10 - np.floor(np.log2(np.maximum(m, 1e-38))), 0.0)
+    f = np.exp2(e).astype(np.float32)
+    return g * f[None, None, :], (scale / f).astype(np.float32)
+
+
+def choose_block_n(cout, precision=_lib.PREC_SPLIT):
+    if cout >= 128:
+        return 128
+    if cout > 32:
+        return 64
+    if cout > 16:
+        return 32
+    return 16
+
+
+def tile_weights(g, block_n):
+    """[P, k_pad, cout_pad] fp32 -> uint8 image: for each (phase, n_tile, k_block) a [2 (hi,lo)][block_n][64]
+    fp16 block in the tcgen05 K-major SWIZZLE_128B layout: 16-byte chunk j of row r sits at chunk j ^ (r % 8)."""
+    P, kp, cp = g.shape
+    assert kp % BK == 0 and cp % block_n == 0
+    hi = g.astype(np.float16)
+    lo = (g - hi.astype(np.float32)).astype(np.float16)
+    t = np.stack((hi, lo), 0)                                              # [2, P, k, c]
+    t = t.reshape(2, P, kp // BK, 8, 8, cp // block_n, block_n)            # [2, P, kb, j, e, nt, r]
+    t = t.transpose(1, 5, 2, 0, 6, 3, 4)                                   # [P, nt, kb, 2, r, j, e]
+    out = np.empty_like(t)
+    r = np.arange(block_n)
+    for j in range(8):
+        out[:, :, :, :, r, j ^ (r % 8), :] = t[:, :, :, :, r, j, :]
+    return np.ascontiguousarray(out).view(np.uint8).reshape(-1)
+
+
+# --------------------------------------------------------------------------------------------------
+# activations
+# --------------------------------------------------------------------------------------------------
+class Act:
+    """Split-fp16 NHWC activation buffer on the GPU: value = hi + lo.  `view(coff, c)` selects a channel slice."""
+
+    def __init__(self, n, h, w, c, device, split=True, zero=False):
+        self.n, self.h, self.w, self.c = n, h, w, pad8(c)
+        self.ld, self.coff = self.c, 0
+        mk = torch.zeros if zero else torch.empty
+        self.hi = mk((n, h, w, self.ld), dtype=torch.float16, device=device)
+        self.lo = mk((n, h, w, self.ld), dtype=torch.float16, device=device) if split else None
+        self._base = self
+
+    def view(self, coff, c, n0=0, n=None):
+        v = object.__new__(Act)
+        v.__dict__.update(self.__dict__)
+        v.coff, v.c = self.coff + coff, pad8(c)
+        v._n0, v.n = getattr(self, "_n0", 0) + n0, (self.n - n0 if n is None else n)
+        assert v.coff % 8 == 0 and v.coff + v.c <= self.ld
+        return v
+
+    def struct(self):
+        n0 = getattr(self, "_n0", 0)
+        off = n0 * self.h * self.w * self.ld * 2
+        return FtAct(self.hi.data_ptr() + off, (self.lo.data_ptr() + off) if self.lo is not None else None,
+                     self.n, self.h, self.w, self.c, self.ld, self.coff)
+
+    def to_nchw(self, c=None):
+        """Debug/test helper: materialise the view as fp32 NCHW."""
+        n0 = getattr(self, "_n0", 0)
+        c = self.c if c is None else c
+        t = self.hi[n0:n0 + self.n, :, :, self.coff:self.coff + c].float()
+        if self.lo is not None:
+            t = t + self.lo[n0:n0 + self.n, :, :, self.coff:self.coff + c].float()
+        return t.permute(0, 3, 1, 2).contiguous()
+
+
+NULL_ACT = FtAct(None, None, 0, 0, 0, 0, 0, 0)
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# --------------------------------------------------------------------------------------------------
+# one fused conv layer
+# --------------------------------------------------------------------------------------------------
+class ConvLayer:
+    """conv / deconv(k4,s2,p1) + per-channel scale/shift + optional residual + activation, weights resident on the GPU."""
+
+    def __init__(self, kind, weight, scale, shift, stride=1, pad=0, act=_lib.ACT_NONE, slope=0.1, cin_p=None, device=None, block_n=None, keep_host=False):
+        if kind == _lib.KIND_CONV:
+            self.cout, cin, self.kh, self.kw = weight.shape
+        else:
+            cin, self.cout, self.kh, self.kw = weight.shape
+        self.kind, self.stride, self.pad, self.act, self.slope = kind, stride, pad, act, slope
+        self.cin, self.cin_p = cin, cin_p or pad8(cin)
+        assert self.cin_p % 8 == 0 and self.cin_p >= cin
+        g = gemm_weights_conv(weight, self.cin_p) if kind == _lib.KIND_CONV else gemm_weights_deconv(weight, self.cin_p)
+        self.block_n = block_n or choose_block_n(self.cout)
+        self.cout_pad = round_up(self.cout, self.block_n)
+        self.k_pad = g.shape[1]
+        gp = np.zeros((g.shape[0], self.k_pad, self.cout_pad), np.float32)
+        sc = np.zeros(self.cout_pad, np.float32)
+        sh = np.zeros(self.cout_pad, np.float32)
+        gp[:, :, :self.cout], sc[:self.cout], sh[:self.cout] = g, scale, shift
+        gp, sc = normalise_columns(gp, sc)
+        self.host = dict(w_gemm=gp, scale=sc, shift=sh) if keep_host else None
+        self.w_tile_host = tile_weights(gp, self.block_n) if keep_host else None
+        if device is not None:
+            self.w_gemm = torch.from_numpy(gp).to(device)
+            self.w_tile = torch.from_numpy(self.w_tile_host if keep_host else tile_weights(gp, self.block_n)).to(device)
+            self.scale, self.shift = torch.from_numpy(sc).to(device), torch.from_numpy(sh).to(device)
+
+    def out_hw(self, h, w):
+        if self.kind == _lib.KIND_DECONV:
+            return 2 * h, 2 * w
+        return (h + 2 * self.pad - self.kh) // self.stride + 1, (w + 2 * self.pad - self.kw) // self.stride + 1
+
+    def desc(self, x, out=None, out_f32=None, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05):
+        assert x.c == self.cin_p, "input view has %d channels, layer expects %d" % (x.c, self.cin_p)
+        d = FtConvDesc()
+        d.in_ = x.struct()
+        d.out = out.struct() if out is not None else NULL_ACT
+        d.res = res.struct() if res is not None else NULL_ACT
+        d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+        d.w_tile, d.w_gemm = self.w_tile.data_ptr(), self.w_gemm.data_ptr()
+        d.scale, d.shift = self.scale.data_ptr(), self.shift.data_ptr()
+        d.kind, d.kh, d.kw, d.stride, d.pad = self.kind, self.kh, self.kw, self.stride, self.pad
+        d.cout, d.cout_pad, d.k_pad, d.block_n = self.cout, self.cout_pad, self.k_pad, self.block_n
+        d.act, d.slope, d.precision, d.impl = self.act, self.slope, precision, impl
+        return d
+
+
+def conv_from_modules(conv, bn=None, act=_lib.ACT_NONE, cin_p=None, device=None, keep_host=False):
+    """nn.Conv2d / nn.ConvTranspose2d (+ eval BatchNorm2d) -> ConvLayer."""
+    is_deconv = isinstance(conv, torch.nn.ConvTranspose2d)
+    cout = conv.out_channels
+    if bn is not None:
+        scale, shift = fold_bn(bn)
+        if conv.bias is not None:
+            shift = shift + conv.bias.detach().float().cpu().numpy() * scale
+    else:
+        scale = np.ones(cout, np.float32)
+        shift = conv.bias.detach().float().cpu().numpy() if conv.bias is not None else np.zeros(cout, np.float32)
+    if is_deconv:
+        assert conv.kernel_size == (4, 4) and conv.stride == (2, 2) and conv.padding == (1, 1) and conv.output_padding == (0, 0)
+        return ConvLayer(_lib.KIND_DECONV, conv.weight, scale, shift, act=act, cin_p=cin_p, device=device, keep_host=keep_host)
+    assert conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
+    assert conv.dilation == (1, 1) and conv.groups == 1
+    return ConvLayer(_lib.KIND_CONV, conv.weight, scale, shift, stride=conv.stride[0], pad=conv.padding[0], act=act,
+                     cin_p=cin_p, device=device, keep_host=keep_host)
+
+
+# --------------------------------------------------------------------------------------------------
+# plans: a forward pass = a fixed list of C-ABI calls over pre-allocated buffers (CUDA-graph friendly)
+# --------------------------------------------------------------------------------------------------
+class Plan:
+    def __init__(self, device, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05):
+        self.device, self.precision, self.impl = device, precision, impl
+        self.calls = []      # (callable, args tuple); args keep ctypes structs alive
+        self.keep = []       # buffers referenced by raw pointer
+        self.graph = None
+        self.taps = {}       # name -> Act / tensor, for layer-by-layer tests
+
+    def act(self, n, h, w, c, zero=False):
+        a = Act(n, h, w, c, self.device, split=True, zero=zero)
+        self.keep.append(a)
+        return a
+
+    def f32(self, *shape):
+        t = torch.empty(shape, dtype=torch.float32, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def conv(self, layer, x, out=None, out_f32=None, res=None, name=None):
+        d = layer.desc(x, out, out_f32, res, self.precision, self.impl)
+        self.calls.append(("conv2d", _lib.lib().ft_conv2d_fprop, (ctypes.byref(d),), d))
+        if name:
+            self.taps[name] = out if out is not None else out_f32
+        return out if out is not None else out_f32
+
+    def call(self, what, fn, *args):
+        self.calls.append((what, fn, args, args))
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+            return
+        s = stream_ptr()
+        for what, fn, args, _keep in self.calls:
+            _lib.check(fn(*args, s), what)
+
+    def capture(self):
+        """Capture the call list into a CUDA graph (one launch per forward instead of one per layer)."""
+        self.run()                      # warm-up: sets function attributes, faults in code
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            s = stream_ptr()
+            for what, fn, args, _keep in self.calls:
+                _lib.check(fn(*args, s), what)
+        self.graph = g
+        return self

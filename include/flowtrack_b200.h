@@ -1,0 +1,152 @@
+/*
+ * flowtrack_b200.h -- C ABI of libflowtrack_b200.so, the B200 (sm_100a) implementation of the
+ * FlowTrack per-frame-pair inference hot path (PoseResNet forward, FlowNet2-family forward,
+ * Correlation / Resample2d / ChannelNorm, heat-map decode and box propagation).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name says `host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - nothing allocates, frees or synchronises: the calls only enqueue kernels on `stream`, so they are
+ *     CUDA-graph-capture safe;  inputs are borrowed and never modified, outputs are owned by the caller;
+ *   - return 0 on success, non-zero on an argument or launch error; ft_last_error() describes it
+ *     (thread-local).  NB the reference glue returns 1 for success (correlation_cuda.c:90); the Python
+ *     shim maps non-zero to RuntimeError so module-level behaviour (raise on failure) is unchanged.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo root):
+ *   ft_correlation_forward   Correlation_forward_cuda            lib/flownet/networks/correlation_package/src/correlation_cuda.h:1-9
+ *                            (+ Correlation_forward_cuda_kernel   .../src/correlation_cuda_kernel.h:5-39; kernels .cu:10-106)
+ *   ft_resample2d_forward    Resample2d_cuda_forward             lib/flownet/networks/resample2d_package/src/Resample2d_cuda.h:1
+ *                            (kernel_Resample2d_updateOutput      .../src/Resample2d_kernel.cu:20-66,188-206)
+ *   ft_channelnorm_forward   ChannelNorm_cuda_forward            lib/flownet/networks/channelnorm_package/src/ChannelNorm_cuda.h:1
+ *                            (kernel_ChannelNorm_updateOutput     .../src/ChannelNorm_kernel.cu:19-51,82-98)
+ *   ft_conv2d_fprop          every nn.Conv2d / nn.ConvTranspose2d(k4,s2,p1) + eval BatchNorm2d / bias +
+ *                            ReLU / LeakyReLU(0.1) + residual add on the path (cuDNN/ATen calls made by
+ *                            lib/pose/models/{resnet.py:19-27,blocks.py:89-120,pose_deconv.py:19-46} and
+ *                            lib/flownet/networks/{submodules.py:7-38,FlowNetS.py,FlowNetC.py,FlowNetSD.py,FlowNetFusion.py})
+ *   ft_maxpool3x3s2          nn.MaxPool2d(3,2,1)                  lib/pose/models/resnet.py:23
+ *   ft_pack_image / ft_pack_pair   `.cuda()` + per-sample rgb-mean normalisation   lib/flownet/model/models.py:112-119,255-257
+ *   ft_upsample4x            nn.Upsample(scale_factor=4, bilinear|nearest)          lib/flownet/networks/FlowNetS.py:58, models.py:32,59-60
+ *   ft_decode_keypoints      max_preds + final_preds + transform_preds              lib/pose/utils/evaluation.py:11-35, transforms.py:173-228
+ *   ft_box_propagation       box_propagation                                       lib/tracking/flow_utils.py:7-35
+ */
+#ifndef FLOWTRACK_B200_H_
+#define FLOWTRACK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FT_ABI_VERSION 1
+
+/* ---- activations ------------------------------------------------------------------------------
+ * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
+ * hi = fp16(v), lo = fp16(v - hi)  (22 significant bits).  `hi` and `lo` are
+ * two [n,h,w,ld] __half arrays; a view selects channels [coff, coff+c) of every pixel, so producers
+ * write straight into slices of a channel-concatenated buffer (torch.cat on the path costs nothing).
+ * c, ld and coff are multiples of 8 (16-byte vectors).  lo == NULL means "hi only" (fast mode). */
+typedef struct {
+    void* hi;
+    void* lo;
+    int32_t n, h, w;
+    int32_t c;      /* channels visible through the view (padded to a multiple of 8)            */
+    int32_t ld;     /* elements between consecutive pixels                                       */
+    int32_t coff;   /* first channel of the view inside a pixel                                  */
+} ft_act;
+
+enum { FT_ACT_NONE = 0, FT_ACT_RELU = 1, FT_ACT_LEAKY = 2 };
+enum { FT_CONV = 0, FT_DECONV_K4S2P1 = 1 };
+enum { FT_PREC_SPLIT = 0,  /* 3 tcgen05 MMAs per tile (hi*hi + lo*hi + hi*lo): fp32-grade results  */
+       FT_PREC_FAST  = 1   /* 1 MMA on the hi planes only: fp16-operand results                    */ };
+enum { FT_IMPL_TCGEN05 = 0,  /* tcgen05/TMEM implicit GEMM (the product path)                      */
+       FT_IMPL_SIMT    = 1   /* fp32 CUDA-core kernel, same data formats (bring-up / cross-check)  */ };
+
+/* One fused convolution:  out = act( conv(in, W) * scale[c] + shift[c] (+ residual) ).
+ * Weights are supplied pre-transformed by the host (flowtrack/pytorch_b200/engine.py):
+ *   w_gemm : fp32 [n_phase][k_pad][cout_pad], k = tap * in.c + ci  (taps row-major over the kernel
+ *            window; for FT_DECONV_K4S2P1 the 4 output-parity phases each see a 2x2 tap subset);
+ *   w_tile : the same matrix as tcgen05 operand tiles: for each (phase, n_tile, k_block of 64)
+ *            two [block_n][64] fp16 K-major 128B-swizzled images (hi then lo), contiguous.
+ * scale/shift have cout_pad entries (zeros in the padding).                                        */
+typedef struct {
+    ft_act in;
+    ft_act out;             /* out.hi == NULL -> no split-fp16 output                              */
+    ft_act res;             /* res.hi == NULL -> no residual                                       */
+    float* out_f32;         /* optional contiguous NCHW fp32 output [n, cout, ho, wo]              */
+    const void*  w_tile;
+    const float* w_gemm;
+    const float* scale;
+    const float* shift;
+    int32_t kind;           /* FT_CONV | FT_DECONV_K4S2P1                                          */
+    int32_t kh, kw, stride, pad;
+    int32_t cout;           /* valid output channels                                               */
+    int32_t cout_pad;       /* multiple of block_n                                                 */
+    int32_t k_pad;          /* multiple of 64                                                      */
+    int32_t block_n;        /* 16, 32, 64, 128 or 256                                              */
+    int32_t act;            /* FT_ACT_*                                                            */
+    float   slope;          /* LeakyReLU slope                                                     */
+    int32_t precision;      /* FT_PREC_*                                                           */
+    int32_t impl;           /* FT_IMPL_*                                                           */
+} ft_conv_desc;
+
+int         ft_abi_version(void);
+/* sizeof(ft_act) (which = 0) / sizeof(ft_conv_desc) (which = 1): lets a binding verify its struct layout. */
+int         ft_sizeof(int which);
+const char* ft_last_error(void);
+/* Number of kernels this library has launched since load / since the last reset (bench accounting). */
+long long   ft_launch_count(void);
+void        ft_reset_launch_count(void);
+
+/* ---- the three native ops of the reference (contiguous NCHW fp32, as there) --------------------- */
+int ft_correlation_shape(int H, int W, int pad, int ksize, int max_disp, int stride1, int stride2,
+                         int* outC, int* outH, int* outW);
+/* in1,in2: [B,C,H,W] -> out: [B,outC,outH,outW].  fuse_leaky != 0 applies LeakyReLU(0.1) (FlowNetC.py:87). */
+int ft_correlation_forward(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
+                           int pad, int ksize, int max_disp, int stride1, int stride2, int fuse_leaky,
+                           void* stream);
+/* img: [B,C,H,W], flow: [B,2,H,W] (u,v) -> out: [B,C,H,W] */
+int ft_resample2d_forward(const float* img, const float* flow, float* out, int B, int C, int H, int W, void* stream);
+/* x: [B,C,H,W] -> out: [B,1,H,W] */
+int ft_channelnorm_forward(const float* x, float* out, int B, int C, int H, int W, void* stream);
+
+/* ---- conv stack ---------------------------------------------------------------------------------- */
+int ft_conv2d_fprop(const ft_conv_desc* d, void* stream);
+int ft_maxpool3x3s2(const ft_act* in, const ft_act* out, void* stream);
+/* src: [B,C,H,W] fp32 (arbitrary strides given in elements) -> split-fp16 NHWC view `dst` channels
+ * [0,C), multiplied by `mul`; channels [C, dst->c) are zero-filled.                                   */
+int ft_pack_image(const float* src, long long sb, long long sc, long long sh, long long sw, int C,
+                  float mul, const ft_act* dst, void* stream);
+/* FlowNet2 input normalisation: pair [B,3,2,H,W] (RGB 0..255) -> x = (pair - mean_bc) / rgb_max laid
+ * out as [B,6,H,W] fp32 (x_f32, optional) and as split-fp16 NHWC (dst, optional, 6 -> 8 channels).
+ * `mean_ws` is a [B,3] fp32 workspace.                                                              */
+int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* mean_ws, float* x_f32,
+                 const ft_act* dst, void* stream);
+/* src: [B,C,h,w] fp32 -> dst: [B,C,4h,4w] fp32 times `mul`.  mode 0 = bilinear (align_corners=False),
+ * 1 = nearest.                                                                                        */
+int ft_upsample4x(const float* src, float* dst, int B, int C, int h, int w, float mul, int mode, void* stream);
+/* FlowNet2 stacking glue (models.py:126-131): warped = resample2d(x[:,3:6], flow); err = |x[:,0:3]-warped|_2;
+ * writes [x(6) | warped(3) | flow/div_flow(2) | err(1)] as 12 (+4 zero) split-fp16 NHWC channels.     */
+int ft_warp_concat(const float* x6, const float* flow, float div_flow, int B, int H, int W,
+                   const ft_act* dst, void* stream);
+/* FlowNet2 fusion input (models.py:150-172): [x0(3) | sd(2) | s2(2) | |sd| | |s2| | err_sd | err_s2]
+ * as 11 (+5 zero) split-fp16 NHWC channels; sd / s2 are the two full-resolution flow candidates.      */
+int ft_fusion_concat(const float* x6, const float* flow_sd, const float* flow_s2, int B, int H, int W,
+                     const ft_act* dst, void* stream);
+
+/* ---- decode -------------------------------------------------------------------------------------- */
+/* hm: [N,C,h,w] fp32; center: [N,2], scale: [N] fp32 -> kps: [N,C,3] = (x, y, score) in image
+ * coordinates (max_preds + optional quarter-pixel shift + inverse crop transform).                   */
+int ft_decode_keypoints(const float* hm, int N, int C, int h, int w, const float* center,
+                        const float* scale, int adjust, float* kps, void* stream);
+/* kps: [N,K,3] previous-frame key-points; frame_of: [N] int32 index of each person's frame pair;
+ * flow: [B,2,H,W] -> boxes: [N,4] (x0,y0,x1,y1).  Key-point pixels are clamped into the flow field
+ * before the look-up (the reference indexes unclamped, lib/tracking/flow_utils.py:23-24).             */
+int ft_box_propagation(const float* kps, const int32_t* frame_of, int N, int K, const float* flow,
+                       int B, int H, int W, float* boxes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWTRACK_B200_H_ */

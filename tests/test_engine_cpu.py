@@ -1,0 +1,110 @@
+"""CPU (no GPU): host-side plumbing of the B200 path -- BN folding, GEMM weight ordering, the 4-phase
+deconv decomposition, the tcgen05 tile image, state_dict compatibility, library symbols (config 1)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from flowtrack.pytorch_b200 import _lib, engine
+from tests import emulate
+from tests.golden import recipes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rand_bn(c, g):
+    bn = nn.BatchNorm2d(c).eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(c, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(c, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(c, generator=g) * 0.2)
+        bn.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+    return bn
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,hw", [(3, 64, 7, 2, (32, 24)), (64, 64, 1, 1, (8, 6)), (24, 40, 3, 2, (9, 7)),
+                                                   (16, 8, 5, 2, (12, 16)), (10, 2, 3, 1, (6, 8))])
+def test_conv_fold_and_ordering(cin, cout, k, stride, hw):
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    conv = nn.Conv2d(cin, cout, k, stride, (k - 1) // 2, bias=False)
+    bn = _rand_bn(cout, g)
+    layer = engine.conv_from_modules(conv, bn, _lib.ACT_RELU, keep_host=True)
+    x = torch.randn(2, cin, *hw, generator=g)
+    with torch.no_grad():
+        ref = torch.relu(bn(conv(x)))
+    out = emulate.emulate_layer(layer, emulate.nhwc(x, layer.cin_p)).permute(0, 3, 1, 2)
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("cin,cout,hw,bias", [(2048 // 32, 32, (8, 6), False), (10, 16, (5, 7), True), (2, 2, (3, 4), False)])
+def test_deconv_four_phase_decomposition(cin, cout, hw, bias):
+    g = torch.Generator().manual_seed(cin)
+    dc = nn.ConvTranspose2d(cin, cout, 4, 2, 1, bias=bias)
+    layer = engine.conv_from_modules(dc, None, _lib.ACT_LEAKY, keep_host=True)
+    x = torch.randn(2, cin, *hw, generator=g)
+    with torch.no_grad():
+        ref = torch.nn.functional.leaky_relu(dc(x), 0.1)
+    out = emulate.emulate_layer(layer, emulate.nhwc(x, layer.cin_p)).permute(0, 3, 1, 2)
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max() < 1e-5
+
+
+def test_tile_image_roundtrip_and_split_precision():
+    conv = nn.Conv2d(72, 130, 3, 1, 1)          # K = 9*72 = 648 -> k_pad 704; cout 130 -> block 128, cout_pad 256
+    layer = engine.conv_from_modules(conv, None, keep_host=True)
+    assert layer.block_n == 128 and layer.cout_pad == 256 and layer.k_pad == 704
+    wg = layer.host["w_gemm"]
+    back = emulate.untile(layer)
+    rel = np.abs(back - wg).max() / np.abs(wg).max()
+    assert rel < 2.0 ** -21                                # hi+lo carries >= 21 significant bits
+    assert layer.w_tile_host.size == 1 * 2 * 11 * 2 * 128 * 64 * 2
+    m = np.abs(wg).max(axis=(0, 1))[:130]
+    assert np.all((m >= 1024) & (m < 2048))               # power-of-two column normalisation
+
+
+def test_pose_state_dict_layout_matches_reference(golden):
+    import hashlib
+    from flowtrack.pytorch_b200.pose import models
+    for depth in (50, 101, 152):
+        m = models.deconv("resnet%d" % depth, 17, False)
+        dig = hashlib.sha256("\n".join("%s %s" % (k, tuple(v.shape)) for k, v in m.state_dict().items()).encode()).hexdigest()
+        assert dig == str(golden["pose%d_keys" % depth])
+
+
+def test_pose_config1_plumbing_on_cpu(golden):
+    """BASELINE config 1: R50 single crop on CPU -- oracle forward vs the folded/decomposed graph the GPU path executes."""
+    from flowtrack.pytorch_b200.pose import models
+    orc = recipes.pose_oracle_model(50)
+    m = models.deconv("resnet50", 17, False)
+    m.load_state_dict(orc.state_dict(), strict=True)
+    x = recipes.pose_input(50)[:1]
+    with torch.no_grad():
+        ref = orc(x)
+    out = emulate.emulate_pose(m, x)
+    assert out.shape == ref.shape == (1, 17, 32, 24)
+    assert (out - ref).abs().max() < 1e-4
+    assert (ref - torch.from_numpy(golden["pose50_heatmap"][:1])).abs().max() < 2e-4
+
+
+def test_no_cpu_fallback():
+    from flowtrack.pytorch_b200.pose import models
+    m = models.deconv("resnet50", 17, False)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError, match="inference path only"):
+        m.train()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "flowtrack_b200.h")).read()
+    declared = set(re.findall(r"\b(ft_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"ft_act", "ft_conv_desc"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    l = _lib.lib()                                         # loads the .so and resolves every symbol
+    assert l.ft_abi_version() == 1
+    assert l.ft_sizeof(0) == ctypes.sizeof(_lib.FtAct) == 40 and l.ft_sizeof(1) == ctypes.sizeof(_lib.FtConvDesc)
