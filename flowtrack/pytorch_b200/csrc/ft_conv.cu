@@ -25,6 +25,8 @@
 // The SIMT kernel at the bottom computes the same thing with fp32 FMAs on the same data formats; it is
 // the on-GPU cross-check used by the tests (FT_IMPL_SIMT), not a fallback: ft_conv2d_fprop never
 // switches implementation on its own.
+#include <stdlib.h>
+
 #include "ft_common.cuh"
 
 namespace ft {
@@ -53,6 +55,8 @@ struct ConvK {
     int8_t tap_dx[4][64];
     int8_t ph_oy[4];
     int8_t ph_ox[4];
+    uint32_t desc_hi;   // upper 32 bits of the smem matrix descriptor (SBO | version | layout); FT_DBG_DESC overrides
+    uint32_t desc_lbo;  // leading-byte-offset field
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -120,14 +124,13 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// K-major operand tile, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
-    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address  [0,14)
-    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset [32,46)
-    d |= (uint64_t)1 << 46;                             // descriptor version 1 (sm_100)
-    d |= (uint64_t)2 << 61;                             // layout: SWIZZLE_128B
-    return d;
+// K-major operand tile, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |
+//   [32,46) stride byte offset >> 4 | [46,48) version = 1 on sm_100 | [61,64) layout (2 = SWIZZLE_128B)
+constexpr uint32_t DESC_HI_DEFAULT = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t DESC_LBO_DEFAULT = 1;
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr, uint32_t hi, uint32_t lbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)lbo << 16) | ((uint64_t)hi << 32);
 }
 // kind::f16 instruction descriptor: D fp32, A/B fp16, K-major both, N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t f16_idesc(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
@@ -298,10 +301,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * A_TILE;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = sw128_desc(a_hi + k * 32), db = sw128_desc(b_hi + k * 32);
+                        const uint64_t da = sw128_desc(a_hi + k * 32, p.desc_hi, p.desc_lbo), db = sw128_desc(b_hi + k * 32, p.desc_hi, p.desc_lbo);
                         tc_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
                         if (SPLIT) {
-                            const uint64_t dal = sw128_desc(a_hi + A_TILE + k * 32), dbl = sw128_desc(b_hi + G::B_TILE + k * 32);
+                            const uint64_t dal = sw128_desc(a_hi + A_TILE + k * 32, p.desc_hi, p.desc_lbo), dbl = sw128_desc(b_hi + G::B_TILE + k * 32, p.desc_hi, p.desc_lbo);
                             tc_mma_f16(d_tmem, dal, db, idesc, 1);
                             tc_mma_f16(d_tmem, da, dbl, idesc, 1);
                         }
@@ -564,6 +567,13 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     k.m_tiles = ceil_div(k.M, BM);
     k.n_tiles = d->cout_pad / d->block_n;
     k.num_tiles = k.n_phase * k.m_tiles * k.n_tiles;
+    k.desc_hi = DESC_HI_DEFAULT, k.desc_lbo = DESC_LBO_DEFAULT;
+    if (const char* dbg = getenv("FT_DBG_DESC")) {   // bring-up knob: "sbo16,version,layout,lbo16"
+        unsigned sbo = 64, ver = 1, lay = 2, lbo = 1;
+        sscanf(dbg, "%u,%u,%u,%u", &sbo, &ver, &lay, &lbo);
+        k.desc_hi = (sbo & 0x3FFF) | ((ver & 3) << 14) | ((lay & 7) << 29);
+        k.desc_lbo = lbo & 0x3FFF;
+    }
     const bool split = d->precision == FT_PREC_SPLIT;
     switch (d->block_n) {
 #define FT_CASE(BN_)                                                       \

@@ -1,0 +1,35 @@
+"""Helpers for the -m gpu tests: drive single layers / ops through the C ABI."""
+import ctypes
+
+import torch
+
+from flowtrack.pytorch_b200 import _lib, engine
+
+
+def sp():
+    return engine.stream_ptr()
+
+
+def pack_nchw(x, cpad=None):
+    """fp32 NCHW cuda tensor -> split-fp16 NHWC Act via ft_pack_image."""
+    B, C, H, W = x.shape
+    a = engine.Act(B, H, W, cpad or C, x.device)
+    st = x.stride()
+    _lib.check(_lib.lib().ft_pack_image(x.data_ptr(), st[0], st[1], st[2], st[3], C, 1.0, a.struct(), sp()), "pack_image")
+    return a
+
+
+def run_layer(layer, x_act, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05, want_f32=False, out=None):
+    ho, wo = layer.out_hw(x_act.h, x_act.w)
+    if out is None:
+        out = engine.Act(x_act.n, ho, wo, layer.cout, x_act.hi.device, zero=True)
+    f32 = torch.zeros(x_act.n, layer.cout, ho, wo, device=x_act.hi.device) if want_f32 else None
+    d = layer.desc(x_act, out, f32, res, precision, impl)
+    _lib.check(_lib.lib().ft_conv2d_fprop(ctypes.byref(d), sp()), "conv2d")
+    torch.cuda.synchronize()
+    return (out, f32) if want_f32 else out
+
+
+def strict_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False

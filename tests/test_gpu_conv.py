@@ -1,0 +1,98 @@
+"""GPU parity of ft_conv2d_fprop: SIMT cross-check kernel and the tcgen05 kernel (split and fast
+precision) vs torch fp32 convolution of the same op.  Tolerances: split mode is fp32-grade
+(<= 2e-5 relative to the output scale), fast mode is fp16-operand (<= 2e-3 relative)."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from flowtrack.pytorch_b200 import _lib, engine
+from tests import gpu_util
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, module ctor, input shape, act
+    ("1x1_64_64", lambda: nn.Conv2d(64, 64, 1, bias=False), (2, 64, 16, 12), _lib.ACT_RELU),
+    ("1x1_256_64_tail", lambda: nn.Conv2d(256, 64, 1, bias=False), (3, 256, 7, 9), _lib.ACT_RELU),        # M = 189: tail tile
+    ("3x3_64", lambda: nn.Conv2d(64, 64, 3, 1, 1, bias=False), (2, 64, 16, 12), _lib.ACT_RELU),
+    ("3x3_s2_128", lambda: nn.Conv2d(128, 128, 3, 2, 1, bias=False), (2, 128, 16, 12), _lib.ACT_RELU),
+    ("1x1_s2_down", lambda: nn.Conv2d(256, 512, 1, 2, bias=False), (2, 256, 16, 12), _lib.ACT_NONE),
+    ("stem7x7", lambda: nn.Conv2d(3, 64, 7, 2, 3, bias=False), (2, 3, 64, 48), _lib.ACT_RELU),
+    ("flow5x5_s2", lambda: nn.Conv2d(64, 128, 5, 2, 2), (1, 64, 24, 32), _lib.ACT_LEAKY),
+    ("cin1032_pred", lambda: nn.Conv2d(1026, 2, 3, 1, 1), (1, 1026, 6, 8), _lib.ACT_NONE),                 # odd concat width, Cout 2
+    ("head17", lambda: nn.Conv2d(256, 17, 1), (2, 256, 16, 12), _lib.ACT_NONE),
+    ("wide_2048", lambda: nn.Conv2d(512, 2048, 1, bias=False), (4, 512, 8, 6), _lib.ACT_NONE),
+    ("deconv_2048", lambda: nn.ConvTranspose2d(2048, 256, 4, 2, 1, bias=False), (2, 2048, 8, 6), _lib.ACT_RELU),
+    ("deconv_flow", lambda: nn.ConvTranspose2d(386, 64, 4, 2, 1), (1, 386, 12, 16), _lib.ACT_LEAKY),
+    ("deconv_2to2", lambda: nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=False), (2, 2, 6, 8), _lib.ACT_NONE),
+]
+
+
+def _ref(mod, x, act):
+    with torch.no_grad():
+        y = mod(x)
+    if act == _lib.ACT_RELU:
+        y = torch.relu(y)
+    elif act == _lib.ACT_LEAKY:
+        y = F.leaky_relu(y, 0.1)
+    return y
+
+
+@pytest.mark.parametrize("name,ctor,shape,act", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("impl,prec,tol", [(_lib.IMPL_SIMT, _lib.PREC_SPLIT, 2e-5), (_lib.IMPL_TCGEN05, _lib.PREC_SPLIT, 2e-5),
+                                           (_lib.IMPL_TCGEN05, _lib.PREC_FAST, 3e-3)], ids=["simt", "tc_split", "tc_fast"])
+def test_conv_layer(name, ctor, shape, act, impl, prec, tol):
+    torch.manual_seed(hash(name) % 1000)
+    mod = ctor().double()
+    x = torch.randn(*shape, dtype=torch.float64)
+    ref = _ref(mod, x, act).float()
+    layer = engine.conv_from_modules(mod.float(), None, act, device="cuda")
+    xa = gpu_util.pack_nchw(x.float().cuda(), layer.cin_p)
+    out, f32 = gpu_util.run_layer(layer, xa, precision=prec, impl=impl, want_f32=True)
+    got = out.to_nchw(layer.cout).cpu()
+    scale = max(1.0, ref.abs().max().item())
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max() <= tol * scale, (got - ref).abs().max().item()
+    assert (f32.cpu() - ref).abs().max() <= tol * scale                            # fp32 NCHW output path
+    if out.c > layer.cout:
+        assert out.to_nchw()[:, layer.cout:].abs().max() == 0                      # padded channels are written as zeros
+
+
+@pytest.mark.parametrize("prec,tol", [(_lib.PREC_SPLIT, 2e-5), (_lib.PREC_FAST, 3e-3)])
+def test_bottleneck_tail_with_bn_and_residual(prec, tol):
+    """conv3 of a bottleneck: 1x1 + folded BN + residual add + ReLU in one launch, written into a channel slice."""
+    g = torch.Generator().manual_seed(5)
+    conv = nn.Conv2d(64, 256, 1, bias=False)
+    bn = nn.BatchNorm2d(256).eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(256, generator=g) * 0.2 + 0.1)
+        bn.bias.copy_(torch.randn(256, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(256, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(256, generator=g) + 0.5)
+    x, r = torch.randn(3, 64, 16, 12, generator=g), torch.randn(3, 256, 16, 12, generator=g)
+    with torch.no_grad():
+        ref = torch.relu(bn(conv(x)) + r)
+    layer = engine.conv_from_modules(conv, bn, _lib.ACT_RELU, device="cuda")
+    xa, ra = gpu_util.pack_nchw(x.cuda()), gpu_util.pack_nchw(r.cuda())
+    big = engine.Act(3, 16, 12, 256 + 64, "cuda", zero=True)                        # write into channels [64, 320) of a wider buffer
+    out = gpu_util.run_layer(layer, xa, res=ra, precision=prec, out=big.view(64, 256))
+    got = out.to_nchw().cpu()
+    assert (got - ref).abs().max() <= tol * max(1.0, ref.abs().max().item())
+    assert big.to_nchw()[:, :64].abs().max() == 0                                   # neighbours of the slice untouched
+
+
+def test_tc_matches_simt_bitwise_scale_on_large_tile_count():
+    """Persistent scheduling: many tiles per CTA, both TMEM accumulator stages and all smem stages wrap."""
+    torch.manual_seed(11)
+    conv = nn.Conv2d(128, 256, 3, 1, 1, bias=True)
+    x = torch.randn(8, 128, 64, 48)                                                 # M = 24576 -> 192 m-tiles x 2 n-tiles
+    layer = engine.conv_from_modules(conv, None, _lib.ACT_LEAKY, device="cuda")
+    xa = gpu_util.pack_nchw(x.cuda())
+    a = gpu_util.run_layer(layer, xa, impl=_lib.IMPL_TCGEN05).to_nchw()
+    b = gpu_util.run_layer(layer, xa, impl=_lib.IMPL_SIMT).to_nchw()
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        ref = F.leaky_relu(conv.cuda()(x.cuda()), 0.1)
+    assert (a - b).abs().max() < 2e-5 * ref.abs().max()
+    assert (a - ref).abs().max() < 2e-5 * ref.abs().max()

@@ -1,0 +1,167 @@
+"""GPU parity: native flow ops, layout kernels and decode vs the CPU oracle (and, for Correlation,
+vs the reference's own kernel compiled into oracle/_ref when that .so travelled with the snapshot)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from flowtrack.pytorch_b200 import _lib, engine
+from oracle import decode_oracle, flow_oracle, ops_oracle
+from tests import gpu_util
+from tests.golden import recipes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+L = _lib.lib
+
+
+def _corr(a, b, pad, k, md, s1, s2, leaky=0):
+    B, C, H, W = a.shape
+    oc, oh, ow = ops_oracle.correlation_shape(H, W, pad, k, md, s1, s2)
+    out = torch.full((B, oc, oh, ow), float("nan"), device="cuda")
+    _lib.check(L().ft_correlation_forward(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, C, H, W, pad, k, md, s1, s2, leaky, gpu_util.sp()), "corr")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("shape,params", [((2, 256, 48, 64), (20, 1, 20, 1, 2)),      # FlowNetC shape (fast path)
+                                          ((1, 40, 13, 70), (20, 1, 20, 1, 2)),       # ragged: H not /8, W > 64, C not /4
+                                          ((2, 24, 12, 16), (4, 1, 4, 1, 1)),         # generic path
+                                          ((1, 8, 14, 18), (3, 3, 2, 2, 1))])         # 3x3 patches, stride1 2
+def test_correlation_vs_oracle(shape, params):
+    g = torch.Generator().manual_seed(sum(shape))
+    a, b = torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)
+    ref = ops_oracle.correlation_torch(a, b, *params)
+    out = _corr(a.cuda(), b.cuda(), *params).cpu()
+    assert out.shape == ref.shape
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max() < 1e-5 * max(1.0, ref.abs().max().item())
+    if shape[0] * shape[1] * shape[2] * shape[3] < 300000:
+        assert (out - ops_oracle.correlation_c(a, b, *params)).abs().max() < 1e-5
+
+
+def test_correlation_leaky_and_linearity():
+    g = torch.Generator().manual_seed(1)
+    a, b = torch.randn(2, 256, 48, 64, generator=g).cuda(), torch.randn(2, 256, 48, 64, generator=g).cuda()
+    o = _corr(a, b, 20, 1, 20, 1, 2)
+    ol = _corr(a, b, 20, 1, 20, 1, 2, leaky=1)
+    assert torch.equal(ol, torch.where(o > 0, o, 0.1 * o))
+    assert (_corr(2 * a, b, 20, 1, 20, 1, 2) - 2 * o).abs().max() < 1e-6          # linear in input1
+    centre = o[:, 220]                                                             # zero displacement = mean_c a*b
+    assert (centre - (a * b).mean(1)).abs().max() < 1e-5
+
+
+def test_correlation_vs_reference_kernel():
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_correlation.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libref_correlation.so not built (needs /root/reference at build time)")
+    ref = ctypes.CDLL(so)
+    g = torch.Generator().manual_seed(2)
+    B, C, H, W = 2, 256, 48, 64
+    a, b = torch.randn(B, C, H, W, generator=g).cuda(), torch.randn(B, C, H, W, generator=g).cuda()
+    out = torch.zeros(B, 441, H, W, device="cuda")
+    r1 = torch.zeros(B, H + 40, W + 40, C, device="cuda")
+    r2 = torch.zeros_like(r1)
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    ref.Correlation_forward_cuda_kernel.argtypes = [vp] + [ci] * 8 + [vp] + [ci] * 7 + [vp] + [ci] * 5 + [vp, vp] + [ci] * 6 + [vp]
+    ok = ref.Correlation_forward_cuda_kernel(out.data_ptr(), B, 441, H, W, *out.stride(), a.data_ptr(), C, H, W, *a.stride(),
+                                             b.data_ptr(), C, *b.stride(), r1.data_ptr(), r2.data_ptr(), 20, 1, 20, 1, 2, 1, None)
+    torch.cuda.synchronize()
+    assert ok == 1
+    mine = _corr(a, b, 20, 1, 20, 1, 2)
+    assert (mine - out).abs().max() < 1e-5
+
+
+def test_resample2d_and_channelnorm():
+    g = torch.Generator().manual_seed(3)
+    img, flow = torch.randn(2, 3, 96, 128, generator=g), torch.randn(2, 2, 96, 128, generator=g) * 9
+    flow[0, :, :4] = 500.0                                                        # far out of range: clamp-to-edge
+    out = torch.empty(2, 3, 96, 128, device="cuda")
+    _lib.check(L().ft_resample2d_forward(img.cuda().data_ptr(), flow.cuda().data_ptr(), out.data_ptr(), 2, 3, 96, 128, gpu_util.sp()), "resample")
+    assert (out.cpu() - ops_oracle.resample2d_c(img, flow)).abs().max() < 1e-5
+    zero = torch.zeros_like(flow).cuda()
+    _lib.check(L().ft_resample2d_forward(img.cuda().data_ptr(), zero.data_ptr(), out.data_ptr(), 2, 3, 96, 128, gpu_util.sp()), "resample")
+    assert torch.equal(out.cpu(), img)                                            # identity warp is exact
+    x = torch.randn(2, 3, 96, 128, generator=g)
+    n = torch.empty(2, 1, 96, 128, device="cuda")
+    _lib.check(L().ft_channelnorm_forward(x.cuda().data_ptr(), n.data_ptr(), 2, 3, 96, 128, gpu_util.sp()), "cnorm")
+    assert (n.cpu() - ops_oracle.channelnorm_c(x)).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_upsample4x(mode):
+    x = torch.randn(2, 2, 24, 32, generator=torch.Generator().manual_seed(4))
+    out = torch.empty(2, 2, 96, 128, device="cuda")
+    _lib.check(L().ft_upsample4x(x.cuda().data_ptr(), out.data_ptr(), 2, 2, 24, 32, 20.0, mode, gpu_util.sp()), "up")
+    ref = F.interpolate(x * 20.0, scale_factor=4, mode="bilinear", align_corners=False) if mode == 0 else F.interpolate(x * 20.0, scale_factor=4, mode="nearest")
+    assert (out.cpu() - ref).abs().max() < 1e-4
+
+
+def test_pack_pair_and_layout_roundtrip():
+    pair = recipes.flow_input(2, (64, 128))
+    B, H, W = 2, 64, 128
+    d = engine.Act(B, H, W, 8, "cuda")
+    xf = torch.empty(B, 6, H, W, device="cuda")
+    ws = torch.empty(B * 3, device="cuda")
+    _lib.check(L().ft_pack_pair(pair.cuda().data_ptr(), B, H, W, 255.0, ws.data_ptr(), xf.data_ptr(), d.struct(), gpu_util.sp()), "pack_pair")
+    ref = flow_oracle.normalise_pair(pair, 255.0)
+    assert (xf.cpu() - ref).abs().max() < 1e-6
+    back = d.to_nchw().cpu()
+    assert (back[:, :6] - ref).abs().max() < 1e-6 and back[:, 6:].abs().max() == 0   # split-fp16 keeps ~22 bits
+
+
+def test_maxpool():
+    x = torch.randn(2, 64, 32, 24, generator=torch.Generator().manual_seed(6)).cuda()
+    a = gpu_util.pack_nchw(x)
+    o = engine.Act(2, 16, 12, 64, "cuda")
+    _lib.check(L().ft_maxpool3x3s2(a.struct(), o.struct(), gpu_util.sp()), "maxpool")
+    assert torch.equal(o.to_nchw(), F.max_pool2d(a.to_nchw(), 3, 2, 1))
+
+
+def test_decode_matches_oracle_and_golden(golden):
+    hm = recipes.decode_heatmaps()
+    center = torch.tensor(golden["decode_center"], dtype=torch.float32)
+    scale = torch.tensor(golden["decode_scale"], dtype=torch.float32)
+    for adjust, key in ((1, "decode_coords_adjust"), (0, "decode_coords_plain")):
+        kps = torch.empty(3, 17, 3, device="cuda")
+        _lib.check(L().ft_decode_keypoints(hm.cuda().data_ptr(), 3, 17, 64, 48, center.cuda().data_ptr(), scale.cuda().data_ptr(), adjust, kps.data_ptr(), gpu_util.sp()), "decode")
+        kps = kps.cpu().numpy()
+        np.testing.assert_allclose(kps[:, :, :2], golden[key], atol=2e-3)          # fixtures made by the real final_preds
+        np.testing.assert_array_equal(kps[:, :, 2:], golden["decode_scores"])
+        c, s = decode_oracle.final_preds(hm.numpy(), golden["decode_center"], golden["decode_scale"], bool(adjust))
+        np.testing.assert_allclose(kps[:, :, :2], c, atol=2e-3)
+    # ties: first maximum wins (torch.max semantics)
+    flat = torch.zeros(1, 1, 4, 6)
+    flat[0, 0, 1, 2] = flat[0, 0, 3, 5] = 1.0
+    kps = torch.empty(1, 1, 3, device="cuda")
+    one = torch.tensor([[3.0, 2.0]]).cuda()
+    sc = torch.tensor([4.0]).cuda()                                                # s = h/scale = 1 -> identity + offset
+    _lib.check(L().ft_decode_keypoints(flat.cuda().data_ptr(), 1, 1, 4, 6, one.data_ptr(), sc.data_ptr(), 0, kps.data_ptr(), gpu_util.sp()), "decode")
+    assert kps.cpu().tolist() == [[[2.0, 1.0, 1.0]]]
+
+
+def test_box_propagation_vs_oracle():
+    g = torch.Generator().manual_seed(8)
+    B, H, W, N, K = 3, 96, 128, 7, 17
+    flow = torch.randn(B, 2, H, W, generator=g) * 5
+    kp = torch.rand(N, K, 3, generator=g) * torch.tensor([W - 1.0, H - 1.0, 1.0])
+    kp[:, ::5, 2] = -0.2                                                           # some joints below threshold
+    frame_of = torch.tensor([0, 0, 1, 1, 2, 2, 2], dtype=torch.int32)
+    boxes = torch.empty(N, 4, device="cuda")
+    _lib.check(L().ft_box_propagation(kp.cuda().data_ptr(), frame_of.cuda().data_ptr(), N, K, flow.cuda().data_ptr(), B, H, W, boxes.data_ptr(), gpu_util.sp()), "boxprop")
+    for n in range(N):
+        ref = decode_oracle.box_propagation(kp[n:n + 1].numpy(), flow[frame_of[n]].numpy())
+        np.testing.assert_allclose(boxes[n].cpu().numpy(), ref[0], atol=1e-4)
+
+
+def test_bad_arguments_raise():
+    with pytest.raises(RuntimeError, match="correlation"):
+        _lib.check(L().ft_correlation_forward(None, None, None, 1, 1, 1, 1, 20, 1, 20, 1, 2, 0, None), "corr")
+    a = engine.Act(1, 4, 4, 8, "cuda")
+    bad = a.struct()
+    bad.ld = 12
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        _lib.check(L().ft_maxpool3x3s2(bad, a.struct(), None), "maxpool")
