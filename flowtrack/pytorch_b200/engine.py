@@ -179,6 +179,13 @@ class ConvLayer:
             return 2 * h, 2 * w
         return (h + 2 * self.pad - self.kh) // self.stride + 1, (w + 2 * self.pad - self.kw) // self.stride + 1
 
+    def flops(self, n, h, w):
+        """Algorithmic FLOPs (2 x MACs over the real, un-padded channels) of one forward on an n x h x w input."""
+        if self.kind == _lib.KIND_DECONV:
+            return 2 * n * h * w * self.cin * self.cout * self.kh * self.kw
+        ho, wo = self.out_hw(h, w)
+        return 2 * n * ho * wo * self.cin * self.cout * self.kh * self.kw
+
     def desc(self, x, out=None, out_f32=None, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05):
         assert x.c == self.cin_p, "input view has %d channels, layer expects %d" % (x.c, self.cin_p)
         d = FtConvDesc()
@@ -224,6 +231,7 @@ class Plan:
         self.keep = []       # buffers referenced by raw pointer
         self.graph = None
         self.taps = {}       # name -> Act / tensor, for layer-by-layer tests
+        self.flops = {}      # call index -> algorithmic FLOPs (convolutions only)
 
     def act(self, n, h, w, c, zero=False):
         a = Act(n, h, w, c, self.device, split=True, zero=zero)
@@ -238,6 +246,7 @@ class Plan:
     def conv(self, layer, x, out=None, out_f32=None, res=None, name=None):
         d = layer.desc(x, out, out_f32, res, self.precision, self.impl)
         self.calls.append(("conv2d", _lib.lib().ft_conv2d_fprop, (ctypes.byref(d),), d))
+        self.flops[len(self.calls) - 1] = layer.flops(x.n, x.h, x.w)
         if name:
             self.taps[name] = out if out is not None else out_f32
         return out if out is not None else out_f32
@@ -245,13 +254,34 @@ class Plan:
     def call(self, what, fn, *args):
         self.calls.append((what, fn, args, args))
 
+    def enqueue(self):
+        """Issue every call of the plan on the current stream (also what graph capture records)."""
+        s = stream_ptr()
+        for what, fn, args, _keep in self.calls:
+            _lib.check(fn(*args, s), what)
+
+    def time_calls(self, reps=3):
+        """Per-call device time in ms (CUDA events on the launching stream, averaged over `reps` un-graphed passes).
+        Event pairs around single launches include a few us of launch gap; bench.py uses this for the roofline."""
+        s = stream_ptr()
+        n = len(self.calls)
+        tot = [0.0] * n
+        for _ in range(reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+            ev[0].record()
+            for i, (what, fn, args, _keep) in enumerate(self.calls):
+                _lib.check(fn(*args, s), what)
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            for i in range(n):
+                tot[i] += ev[i].elapsed_time(ev[i + 1])
+        return [t / reps for t in tot]
+
     def run(self):
         if self.graph is not None:
             self.graph.replay()
             return
-        s = stream_ptr()
-        for what, fn, args, _keep in self.calls:
-            _lib.check(fn(*args, s), what)
+        self.enqueue()
 
     def capture(self):
         """Capture the call list into a CUDA graph (one launch per forward instead of one per layer)."""
@@ -259,8 +289,6 @@ class Plan:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            s = stream_ptr()
-            for what, fn, args, _keep in self.calls:
-                _lib.check(fn(*args, s), what)
+            self.enqueue()
         self.graph = g
         return self

@@ -62,6 +62,24 @@ class _FlowBase(nn.Module):
     def _build(self, p, L, pair, B, H, W):
         raise NotImplementedError
 
+    def plan_for(self, B, H, W, device):
+        """(plan, static fp32 input [B,3,2,H,W], static fp32 flow [B,2,H,W]) for this batch shape; built once and cached."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("%s.forward needs a CUDA tensor: this package has no CPU path" % type(self).__name__)
+        if H % 64 or W % 64:
+            raise ValueError("expected [B,3,2,H,W] with H, W multiples of 64, got %s" % ((B, 3, 2, H, W),))
+        prec = _lib.PREC_FAST if self.precision == "fast" else _lib.PREC_SPLIT
+        key = (B, H, W, prec, self._impl, device.index if device.index is not None else torch.cuda.current_device())
+        if key not in self._plans:
+            if self._layers is None:
+                self._layers = self._pack(device)
+            p = engine.Plan(device, prec, self._impl)
+            pair = p.f32(B, 3, 2, H, W)
+            out = self._build(p, self._layers, pair, B, H, W)
+            self._plans[key] = (p, pair, out)
+        return self._plans[key]
+
     @torch.no_grad()
     def forward(self, inputs):
         if not inputs.is_cuda:
@@ -69,16 +87,7 @@ class _FlowBase(nn.Module):
         if inputs.dim() != 5 or inputs.shape[1] != 3 or inputs.shape[2] != 2 or inputs.shape[3] % 64 or inputs.shape[4] % 64:
             raise ValueError("expected [B,3,2,H,W] with H, W multiples of 64, got %s" % (tuple(inputs.shape),))
         B, _, _, H, W = inputs.shape
-        prec = _lib.PREC_FAST if self.precision == "fast" else _lib.PREC_SPLIT
-        key = (B, H, W, prec, self._impl, inputs.device.index)
-        if key not in self._plans:
-            if self._layers is None:
-                self._layers = self._pack(inputs.device)
-            p = engine.Plan(inputs.device, prec, self._impl)
-            pair = p.f32(B, 3, 2, H, W)
-            out = self._build(p, self._layers, pair, B, H, W)
-            self._plans[key] = (p, pair, out)
-        p, pair, out = self._plans[key]
+        p, pair, out = self.plan_for(B, H, W, inputs.device)
         pair.copy_(inputs)
         if self.use_cuda_graph and p.graph is None and not torch.cuda.is_current_stream_capturing():
             p.capture()

@@ -148,17 +148,27 @@ class DeconvResnet(nn.Module):
         p.conv(L["head"], cur, None, out_f32=out, name="heatmap")
         return p, src, out
 
+    def plan_for(self, B, H, W, device):
+        """(plan, static fp32 NCHW input [B,3,H,W], static fp32 NCHW heat-maps) for this batch shape; built once and
+        cached.  tracking/pipeline.py captures several plans into one CUDA graph through this."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("DeconvResnet.forward needs a CUDA tensor: this package has no CPU path")
+        if H % 32 or W % 32:
+            raise ValueError("expected [B,3,H,W] with H, W multiples of 32, got %s" % ((B, 3, H, W),))
+        prec = _lib.PREC_FAST if self.precision == "fast" else _lib.PREC_SPLIT
+        key = (B, H, W, prec, self._impl, device.index if device.index is not None else torch.cuda.current_device())
+        if key not in self._plans:
+            self._plans[key] = self._build_plan(B, H, W, device, prec, self._impl)
+        return self._plans[key]
+
     def _plan(self, x):
         if not x.is_cuda:
             raise RuntimeError("DeconvResnet.forward needs a CUDA tensor: this package has no CPU path")
         B, C, H, W = x.shape
-        if C != 3 or H % 32 or W % 32:
+        if C != 3:
             raise ValueError("expected [B,3,H,W] with H, W multiples of 32, got %s" % (tuple(x.shape),))
-        prec = _lib.PREC_FAST if self.precision == "fast" else _lib.PREC_SPLIT
-        key = (B, H, W, prec, self._impl, x.device.index)
-        if key not in self._plans:
-            self._plans[key] = self._build_plan(B, H, W, x.device, prec, self._impl)
-        return self._plans[key]
+        return self.plan_for(B, H, W, x.device)
 
     @torch.no_grad()
     def forward(self, x):

@@ -1,0 +1,152 @@
+"""The joint per-frame-pair step (the intended `process_frame` of tools/tracking/demo.py:35-42, minus detection):
+
+    flow      = flow_net(pair)                      FlowNet2-family forward          (net_utils.flow_est, :73-92)
+    boxes     = box_propagation(prev_kps, flow)     flow look-up at the key-points   (flow_utils.py:7-35)
+    heatmaps  = pose_net(crops)                     PoseResNet forward               (net_utils.pose_est, :36-71)
+    keypoints = final_preds(heatmaps, centers, scales, adjust_coords=True)           (evaluation.py:22-35)
+
+for a batch of `pairs` frame pairs with `people` person crops each, as ONE CUDA graph: the flow net and the pose
+net are captured on two forked streams (they are independent until the box propagation), the decode and the
+propagation kernels join them.  All buffers are static, so a step is: copy inputs in, replay, copy results out.
+
+Multi-GPU: frame pairs are independent, so each rank owns a shard of pairs and runs this
+pipeline on it; `gather_keypoints` is the single collective of the path -- one NCCL all-gather of the per-person
+key-point records (and boxes) at the end of a batch.  `shard_pairs` is the partition rule (also used by the gloo
+CPU tests)."""
+import torch
+
+from .. import _lib, engine
+from . import flow_utils, net_utils
+
+
+def shard_pairs(num_pairs, rank, world):
+    """Contiguous block partition of pair indices: rank r gets [lo, hi).  Sizes differ by at most one."""
+    base, rem = divmod(num_pairs, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_keypoints(local, group=None):
+    """All-gather equally sized per-rank record tensors [n_local, ...] -> [world*n_local, ...] (rank-major).
+    Works on CUDA tensors over NCCL and on CPU tensors over gloo."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    else:
+        dist.all_gather(list(out.chunk(world)), local.contiguous(), group=group)
+    return out
+
+
+class FramePairPipeline:
+    def __init__(self, pose_net, flow_net, pairs, people, frame_hw=(384, 512), crop_hw=(256, 192), device="cuda", use_cuda_graph=True,
+                 concurrent=True):
+        self.pose_net, self.flow_net = pose_net, flow_net
+        self.pairs, self.people, self.n = pairs, people, pairs * people
+        self.device = torch.device(device)
+        self.frame_hw, self.crop_hw = frame_hw, crop_hw
+        self.num_joints = pose_net.num_classes
+        dev = self.device
+        self.pose_plan, self.crops, self.heatmaps = pose_net.plan_for(self.n, crop_hw[0], crop_hw[1], dev)
+        self.flow_plan, self.pair, self.flow = flow_net.plan_for(pairs, frame_hw[0], frame_hw[1], dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.centers, self.scales = torch.zeros(self.n, 2, **f32), torch.ones(self.n, **f32)
+        self.prev_kps = torch.zeros(self.n, self.num_joints, 3, **f32)
+        self.frame_of = torch.arange(self.n, dtype=torch.int32, device=dev) // people      # person i belongs to pair i // people
+        self.keypoints = torch.zeros(self.n, self.num_joints, 3, **f32)
+        self.boxes = torch.zeros(self.n, 4, **f32)
+        self.use_cuda_graph, self.concurrent = use_cuda_graph, concurrent
+        self.graph, self.launches_per_step = None, 0
+        self._side = torch.cuda.Stream(device=dev)
+        # pinned staging for the host-facing call
+        pin = dict(dtype=torch.float32, pin_memory=True)
+        self._h_pair, self._h_crops = torch.empty(self.pair.shape, **pin), torch.empty(self.crops.shape, **pin)
+        self._h_meta = torch.empty(self.n * (2 + 1 + self.num_joints * 3), **pin)
+        self._d_meta = torch.empty(self._h_meta.shape, **f32)
+        self._h_out = torch.empty(self.n * (self.num_joints * 3 + 4), **pin)
+        self._d_out = torch.empty(self._h_out.shape, **f32)
+
+    # ---- device-side step ------------------------------------------------------------------------------
+    def _enqueue(self):
+        main = torch.cuda.current_stream()
+        if self.concurrent:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self.flow_plan.enqueue()
+        else:
+            self.flow_plan.enqueue()
+        self.pose_plan.enqueue()
+        net_utils.final_preds_cuda(self.heatmaps, self.centers, self.scales, True, out=self.keypoints)
+        if self.concurrent:
+            main.wait_stream(self._side)
+        flow_utils.box_propagation_cuda(self.prev_kps, self.flow, self.frame_of, out=self.boxes)
+
+    def capture(self):
+        with torch.cuda.device(self.device):
+            self._enqueue()                      # warm-up: function attributes, code upload
+            torch.cuda.synchronize()
+            _lib.reset_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self.launches_per_step = _lib.launch_count()
+            self.graph = g
+        return self
+
+    @torch.no_grad()
+    def step_device(self):
+        """One batch with inputs already resident in the static device buffers (self.pair, self.crops, self.centers,
+        self.scales, self.prev_kps).  Results land in self.keypoints / self.boxes / self.flow.  No host sync."""
+        if self.use_cuda_graph:
+            if self.graph is None:
+                self.capture()
+            self.graph.replay()
+        else:
+            if not self.launches_per_step:
+                _lib.reset_launch_count()
+                self._enqueue()
+                self.launches_per_step = _lib.launch_count()
+            else:
+                self._enqueue()
+
+    # ---- host-facing step --------------------------------------------------------------------------------
+    @property
+    def h2d_bytes(self):
+        return 4 * (self._h_pair.numel() + self._h_crops.numel() + self._h_meta.numel())
+
+    @property
+    def d2h_bytes(self):
+        return 4 * self._h_out.numel()
+
+    @torch.no_grad()
+    def process(self, pairs, crops, centers, scales, prev_keypoints):
+        """Host tensors in, host tensors out: pairs [pairs,3,2,H,W] (RGB 0..255), crops [pairs*people,3,h,w], centers
+        [n,2], scales [n], prev_keypoints [n,K,3] (all fp32) -> (keypoints [n,K,3], boxes [n,4]) CPU tensors."""
+        n, K = self.n, self.num_joints
+        self._h_pair.copy_(pairs)
+        self._h_crops.copy_(crops)
+        m = self._h_meta
+        m[:2 * n].copy_(torch.as_tensor(centers, dtype=torch.float32).reshape(-1))
+        m[2 * n:3 * n].copy_(torch.as_tensor(scales, dtype=torch.float32).reshape(-1))
+        m[3 * n:].copy_(torch.as_tensor(prev_keypoints, dtype=torch.float32).reshape(-1))
+        return self.process_staged()
+
+    @torch.no_grad()
+    def process_staged(self):
+        """The timed part of process(): pinned host staging buffers -> device, one step, results -> pinned host."""
+        n, K = self.n, self.num_joints
+        self.pair.copy_(self._h_pair, non_blocking=True)
+        self.crops.copy_(self._h_crops, non_blocking=True)
+        self._d_meta.copy_(self._h_meta, non_blocking=True)
+        self.centers.copy_(self._d_meta[:2 * n].view(n, 2))
+        self.scales.copy_(self._d_meta[2 * n:3 * n])
+        self.prev_kps.copy_(self._d_meta[3 * n:].view(n, K, 3))
+        self.step_device()
+        self._d_out[:n * K * 3].copy_(self.keypoints.view(-1))
+        self._d_out[n * K * 3:].copy_(self.boxes.view(-1))
+        self._h_out.copy_(self._d_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._h_out[:n * K * 3].view(n, K, 3), self._h_out[n * K * 3:].view(n, 4)
