@@ -1,37 +1,51 @@
 // ft_conv.cu -- fused convolution / k4s2p1 transposed convolution as an implicit GEMM on the
-// Blackwell tensor cores (tcgen05.mma, accumulators in TMEM), sm_100a only.
+// Blackwell tensor cores (tcgen05.mma, accumulators in TMEM, operands fed by TMA), sm_100a only.
 //
-//   out[m, co] = act( (sum_k A[m,k] * Wt[co,k]) * scale[co] + shift[co] (+ res[m,co]) )
-//     m  = output pixel (batch folded in: n*Qh*Qw + qy*Qw + qx; 128 rows per tile, tiles may straddle
-//          image rows / images so the 8x6 maps of layer4 fill tiles as well as the 64x48 ones)
-//     k  = tap * Cin_p + ci   (implicit im2col: the A tile is gathered on the fly, never materialised)
+//   out[m, co] = act( (sum_k A[m,k] * Wt[co,k]) * scale[co] + shift[co] )        (residual: see below)
+//     m  = output pixel.  A tile is 128 pixels = a box of bw x bh x bn (columns x rows x images) of the
+//          output grid, bw*bh*bn = 128, chosen per layer so the 8x6 maps of layer4 fill tiles as well as
+//          the 64x48 ones.
+//     k  = (tap, 64-channel block): implicit im2col -- for every tap the A tile is ONE TMA box load of
+//          the NHWC activation tensor at the tap's offset; image borders (padding) and channel tails are
+//          zero-filled by the TMA unit, so no thread ever computes an address.
+//          Stride-2 convolutions read through four "parity views" of the input (tensor maps whose pixel
+//          strides are doubled), transposed convolutions write through four parity views of the output.
+//   residual (bottleneck conv3): folded into the GEMM as extra k-blocks  acc += R[m, 64-block] * I*f,
+//          R read through the same TMA pipeline as A, so the epilogue never waits on a global load
+//          (host side folds BatchNorm's scale into the weights for these layers; engine.py).
 //
-// CTA = 9 warps, persistent over output tiles (static round-robin):
-//   warps 0-3  epilogue : tcgen05.ld the 128 x BN fp32 accumulator (lane = pixel row), scale/shift
-//                         (folded BN or bias), residual, ReLU/LeakyReLU, re-split to fp16 hi/lo, store NHWC
-//                         (or fp32 NCHW for network outputs).  Double-buffered TMEM accumulator, so the
-//                         epilogue of tile i overlaps the main loop of tile i+1.
-//   warps 4-7  producers: gather the A tile (128 pixels x 64 k) with 16-byte cp.async into the
-//                         128B-swizzled K-major smem image tcgen05 expects; out-of-image taps and the
-//                         M/K tails are zero-filled by cp.async's src-size operand.  One of them also
-//                         issues the bulk copy (cp.async.bulk -> UBLKCP) of the pre-swizzled weight tile.
-//   warp 8     MMA      : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) four
+// CTA = 6 warps (10 for the gather variant), persistent over output tiles (static round-robin):
+//   warps 0-3  epilogue : tcgen05.ld the 128 x BN fp32 accumulator (lane = pixel row) in slabs of 16/32/64
+//                         columns, scale/shift (folded BN or bias), ReLU/LeakyReLU, re-split to fp16 hi/lo,
+//                         st.shared into a swizzled staging slab, then ONE TMA store per plane writes the slab
+//                         to the NHWC output (coalesced, clipped at tensor edges).  Double-buffered TMEM
+//                         accumulator and double-buffered staging: the epilogue of tile i overlaps the main
+//                         loop of tile i+1.  (fp32 NCHW network outputs are written straight from registers.)
+//   warp 4     MMA      : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) four
 //                         times per 64-wide k-block -- three times that in split mode:
 //                         acc += A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  (fp16 hi/lo pairs carry 22 significant
 //                         bits, which is what the 1e-3 heat-map parity gate needs).
-//   mbarriers: full[s] (producers + weight bytes -> MMA), empty[s] (tcgen05.commit -> producers),
+//   warp 5     TMA      : one thread: per k-block one cp.async.bulk.tensor.4d per activation plane plus one
+//                         cp.async.bulk of the pre-swizzled weight tile, all completing on the stage's mbarrier.
+//   warps 6-9  gather   : only in the GATHER variant (Cin < 64: the 7x7 / 3x3 stems, where a 64-channel box per
+//                         tap would be mostly padding): im2col by 16-byte cp.async with K packed across taps.
+//   mbarriers: full[s] (TMA bytes -> MMA), empty[s] (tcgen05.commit -> producer),
 //              acc_full[a] (tcgen05.commit -> epilogue), acc_empty[a] (epilogue -> MMA).
 //
 // The SIMT kernel at the bottom computes the same thing with fp32 FMAs on the same data formats; it is
 // the on-GPU cross-check used by the tests (FT_IMPL_SIMT), not a fallback: ft_conv2d_fprop never
 // switches implementation on its own.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "ft_common.cuh"
 
 namespace ft {
 
-struct ConvK {
+struct alignas(64) ConvK {
+    CUtensorMap in_map[4][2];    // [input parity view][hi, lo]   (stride 1: only view 0)
+    CUtensorMap out_map[4][2];   // [output phase][hi, lo]        (plain conv: only phase 0)
+    CUtensorMap res_map[2];      // residual as an A-operand source
     const __half* in_hi;
     const __half* in_lo;
     __half* out_hi;
@@ -43,20 +57,19 @@ struct ConvK {
     const float* w_gemm;
     const float* scale;
     const float* shift;
-    int N, H, W, in_ld, in_coff, cin_p, cpt;
+    int N, H, W, in_ld, in_coff, cin_p, cin_k, cpt;
     int Qh, Qw, Ho, Wo, out_ld, out_coff, cout, cout_p8, cout_pad;
     int res_ld, res_coff;
     int in_stride, out_mul;
-    int n_phase, taps, k_blocks, k_pad;
+    int n_phase, taps, cb, kb_main, kb_total, k_pad;
     int M, m_tiles, n_tiles, num_tiles;
+    int bw, bh, bn, lg_bw, lg_bh, tiles_w, tiles_h;
     int act;
     float slope;
     int8_t tap_dy[4][64];
     int8_t tap_dx[4][64];
     int8_t ph_oy[4];
     int8_t ph_ox[4];
-    uint32_t desc_hi;   // upper 32 bits of the smem matrix descriptor (SBO | version | layout); FT_DBG_DESC overrides
-    uint32_t desc_lbo;  // leading-byte-offset field
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -108,6 +121,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+// TMA: 4-D box of a tiled tensor map -> shared memory (zero fill outside the tensor), completes on an mbarrier
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+// TMA: shared memory -> 4-D box of a tiled tensor map (clipped at the tensor edges), bulk-group completion
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -127,10 +159,9 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
 // K-major operand tile, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |
 //   [32,46) stride byte offset >> 4 | [46,48) version = 1 on sm_100 | [61,64) layout (2 = SWIZZLE_128B)
-constexpr uint32_t DESC_HI_DEFAULT = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-constexpr uint32_t DESC_LBO_DEFAULT = 1;
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr, uint32_t hi, uint32_t lbo) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)lbo << 16) | ((uint64_t)hi << 32);
+constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)DESC_HI << 32);
 }
 // kind::f16 instruction descriptor: D fp32, A/B fp16, K-major both, N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t f16_idesc(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
@@ -156,38 +187,56 @@ __host__ __device__ constexpr uint32_t f16_idesc(int m, int n) { return (1u << 4
 constexpr int BM = 128;              // pixels per tile (UMMA M)
 constexpr int BK = 64;               // fp16 per k-block = one 128-byte swizzle row
 constexpr int A_TILE = BM * BK * 2;  // 16 KiB
-constexpr int NUM_THREADS = 288;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int EPI_THREADS = 128;
+constexpr int SMEM_LIMIT = 232448;   // 227 KiB opt-in maximum per CTA
 
 template <int BN, bool SPLIT>
 struct Geo {
+    static constexpr int PLANES = SPLIT ? 2 : 1;
     static constexpr int B_TILE = BN * BK * 2;
-    static constexpr int STAGE = (SPLIT ? 2 : 1) * (A_TILE + B_TILE);
-    static constexpr int STAGES = (SMEM_BUDGET / STAGE) > 8 ? 8 : (SMEM_BUDGET / STAGE);
-    static constexpr int LAG = STAGES >= 3 ? 2 : 1;       // cp.async groups a producer keeps in flight
+    static constexpr int STAGE = PLANES * (A_TILE + B_TILE);
+    // epilogue staging slab: SLAB output channels x 128 pixels x 2 planes, double buffered
+    static constexpr int SLAB = (!SPLIT && BN >= 64) ? 64 : (BN >= 32 ? 32 : 16);
+    static constexpr int SLAB_PLANE = BM * SLAB * 2;
+    static constexpr int STAGING = 2 * 2 * SLAB_PLANE;
+    static constexpr int FIXED = 1024 /*align slack*/ + 512 /*barriers*/ + STAGING;
+    static constexpr int STAGES_FIT = (SMEM_LIMIT - FIXED) / STAGE;
+    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+    static constexpr int LAG = STAGES >= 3 ? 2 : 1;       // gather variant: cp.async groups a producer keeps in flight
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM = STAGES * STAGE + FIXED;
     static_assert(STAGES >= 2, "tile too large for shared memory");
 };
 
 struct TileCoord {
     int phase, mt, nt;
+    int qx0, qy0, n0;    // TMA variant: origin of the pixel box
 };
+template <bool GATHER>
 __device__ __forceinline__ TileCoord tile_coord(const ConvK& p, int tile) {
     TileCoord t;
     t.nt = tile % p.n_tiles;               // consecutive CTAs share the A tile (L2 reuse), differ in weights
     const int r = tile / p.n_tiles;
     t.mt = r % p.m_tiles;
     t.phase = r / p.m_tiles;
+    if (GATHER) {
+        t.qx0 = t.mt * BM, t.qy0 = 0, t.n0 = 0;   // linear pixel index; the output map is [C, M]
+    } else {
+        const int tw = t.mt % p.tiles_w, r2 = t.mt / p.tiles_w;
+        t.qx0 = tw * p.bw;
+        t.qy0 = (r2 % p.tiles_h) * p.bh;
+        t.n0 = (r2 / p.tiles_h) * p.bn;
+    }
     return t;
 }
 
-template <int BN, bool SPLIT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvK p) {
+template <int BN, bool SPLIT, bool GATHER>
+__global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const __grid_constant__ ConvK p) {
     using G = Geo<BN, SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + G::STAGES * G::STAGE;
+    const uint32_t staging = smem_base + G::STAGES * G::STAGE;         // 1024-aligned (STAGE is a multiple of 1024)
+    const uint32_t bar_base = staging + G::STAGING;
     // barrier slots (8 bytes each): full[STAGES] | empty[STAGES] | acc_full[2] | acc_empty[2] | tmem ptr
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (G::STAGES + s); };
@@ -199,16 +248,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < G::STAGES; ++s) {
-            mbar_init(full_bar(s), 128 + 1);   // 128 producer arrivals + 1 arrive.expect_tx for the weight bytes
-            mbar_init(empty_bar(s), 1);        // one tcgen05.commit
+            mbar_init(full_bar(s), GATHER ? 128 + 1 : 1);   // (128 gather arrivals +) 1 arrive.expect_tx for the TMA bytes
+            mbar_init(empty_bar(s), 1);                     // one tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(accf_bar(a), 1);
-            mbar_init(acce_bar(a), 128);
+            mbar_init(acce_bar(a), EPI_THREADS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)G::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -218,72 +267,108 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp >= 4 && warp < 8) {
-        // =========================== A / weight producers ===========================
-        const int ptid = threadIdx.x - 128;
-        const int j = ptid & 7;             // 16-byte chunk (8 channels) inside the 64-wide k-block
-        const int r0 = ptid >> 3;           // rows r0 + 16*i
-        const uint32_t row_off = (uint32_t)r0 * 128u + (uint32_t)((j ^ (r0 & 7)) << 4);   // 128B swizzle: chunk ^= row%8
-        int it = 0;                         // k-block iterations issued (across tiles)
-        int arrived = 0;                    // iterations whose full-barrier arrival has been made
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const TileCoord tc = tile_coord(p, tile);
-            int pix[8], iy0[8], ix0[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = tc.mt * BM + r0 + 16 * i;
-                if (m < p.M) {
-                    const int qx = m % p.Qw, t2 = m / p.Qw;
-                    const int qy = t2 % p.Qh, n = t2 / p.Qh;
-                    iy0[i] = qy * p.in_stride;
-                    ix0[i] = qx * p.in_stride;
-                    pix[i] = (n * p.H + iy0[i]) * p.W + ix0[i];
-                } else {
-                    iy0[i] = -(1 << 20);    // fails every bounds test -> zero fill
-                    ix0[i] = 0;
-                    pix[i] = 0;
-                }
-            }
-            const uint8_t* wsrc = p.w_tile + ((size_t)(tc.phase * p.n_tiles + tc.nt) * p.k_blocks) * (size_t)(2 * G::B_TILE);
-            for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
-                const int s = it % G::STAGES;
-                mbar_wait(empty_bar(s), ((it / G::STAGES) & 1) ^ 1);
-                const uint32_t stage = smem_base + s * G::STAGE;
-                if (ptid == 0) {
-                    constexpr uint32_t wbytes = (SPLIT ? 2 : 1) * G::B_TILE;
-                    mbar_arrive_expect_tx(full_bar(s), wbytes);
-                    bulk_g2s(stage + (SPLIT ? 2 : 1) * A_TILE, wsrc + (size_t)kb * (2 * G::B_TILE), wbytes, full_bar(s));
-                }
-                const int g = kb * 8 + j;            // global 8-channel chunk index along K
-                const int tap = g / p.cpt;
-                const int c8 = g - tap * p.cpt;
-                const bool tap_ok = tap < p.taps;
-                const int dy = tap_ok ? p.tap_dy[tc.phase][tap] : 0;
-                const int dx = tap_ok ? p.tap_dx[tc.phase][tap] : 0;
-                const int doff = dy * p.W + dx;
-                const int coff = p.in_coff + c8 * 8;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int iy = iy0[i] + dy, ix = ix0[i] + dx;
-                    const bool ok = tap_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                    const size_t off = ok ? ((size_t)(pix[i] + doff) * p.in_ld + coff) : 0;
-                    const uint32_t dst = stage + row_off + (uint32_t)i * (16u * 128u);
-                    cp_async16(dst, p.in_hi + off, ok ? 16u : 0u);
-                    if (SPLIT) cp_async16(dst + A_TILE, p.in_lo + off, ok ? 16u : 0u);
-                }
-                cp_async_commit();
-                if (it - arrived >= G::LAG) {
-                    cp_async_wait<G::LAG>();
-                    fence_proxy_async();
-                    mbar_arrive(full_bar(arrived % G::STAGES));
-                    ++arrived;
+    if (warp == 5) {
+        // =========================== TMA producer ===========================
+        if (!GATHER && lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord<false>(p, tile);
+                const uint8_t* wsrc = p.w_tile + ((size_t)(tc.phase * p.n_tiles + tc.nt) * p.kb_total) * (size_t)(2 * G::B_TILE);
+                int tap = 0, cblk = 0;
+                for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
+                    const int s = it % G::STAGES;
+                    mbar_wait(empty_bar(s), ((it / G::STAGES) & 1) ^ 1);
+                    const uint32_t stage = smem_base + s * G::STAGE;
+                    mbar_arrive_expect_tx(full_bar(s), (uint32_t)G::STAGE);
+                    if (kb < p.kb_main) {
+                        const int dy = p.tap_dy[tc.phase][tap], dx = p.tap_dx[tc.phase][tap];
+                        int view = 0, cx = tc.qx0 + dx, cy = tc.qy0 + dy;
+                        if (p.in_stride == 2) {      // input pixel 2q+d lives in parity view (d&1) at index q + (d - (d&1))/2
+                            const int py = dy & 1, px = dx & 1;
+                            view = py * 2 + px;
+                            cx = tc.qx0 + ((dx - px) >> 1);
+                            cy = tc.qy0 + ((dy - py) >> 1);
+                        }
+                        tma_load_4d(stage, &p.in_map[view][0], full_bar(s), cblk * BK, cx, cy, tc.n0);
+                        if (SPLIT) tma_load_4d(stage + A_TILE, &p.in_map[view][1], full_bar(s), cblk * BK, cx, cy, tc.n0);
+                        if (++cblk == p.cb) cblk = 0, ++tap;
+                    } else {                          // residual k-block: 64 channels of the residual tensor at the output pixels
+                        const int c0 = tc.nt * BN + (kb - p.kb_main) * BK;
+                        tma_load_4d(stage, &p.res_map[0], full_bar(s), c0, tc.qx0, tc.qy0, tc.n0);
+                        if (SPLIT) tma_load_4d(stage + A_TILE, &p.res_map[1], full_bar(s), c0, tc.qx0, tc.qy0, tc.n0);
+                    }
+                    bulk_g2s(stage + G::PLANES * A_TILE, wsrc + (size_t)kb * (2 * G::B_TILE), G::PLANES * G::B_TILE, full_bar(s));
                 }
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (; arrived < it; ++arrived) mbar_arrive(full_bar(arrived % G::STAGES));
-    } else if (warp == 8) {
+    } else if (warp >= 6) {
+        // =========================== gather producers (GATHER variant only) ===========================
+        if (GATHER) {
+            const int ptid = threadIdx.x - 192;
+            const int j = ptid & 7;             // 16-byte chunk (8 channels) inside the 64-wide k-block
+            const int r0 = ptid >> 3;           // rows r0 + 16*i
+            const uint32_t row_off = (uint32_t)r0 * 128u + (uint32_t)((j ^ (r0 & 7)) << 4);   // 128B swizzle: chunk ^= row%8
+            int it = 0;                         // k-block iterations issued (across tiles)
+            int arrived = 0;                    // iterations whose full-barrier arrival has been made
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord<true>(p, tile);
+                int pix[8], iy0[8], ix0[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int m = tc.mt * BM + r0 + 16 * i;
+                    if (m < p.M) {
+                        const int qx = m % p.Qw, t2 = m / p.Qw;
+                        const int qy = t2 % p.Qh, n = t2 / p.Qh;
+                        iy0[i] = qy * p.in_stride;
+                        ix0[i] = qx * p.in_stride;
+                        pix[i] = (n * p.H + iy0[i]) * p.W + ix0[i];
+                    } else {
+                        iy0[i] = -(1 << 20);    // fails every bounds test -> zero fill
+                        ix0[i] = 0;
+                        pix[i] = 0;
+                    }
+                }
+                const uint8_t* wsrc = p.w_tile + ((size_t)(tc.phase * p.n_tiles + tc.nt) * p.kb_total) * (size_t)(2 * G::B_TILE);
+                for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
+                    const int s = it % G::STAGES;
+                    mbar_wait(empty_bar(s), ((it / G::STAGES) & 1) ^ 1);
+                    const uint32_t stage = smem_base + s * G::STAGE;
+                    if (ptid == 0) {
+                        constexpr uint32_t wbytes = G::PLANES * G::B_TILE;
+                        mbar_arrive_expect_tx(full_bar(s), wbytes);
+                        bulk_g2s(stage + G::PLANES * A_TILE, wsrc + (size_t)kb * (2 * G::B_TILE), wbytes, full_bar(s));
+                    }
+                    const int g = kb * 8 + j;            // global 8-channel chunk index along K (K packed across taps)
+                    const int tap = g / p.cpt;
+                    const int c8 = g - tap * p.cpt;
+                    const bool tap_ok = tap < p.taps;
+                    const int dy = tap_ok ? p.tap_dy[tc.phase][tap] : 0;
+                    const int dx = tap_ok ? p.tap_dx[tc.phase][tap] : 0;
+                    const int doff = dy * p.W + dx;
+                    const int coff = p.in_coff + c8 * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int iy = iy0[i] + dy, ix = ix0[i] + dx;
+                        const bool ok = tap_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                        const size_t off = ok ? ((size_t)(pix[i] + doff) * p.in_ld + coff) : 0;
+                        const uint32_t dst = stage + row_off + (uint32_t)i * (16u * 128u);
+                        cp_async16(dst, p.in_hi + off, ok ? 16u : 0u);
+                        if (SPLIT) cp_async16(dst + A_TILE, p.in_lo + off, ok ? 16u : 0u);
+                    }
+                    cp_async_commit();
+                    if (it - arrived >= G::LAG) {
+                        cp_async_wait<G::LAG>();
+                        fence_proxy_async();
+                        mbar_arrive(full_bar(arrived % G::STAGES));
+                        ++arrived;
+                    }
+                }
+            }
+            cp_async_wait<0>();
+            fence_proxy_async();
+            for (; arrived < it; ++arrived) mbar_arrive(full_bar(arrived % G::STAGES));
+        }
+    } else if (warp == 4) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             constexpr uint32_t idesc = f16_idesc(BM, BN);
@@ -293,20 +378,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 mbar_wait(acce_bar(a), ((local >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
-                for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+                for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
                     const int s = it % G::STAGES;
                     mbar_wait(full_bar(s), (it / G::STAGES) & 1);
                     tc_fence_after();
                     const uint32_t a_hi = smem_base + s * G::STAGE;
-                    const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * A_TILE;
+                    const uint32_t b_hi = a_hi + G::PLANES * A_TILE;
+                    const bool main_block = kb < p.kb_main;     // residual blocks multiply by (identity * f): the W_lo term is zero
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = sw128_desc(a_hi + k * 32, p.desc_hi, p.desc_lbo), db = sw128_desc(b_hi + k * 32, p.desc_hi, p.desc_lbo);
+                        const uint64_t da = sw128_desc(a_hi + k * 32), db = sw128_desc(b_hi + k * 32);
                         tc_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
                         if (SPLIT) {
-                            const uint64_t dal = sw128_desc(a_hi + A_TILE + k * 32, p.desc_hi, p.desc_lbo), dbl = sw128_desc(b_hi + G::B_TILE + k * 32, p.desc_hi, p.desc_lbo);
+                            const uint64_t dal = sw128_desc(a_hi + A_TILE + k * 32);
                             tc_mma_f16(d_tmem, dal, db, idesc, 1);
-                            tc_mma_f16(d_tmem, da, dbl, idesc, 1);
+                            if (main_block) {
+                                const uint64_t dbl = sw128_desc(b_hi + G::B_TILE + k * 32);
+                                tc_mma_f16(d_tmem, da, dbl, idesc, 1);
+                            }
                         }
                     }
                     tc_commit(empty_bar(s));          // smem slot reusable once these MMAs retire
@@ -315,46 +404,60 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             }
         }
     } else {
-        // =========================== epilogue ===========================
-        constexpr int CW = BN >= 32 ? 32 : 16;
-        int local = 0;
+        // =========================== epilogue (warps 0-3) ===========================
+        constexpr int SLAB = G::SLAB;
+        constexpr int RB = SLAB * 2;                  // bytes per staged row per plane: 32 / 64 / 128 = the TMA swizzle span
+        constexpr uint32_t SW_MASK = RB / 16 - 1;
+        const bool leader = threadIdx.x == 0;
+        const int row = warp * 32 + lane;
+        int local = 0, store_ctr = 0;                 // store_ctr: staging slabs stored so far (selects the buffer)
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
-            const TileCoord tc = tile_coord(p, tile);
+            const TileCoord tc = tile_coord<GATHER>(p, tile);
             const int a = local & 1;
-            const int row = warp * 32 + lane;
-            const int m = tc.mt * BM + row;
-            const bool valid = m < p.M;
-            size_t opix = 0;
-            int n = 0, oy = 0, ox = 0;
-            if (valid) {
+            bool valid;
+            int n, oy, ox;
+            if (GATHER) {
+                const int m = tc.mt * BM + row;
+                valid = m < p.M;
                 const int qx = m % p.Qw, t2 = m / p.Qw;
-                const int qy = t2 % p.Qh;
-                n = t2 / p.Qh;
+                n = t2 / p.Qh, oy = t2 % p.Qh, ox = qx;
+            } else {
+                const int qx = tc.qx0 + (row & (p.bw - 1)), qy = tc.qy0 + ((row >> p.lg_bw) & (p.bh - 1));
+                n = tc.n0 + (row >> (p.lg_bw + p.lg_bh));
+                valid = qx < p.Qw && qy < p.Qh && n < p.N;
                 oy = qy * p.out_mul + p.ph_oy[tc.phase];
                 ox = qx * p.out_mul + p.ph_ox[tc.phase];
-                opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
             }
             mbar_wait(accf_bar(a), (local >> 1) & 1);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN);
 #pragma unroll 1
-            for (int cc = 0; cc < BN / CW; ++cc) {
-                uint32_t v[CW];
-                if (CW == 32) {
-                    TMEM_LD_32(t_row + cc * CW, v);
+            for (int cc = 0; cc < BN / SLAB; ++cc) {
+                const int cbase = tc.nt * BN + cc * SLAB;
+                uint32_t v[SLAB];
+                if constexpr (SLAB == 64) {
+                    TMEM_LD_32(t_row + cc * SLAB, v);
+                    TMEM_LD_32(t_row + cc * SLAB + 32, (v + 32));
+                } else if constexpr (SLAB == 32) {
+                    TMEM_LD_32(t_row + cc * SLAB, v);
                 } else {
-                    TMEM_LD_16(t_row + cc * CW, v);
+                    TMEM_LD_16(t_row + cc * SLAB, v);
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cc == BN / CW - 1) {
+                if (cc == BN / SLAB - 1) {
                     // every column of this accumulator stage is now in registers: hand TMEM back to the MMA warp
                     tc_fence_before();
                     mbar_arrive(acce_bar(a));
                 }
-                if (!valid) continue;
-                const int cbase = tc.nt * BN + cc * CW;
+                if (cbase >= p.cout_p8) continue;    // whole slab is channel padding (uniform across the CTA)
+                const uint32_t buf = staging + (uint32_t)(store_ctr & 1) * (2 * G::SLAB_PLANE);
+                // the TMA store that last read this staging buffer (two slabs ago) must have drained it
+                if (p.out_hi) {
+                    if (leader) bulk_wait_read<1>();
+                    named_bar_sync(1, EPI_THREADS);
+                }
 #pragma unroll
-                for (int g8 = 0; g8 < CW / 8; ++g8) {
+                for (int g8 = 0; g8 < SLAB / 8; ++g8) {
                     const int c0 = cbase + g8 * 8;
                     if (c0 >= p.cout_p8) break;
                     float o[8];
@@ -363,26 +466,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
                     const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) o[k] = fmaf(__uint_as_float(v[g8 * 8 + k]), scv[k], shv[k]);
-                    if (p.res_hi) {
-                        const size_t roff = opix * p.res_ld + p.res_coff + c0;
-                        const Half8 rh = *reinterpret_cast<const Half8*>(p.res_hi + roff);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float2 f = __half22float2(rh.v[k]);
-                            o[2 * k] += f.x, o[2 * k + 1] += f.y;
-                        }
-                        if (p.res_lo) {
-                            const Half8 rl = *reinterpret_cast<const Half8*>(p.res_lo + roff);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float2 f = __half22float2(rl.v[k]);
-                                o[2 * k] += f.x, o[2 * k + 1] += f.y;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) o[k] = apply_act(o[k], p.act, p.slope);
+                    for (int k = 0; k < 8; ++k) o[k] = apply_act(fmaf(__uint_as_float(v[g8 * 8 + k]), scv[k], shv[k]), p.act, p.slope);
                     if (p.out_hi) {
                         Half8 hi, lo;
 #pragma unroll
@@ -393,22 +477,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             hi.v[k] = __halves2half2(h0, h1);
                             lo.v[k] = __halves2half2(l0, l1);
                         }
-                        const size_t ooff = opix * p.out_ld + p.out_coff + c0;
-                        *reinterpret_cast<Half8*>(p.out_hi + ooff) = hi;
-                        if (p.out_lo) *reinterpret_cast<Half8*>(p.out_lo + ooff) = lo;
+                        uint32_t off = (uint32_t)row * RB + (uint32_t)g8 * 16u;
+                        off ^= ((off >> 7) & SW_MASK) << 4;
+                        const uint4 hv = *reinterpret_cast<const uint4*>(&hi), lv = *reinterpret_cast<const uint4*>(&lo);
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + off), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w) : "memory");
+                        if (p.out_lo)
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + G::SLAB_PLANE + off), "r"(lv.x), "r"(lv.y), "r"(lv.z), "r"(lv.w) : "memory");
                     }
-                    if (p.out_f32) {
+                    if (p.out_f32 && valid) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
                             if (c0 + k < p.cout) p.out_f32[(((size_t)n * p.cout + c0 + k) * p.Ho + oy) * p.Wo + ox] = o[k];
                     }
                 }
+                if (p.out_hi) {
+                    fence_proxy_async();              // generic-proxy smem writes -> visible to the TMA (async proxy)
+                    named_bar_sync(1, EPI_THREADS);
+                    if (leader) {
+                        tma_store_4d(&p.out_map[tc.phase][0], buf, cc * SLAB + tc.nt * BN, tc.qx0, tc.qy0, tc.n0);
+                        if (p.out_lo) tma_store_4d(&p.out_map[tc.phase][1], buf + G::SLAB_PLANE, cc * SLAB + tc.nt * BN, tc.qx0, tc.qy0, tc.n0);
+                        bulk_commit();
+                    }
+                    ++store_ctr;
+                }
             }
         }
+        if (leader) bulk_wait_all();                  // every output byte has left shared memory and is globally visible
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 4) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G::TMEM_COLS) : "memory");
     }
@@ -431,7 +529,7 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvK p) {
             const int iy = qy * p.in_stride + p.tap_dy[ph][t], ix = qx * p.in_stride + p.tap_dx[ph][t];
             if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
             const size_t off = ((size_t)(n * p.H + iy) * p.W + ix) * p.in_ld + p.in_coff;
-            const float* wt = wp + (size_t)t * p.cin_p * p.cout_pad;
+            const float* wt = wp + (size_t)t * p.cin_k * p.cout_pad;
             for (int ci = 0; ci < p.cin_p; ++ci) {
                 float a = __half2float(p.in_hi[off + ci]);
                 if (p.in_lo) a += __half2float(p.in_lo[off + ci]);
@@ -456,21 +554,21 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvK p) {
     }
 }
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool GATHER>
 static int launch_tc(const ConvK& k, cudaStream_t s) {
     using G = Geo<BN, SPLIT>;
-    static bool attr_set = false;   // per (BN,SPLIT) instantiation
+    static bool attr_set = false;   // per instantiation
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         if (e != cudaSuccess) {
-            set_error("conv_tc_kernel<%d,%d>: cannot opt in to %d B of shared memory: %s", BN, (int)SPLIT, G::SMEM, cudaGetErrorString(e));
+            set_error("conv_tc_kernel<%d,%d,%d>: cannot opt in to %d B of shared memory: %s", BN, (int)SPLIT, (int)GATHER, G::SMEM, cudaGetErrorString(e));
             return 1;
         }
         attr_set = true;
     }
-    int sms = 148;
+    const int sms = 148;
     const int grid = k.num_tiles < sms ? k.num_tiles : sms;
-    conv_tc_kernel<BN, SPLIT><<<grid, NUM_THREADS, G::SMEM, s>>>(k);
+    conv_tc_kernel<BN, SPLIT, GATHER><<<grid, GATHER ? 320 : 192, G::SMEM, s>>>(k);
     return check_launch("conv_tc_kernel");
 }
 
@@ -480,6 +578,54 @@ static int check_view(const ft_act& a, const char* name) {
     FT_REQUIRE(((uintptr_t)a.hi & 15) == 0 && ((uintptr_t)a.lo & 15) == 0, "%s: planes must be 16-byte aligned", name);
     FT_REQUIRE(a.n > 0 && a.h > 0 && a.w > 0, "%s: empty tensor", name);
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor maps (driver entry point resolved through the runtime: no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// fp16 tensor [d3][d2][d1][d0] with d0 contiguous; `stride` in ELEMENTS for d1..d3; box in elements.
+static int make_map(CUtensorMap* m, const void* base, const long long dim[4], const long long stride[3], const int box[4], int swizzle_bytes, const char* what) {
+    EncodeTiledFn enc = encode_fn();
+    FT_REQUIRE(enc, "conv2d: cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t gd[4], gs[3];
+    cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 4; ++i) gd[i] = (cuuint64_t)dim[i], bx[i] = (cuuint32_t)box[i];
+    for (int i = 0; i < 3; ++i) gs[i] = (cuuint64_t)stride[i] * 2;
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FT_REQUIRE(r == CUDA_SUCCESS, "conv2d: cuTensorMapEncodeTiled(%s) failed with %d (dims %lld,%lld,%lld,%lld strides %lld,%lld,%lld box %d,%d,%d,%d)", what, (int)r,
+               dim[0], dim[1], dim[2], dim[3], stride[0], stride[1], stride[2], box[0], box[1], box[2], box[3]);
+    return 0;
+}
+
+// Pixel box of a tile: bw*bh*bn = 128, powers of two, fewest tiles (least padding); ties prefer long rows.
+static void choose_box(int Qw, int Qh, int N, int& bw, int& bh, int& bn) {
+    long long best = -1;
+    for (int lw = 7; lw >= 0; --lw)
+        for (int lh = 7 - lw; lh >= 0; --lh) {
+            const int w = 1 << lw, h = 1 << lh, n = 128 / (w * h);
+            const long long tiles = (long long)ceil_div(Qw, w) * ceil_div(Qh, h) * ceil_div(N, n);
+            if (best < 0 || tiles < best) best = tiles, bw = w, bh = h, bn = n;
+        }
+}
+
+static int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
 }
 
 }  // namespace ft
@@ -495,10 +641,12 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     FT_REQUIRE(d->cout > 0 && d->cout_pad >= d->cout && d->cout_pad % 8 == 0, "conv2d: bad cout/cout_pad (%d/%d)", d->cout, d->cout_pad);
     FT_REQUIRE(d->precision == FT_PREC_SPLIT || d->precision == FT_PREC_FAST, "conv2d: bad precision %d", d->precision);
     FT_REQUIRE(d->precision == FT_PREC_FAST || d->in.lo, "conv2d: split precision needs the input lo plane");
+    FT_REQUIRE(d->k_mode == FT_K_PACKED || d->k_mode == FT_K_TAP64, "conv2d: bad k_mode %d", d->k_mode);
+    const bool split = d->precision == FT_PREC_SPLIT;
 
     ConvK k = {};
     k.in_hi = (const __half*)d->in.hi;
-    k.in_lo = d->precision == FT_PREC_SPLIT ? (const __half*)d->in.lo : nullptr;
+    k.in_lo = split ? (const __half*)d->in.lo : nullptr;
     k.N = d->in.n, k.H = d->in.h, k.W = d->in.w;
     k.in_ld = d->in.ld, k.in_coff = d->in.coff, k.cin_p = d->in.c, k.cpt = d->in.c / 8;
     if (d->kind == FT_CONV) {
@@ -530,9 +678,12 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
         FT_REQUIRE(false, "conv2d: unknown kind %d", d->kind);
     }
     FT_REQUIRE(k.Ho > 0 && k.Wo > 0, "conv2d: empty output");
+    // K layout: FT_K_PACKED k = tap*cin_p + ci ; FT_K_TAP64 k = tap*cin_k + ci with cin_k = cin_p rounded up to 64
+    k.cin_k = d->k_mode == FT_K_TAP64 ? round_up(k.cin_p, BK) : k.cin_p;
+    k.cb = k.cin_k / BK;
     k.k_pad = d->k_pad;
-    FT_REQUIRE(k.k_pad % BK == 0 && k.k_pad >= k.taps * k.cin_p && k.k_pad < k.taps * k.cin_p + BK, "conv2d: k_pad %d does not match taps*cin_p = %d", k.k_pad, k.taps * k.cin_p);
-    k.k_blocks = k.k_pad / BK;
+    FT_REQUIRE(k.k_pad == round_up(k.taps * k.cin_k, BK), "conv2d: k_pad %d does not match taps*cin_k = %d (k_mode %d)", k.k_pad, k.taps * k.cin_k, d->k_mode);
+    k.kb_main = k.k_pad / BK;
     k.cout = d->cout, k.cout_p8 = round_up(d->cout, 8), k.cout_pad = d->cout_pad;
     k.scale = d->scale, k.shift = d->shift, k.act = d->act, k.slope = d->slope;
     k.w_tile = (const uint8_t*)d->w_tile, k.w_gemm = d->w_gemm;
@@ -546,7 +697,8 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     if (d->res.hi) {
         if (int e = check_view(d->res, "conv2d.res")) return e;
         FT_REQUIRE(d->res.n == k.N && d->res.h == k.Ho && d->res.w == k.Wo && d->res.c >= k.cout_p8, "conv2d: residual shape mismatch");
-        k.res_hi = (const __half*)d->res.hi, k.res_lo = (const __half*)d->res.lo, k.res_ld = d->res.ld, k.res_coff = d->res.coff;
+        k.res_hi = (const __half*)d->res.hi, k.res_lo = split ? (const __half*)d->res.lo : nullptr, k.res_ld = d->res.ld, k.res_coff = d->res.coff;
+        FT_REQUIRE(!split || d->res.lo, "conv2d: split precision needs the residual lo plane");
     }
     const long long M = (long long)k.N * k.Qh * k.Qw;
     FT_REQUIRE(M * 4 < (1ll << 31) && (long long)k.N * k.H * k.W < (1ll << 31), "conv2d: tensor too large for 32-bit pixel indices");
@@ -563,30 +715,78 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     }
     FT_REQUIRE(d->impl == FT_IMPL_TCGEN05, "conv2d: unknown impl %d", d->impl);
     FT_REQUIRE(d->w_tile && ((uintptr_t)d->w_tile & 15) == 0, "conv2d: tcgen05 implementation needs a 16-byte aligned w_tile");
-    FT_REQUIRE(d->cout_pad % d->block_n == 0, "conv2d: cout_pad %d is not a multiple of block_n %d", d->cout_pad, d->block_n);
-    k.m_tiles = ceil_div(k.M, BM);
-    k.n_tiles = d->cout_pad / d->block_n;
-    k.num_tiles = k.n_phase * k.m_tiles * k.n_tiles;
-    k.desc_hi = DESC_HI_DEFAULT, k.desc_lbo = DESC_LBO_DEFAULT;
-    if (const char* dbg = getenv("FT_DBG_DESC")) {   // bring-up knob: "sbo16,version,layout,lbo16"
-        unsigned sbo = 64, ver = 1, lay = 2, lbo = 1;
-        sscanf(dbg, "%u,%u,%u,%u", &sbo, &ver, &lay, &lbo);
-        k.desc_hi = (sbo & 0x3FFF) | ((ver & 3) << 14) | ((lay & 7) << 29);
-        k.desc_lbo = lbo & 0x3FFF;
+    const int BN = d->block_n;
+    FT_REQUIRE(BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256, "conv2d: block_n must be 16, 32, 64, 128 or 256 (got %d)", BN);
+    FT_REQUIRE(d->cout_pad % BN == 0, "conv2d: cout_pad %d is not a multiple of block_n %d", d->cout_pad, BN);
+    k.n_tiles = d->cout_pad / BN;
+    const bool gather = d->k_mode == FT_K_PACKED;
+    const int res_blocks = d->res.hi ? ceil_div(BN, BK) : 0;
+    FT_REQUIRE(d->res_blocks == res_blocks, "conv2d: the weight image carries %d residual k-blocks per tile, this call needs %d (residual %s, block_n %d)",
+               d->res_blocks, res_blocks, d->res.hi ? "given" : "absent", BN);
+    k.kb_total = k.kb_main + res_blocks;
+    const int slab = (!split && BN >= 64) ? 64 : (BN >= 32 ? 32 : 16);
+
+    if (gather) {
+        FT_REQUIRE(d->kind == FT_CONV && !d->res.hi, "conv2d: FT_K_PACKED (gather variant) supports plain convolutions without residual only");
+        k.m_tiles = ceil_div(k.M, BM);
+        if (k.out_hi) {   // output as a [M, C] matrix: a tile is 128 consecutive pixels
+            const long long dim[4] = {k.cout_p8, k.M, 1, 1}, str[3] = {k.out_ld, (long long)k.out_ld * k.M, (long long)k.out_ld * k.M};
+            const int box[4] = {slab, BM, 1, 1};
+            if (int e = make_map(&k.out_map[0][0], k.out_hi + k.out_coff, dim, str, box, slab * 2, "out.hi")) return e;
+            if (k.out_lo)
+                if (int e = make_map(&k.out_map[0][1], k.out_lo + k.out_coff, dim, str, box, slab * 2, "out.lo")) return e;
+        }
+    } else {
+        FT_REQUIRE(k.in_stride == 1 || k.in_stride == 2, "conv2d: the TMA variant supports stride 1 and 2 (got %d)", k.in_stride);
+        choose_box(k.Qw, k.Qh, k.N, k.bw, k.bh, k.bn);
+        k.lg_bw = ilog2(k.bw), k.lg_bh = ilog2(k.bh);
+        k.tiles_w = ceil_div(k.Qw, k.bw), k.tiles_h = ceil_div(k.Qh, k.bh);
+        k.m_tiles = k.tiles_w * k.tiles_h * ceil_div(k.N, k.bn);
+        const int abox[4] = {BK, k.bw, k.bh, k.bn};
+        const int st = k.in_stride;
+        for (int view = 0; view < st * st; ++view) {
+            const int py = view / st, px = view % st;
+            if (px >= k.W || py >= k.H) continue;
+            const long long dim[4] = {k.cin_p, (k.W - px + st - 1) / st, (k.H - py + st - 1) / st, k.N};
+            const long long str[3] = {(long long)st * k.in_ld, (long long)st * k.W * k.in_ld, (long long)k.H * k.W * k.in_ld};
+            const size_t off = (size_t)(py * k.W + px) * k.in_ld + k.in_coff;
+            if (int e = make_map(&k.in_map[view][0], k.in_hi + off, dim, str, abox, 128, "in.hi")) return e;
+            if (split)
+                if (int e = make_map(&k.in_map[view][1], k.in_lo + off, dim, str, abox, 128, "in.lo")) return e;
+        }
+        if (k.out_hi) {
+            const int mul = k.out_mul;
+            const int obox[4] = {slab, k.bw, k.bh, k.bn};
+            for (int ph = 0; ph < k.n_phase; ++ph) {
+                const long long dim[4] = {k.cout_p8, k.Qw, k.Qh, k.N};
+                const long long str[3] = {(long long)mul * k.out_ld, (long long)mul * k.Wo * k.out_ld, (long long)k.Ho * k.Wo * k.out_ld};
+                const size_t off = (size_t)(k.ph_oy[ph] * k.Wo + k.ph_ox[ph]) * k.out_ld + k.out_coff;
+                if (int e = make_map(&k.out_map[ph][0], k.out_hi + off, dim, str, obox, slab * 2, "out.hi")) return e;
+                if (k.out_lo)
+                    if (int e = make_map(&k.out_map[ph][1], k.out_lo + off, dim, str, obox, slab * 2, "out.lo")) return e;
+            }
+        }
+        if (d->res.hi) {
+            const long long dim[4] = {k.cout_p8, k.Wo, k.Ho, k.N};
+            const long long str[3] = {k.res_ld, (long long)k.Wo * k.res_ld, (long long)k.Ho * k.Wo * k.res_ld};
+            if (int e = make_map(&k.res_map[0], k.res_hi + k.res_coff, dim, str, abox, 128, "res.hi")) return e;
+            if (split)
+                if (int e = make_map(&k.res_map[1], k.res_lo + k.res_coff, dim, str, abox, 128, "res.lo")) return e;
+        }
     }
-    const bool split = d->precision == FT_PREC_SPLIT;
-    switch (d->block_n) {
-#define FT_CASE(BN_)                                                       \
-    case BN_:                                                              \
-        return split ? launch_tc<BN_, true>(k, s) : launch_tc<BN_, false>(k, s);
+    k.num_tiles = k.n_phase * k.m_tiles * k.n_tiles;
+
+#define FT_CASE(BN_)                                                                                             \
+    case BN_:                                                                                                    \
+        if (gather) return split ? launch_tc<BN_, true, true>(k, s) : launch_tc<BN_, false, true>(k, s);         \
+        return split ? launch_tc<BN_, true, false>(k, s) : launch_tc<BN_, false, false>(k, s);
+    switch (BN) {
         FT_CASE(16)
         FT_CASE(32)
         FT_CASE(64)
         FT_CASE(128)
         FT_CASE(256)
-#undef FT_CASE
-        default:
-            FT_REQUIRE(false, "conv2d: block_n must be 16, 32, 64, 128 or 256 (got %d)", d->block_n);
     }
+#undef FT_CASE
     return 0;
 }

@@ -35,41 +35,45 @@ def fold_bn(bn):
     return s.float().cpu().numpy(), t.float().cpu().numpy()
 
 
-def gemm_weights_conv(weight, cin_p):
-    """Conv2d weight [Cout,Cin,kh,kw] -> [1, k_pad, Cout] with k = (r*kw+s)*cin_p + ci."""
+def gemm_weights_conv(weight, cin_k):
+    """Conv2d weight [Cout,Cin,kh,kw] -> [1, k_pad, Cout] with k = (r*kw+s)*cin_k + ci  (cin_k >= Cin: the per-tap
+    channel count of the K layout -- the padded view width for FT_K_PACKED, that rounded up to 64 for FT_K_TAP64)."""
     w = weight.detach().float().cpu().numpy()
     cout, cin, kh, kw = w.shape
-    k = kh * kw * cin_p
+    k = kh * kw * cin_k
     g = np.zeros((1, round_up(k, BK), cout), np.float32)
-    g[0, :k].reshape(kh * kw, cin_p, cout)[:, :cin] = w.transpose(2, 3, 1, 0).reshape(kh * kw, cin, cout)
+    g[0, :k].reshape(kh * kw, cin_k, cout)[:, :cin] = w.transpose(2, 3, 1, 0).reshape(kh * kw, cin, cout)
     return g
 
 
-def gemm_weights_deconv(weight, cin_p):
+def gemm_weights_deconv(weight, cin_k):
     """ConvTranspose2d(k4,s2,p1) weight [Cin,Cout,4,4] -> [4, k_pad, Cout].
     out[oy] += in[iy]*w[ky] with oy = 2*iy - 1 + ky, so output parity py only sees ky = 1 - py + 2a (a=0,1), read at
-    iy = qy + py - a.  phase = py*2+px, k = (a*2+b)*cin_p + ci  (matches the tap table in ft_conv2d_fprop)."""
+    iy = qy + py - a.  phase = py*2+px, k = (a*2+b)*cin_k + ci  (matches the tap table in ft_conv2d_fprop)."""
     w = weight.detach().float().cpu().numpy()
     cin, cout = w.shape[:2]
     assert w.shape[2:] == (4, 4)
-    k = 4 * cin_p
+    k = 4 * cin_k
     g = np.zeros((4, round_up(k, BK), cout), np.float32)
     for py in range(2):
         for px in range(2):
-            v = g[py * 2 + px, :k].reshape(4, cin_p, cout)
+            v = g[py * 2 + px, :k].reshape(4, cin_k, cout)
             for a in range(2):
                 for b in range(2):
                     v[a * 2 + b, :cin] = w[:, :, 1 - py + 2 * a, 1 - px + 2 * b]
     return g
 
 
-def normalise_columns(g, scale):
-    """Scale every output channel by a power of two so max|w| lands in [1024, 2048): keeps the fp16 `lo`
-    halves out of the subnormal range.  Exact (powers of two), undone through `scale`."""
+def normalise_columns(g, scale, max_exp=None):
+    """Scale every output channel by a power of two f so max|w| lands in [1024, 2048): keeps the fp16 `lo`
+    halves out of the subnormal range.  Exact (powers of two), undone through `scale`.  Returns (g*f, scale/f, f).
+    `max_exp` caps log2 f (residual layers put f itself into fp16 identity blocks)."""
     m = np.abs(g).max(axis=(0, 1))
     e = np.where(m > 0, 10 - np.floor(np.log2(np.maximum(m, 1e-38))), 0.0)
+    if max_exp is not None:
+        e = np.minimum(e, max_exp)
     f = np.exp2(e).astype(np.float32)
-    return g * f[None, None, :], (scale / f).astype(np.float32)
+    return g * f[None, None, :], (scale / f).astype(np.float32), f
 
 
 def choose_block_n(cout, precision=_lib.PREC_SPLIT):
@@ -82,11 +86,24 @@ def choose_block_n(cout, precision=_lib.PREC_SPLIT):
     return 16
 
 
-def tile_weights(g, block_n):
+def tile_weights(g, block_n, res_f=None):
     """[P, k_pad, cout_pad] fp32 -> uint8 image: for each (phase, n_tile, k_block) a [2 (hi,lo)][block_n][64]
-    fp16 block in the tcgen05 K-major SWIZZLE_128B layout: 16-byte chunk j of row r sits at chunk j ^ (r % 8)."""
+    fp16 block in the tcgen05 K-major SWIZZLE_128B layout: 16-byte chunk j of row r sits at chunk j ^ (r % 8).
+    `res_f` (per-channel powers of two) appends ceil(block_n/64) residual k-blocks to every (phase, n_tile): block j is
+    diag(res_f) restricted to channels [64j, 64j+64) of the tile, so the kernel's  acc += residual_tile @ block^T
+    adds residual*f to the accumulator (flowtrack_b200.h, ft_conv_desc.res_blocks)."""
     P, kp, cp = g.shape
     assert kp % BK == 0 and cp % block_n == 0
+    if res_f is not None:
+        nres, nt = -(-block_n // BK), cp // block_n
+        ext = np.zeros((P, nt, kp + nres * BK, block_n), np.float32)       # per n-tile K extension
+        ext[:, :, :kp] = g.reshape(P, kp, nt, block_n).transpose(0, 2, 1, 3)
+        fr = np.asarray(res_f, np.float32).reshape(nt, block_n)
+        assert np.all(np.abs(fr) <= 32768.0)
+        for r in range(block_n):
+            ext[:, :, kp + r, r] = fr[None, :, r]                          # k = kp + (64j + kk) <-> channel r = 64j + kk
+        g = ext.transpose(0, 2, 1, 3).reshape(P, kp + nres * BK, cp)
+        kp = kp + nres * BK
     hi = g.astype(np.float16)
     lo = (g - hi.astype(np.float32)).astype(np.float16)
     t = np.stack((hi, lo), 0)                                              # [2, P, k, c]
@@ -150,7 +167,8 @@ def stream_ptr():
 class ConvLayer:
     """conv / deconv(k4,s2,p1) + per-channel scale/shift + optional residual + activation, weights resident on the GPU."""
 
-    def __init__(self, kind, weight, scale, shift, stride=1, pad=0, act=_lib.ACT_NONE, slope=0.1, cin_p=None, device=None, block_n=None, keep_host=False):
+    def __init__(self, kind, weight, scale, shift, stride=1, pad=0, act=_lib.ACT_NONE, slope=0.1, cin_p=None, device=None, block_n=None, keep_host=False,
+                 residual=False):
         if kind == _lib.KIND_CONV:
             self.cout, cin, self.kh, self.kw = weight.shape
         else:
@@ -158,20 +176,32 @@ class ConvLayer:
         self.kind, self.stride, self.pad, self.act, self.slope = kind, stride, pad, act, slope
         self.cin, self.cin_p = cin, cin_p or pad8(cin)
         assert self.cin_p % 8 == 0 and self.cin_p >= cin
-        g = gemm_weights_conv(weight, self.cin_p) if kind == _lib.KIND_CONV else gemm_weights_deconv(weight, self.cin_p)
+        # K layout: small-Cin plain convolutions (the stems) pack K across taps and are gathered by cp.async;
+        # everything else gives each tap a whole number of 64-channel blocks so a k-block is one TMA box.
+        packed = kind == _lib.KIND_CONV and not residual and (self.cin_p < 32 or stride not in (1, 2))
+        self.k_mode = _lib.K_PACKED if packed else _lib.K_TAP64
+        self.cin_k = self.cin_p if self.k_mode == _lib.K_PACKED else round_up(self.cin_p, BK)
+        self.residual = residual
+        g = gemm_weights_conv(weight, self.cin_k) if kind == _lib.KIND_CONV else gemm_weights_deconv(weight, self.cin_k)
         self.block_n = block_n or choose_block_n(self.cout)
         self.cout_pad = round_up(self.cout, self.block_n)
         self.k_pad = g.shape[1]
+        self.res_blocks = -(-self.block_n // BK) if residual else 0
         gp = np.zeros((g.shape[0], self.k_pad, self.cout_pad), np.float32)
         sc = np.zeros(self.cout_pad, np.float32)
         sh = np.zeros(self.cout_pad, np.float32)
         gp[:, :, :self.cout], sc[:self.cout], sh[:self.cout] = g, scale, shift
-        gp, sc = normalise_columns(gp, sc)
+        if residual:
+            # out = (acc + res*f) / f + shift needs 1/scale == f, a power of two: fold BatchNorm's scale into the weights
+            gp = (gp.astype(np.float64) * sc.astype(np.float64)[None, None, :]).astype(np.float32)
+            sc = np.where(np.arange(self.cout_pad) < self.cout, 1.0, 0.0).astype(np.float32)
+        gp, sc, f = normalise_columns(gp, sc, max_exp=14 if residual else None)
+        res_f = np.where(sc != 0, f, 0.0) if residual else None
         self.host = dict(w_gemm=gp, scale=sc, shift=sh) if keep_host else None
-        self.w_tile_host = tile_weights(gp, self.block_n) if keep_host else None
+        self.w_tile_host = tile_weights(gp, self.block_n, res_f) if keep_host else None
         if device is not None:
             self.w_gemm = torch.from_numpy(gp).to(device)
-            self.w_tile = torch.from_numpy(self.w_tile_host if keep_host else tile_weights(gp, self.block_n)).to(device)
+            self.w_tile = torch.from_numpy(self.w_tile_host if keep_host else tile_weights(gp, self.block_n, res_f)).to(device)
             self.scale, self.shift = torch.from_numpy(sc).to(device), torch.from_numpy(sh).to(device)
 
     def out_hw(self, h, w):
@@ -188,6 +218,7 @@ class ConvLayer:
 
     def desc(self, x, out=None, out_f32=None, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05):
         assert x.c == self.cin_p, "input view has %d channels, layer expects %d" % (x.c, self.cin_p)
+        assert (res is not None) == self.residual, "layer was packed %s residual blocks" % ("with" if self.residual else "without")
         d = FtConvDesc()
         d.in_ = x.struct()
         d.out = out.struct() if out is not None else NULL_ACT
@@ -198,11 +229,13 @@ class ConvLayer:
         d.kind, d.kh, d.kw, d.stride, d.pad = self.kind, self.kh, self.kw, self.stride, self.pad
         d.cout, d.cout_pad, d.k_pad, d.block_n = self.cout, self.cout_pad, self.k_pad, self.block_n
         d.act, d.slope, d.precision, d.impl = self.act, self.slope, precision, impl
+        d.k_mode, d.res_blocks = self.k_mode, self.res_blocks
         return d
 
 
-def conv_from_modules(conv, bn=None, act=_lib.ACT_NONE, cin_p=None, device=None, keep_host=False):
-    """nn.Conv2d / nn.ConvTranspose2d (+ eval BatchNorm2d) -> ConvLayer."""
+def conv_from_modules(conv, bn=None, act=_lib.ACT_NONE, cin_p=None, device=None, keep_host=False, residual=False):
+    """nn.Conv2d / nn.ConvTranspose2d (+ eval BatchNorm2d) -> ConvLayer.  `residual`: the layer will be called with a
+    residual tensor (bottleneck conv3); its weight image then carries the identity k-blocks the kernel needs."""
     is_deconv = isinstance(conv, torch.nn.ConvTranspose2d)
     cout = conv.out_channels
     if bn is not None:
@@ -214,11 +247,12 @@ def conv_from_modules(conv, bn=None, act=_lib.ACT_NONE, cin_p=None, device=None,
         shift = conv.bias.detach().float().cpu().numpy() if conv.bias is not None else np.zeros(cout, np.float32)
     if is_deconv:
         assert conv.kernel_size == (4, 4) and conv.stride == (2, 2) and conv.padding == (1, 1) and conv.output_padding == (0, 0)
+        assert not residual
         return ConvLayer(_lib.KIND_DECONV, conv.weight, scale, shift, act=act, cin_p=cin_p, device=device, keep_host=keep_host)
     assert conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
     assert conv.dilation == (1, 1) and conv.groups == 1
     return ConvLayer(_lib.KIND_CONV, conv.weight, scale, shift, stride=conv.stride[0], pad=conv.padding[0], act=act,
-                     cin_p=cin_p, device=device, keep_host=keep_host)
+                     cin_p=cin_p, device=device, keep_host=keep_host, residual=residual)
 
 
 # --------------------------------------------------------------------------------------------------

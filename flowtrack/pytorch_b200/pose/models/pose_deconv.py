@@ -109,12 +109,13 @@ class DeconvResnet(nn.Module):
     # ---- packing ------------------------------------------------------------------------------------
     def _pack(self, device, keep_host=False):
         R, N = _lib.ACT_RELU, _lib.ACT_NONE
-        mk = lambda conv, bn, act, cin_p=None: engine.conv_from_modules(conv, bn, act, cin_p=cin_p, device=device, keep_host=keep_host)
+        mk = lambda conv, bn, act, cin_p=None, residual=False: engine.conv_from_modules(conv, bn, act, cin_p=cin_p, device=device, keep_host=keep_host,
+                                                                                        residual=residual)
         L = {"stem": mk(self.conv1, self.bn1, R, 8), "blocks": []}
         for li in range(1, 5):
             for blk in getattr(self, "layer%d" % li):
                 L["blocks"].append(dict(
-                    c1=mk(blk.conv1, blk.bn1, R), c2=mk(blk.conv2, blk.bn2, R), c3=mk(blk.conv3, blk.bn3, R),  # ReLU after the residual add
+                    c1=mk(blk.conv1, blk.bn1, R), c2=mk(blk.conv2, blk.bn2, R), c3=mk(blk.conv3, blk.bn3, R, residual=True),  # residual add, then ReLU
                     down=mk(blk.downsample[0], blk.downsample[1], N) if len(blk.downsample) else None))
         L["deconv"] = [mk(self.deconv[3 * i], self.deconv[3 * i + 1], R) for i in range(3)]
         L["head"] = mk(self.heatmap, None, N)

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 1
+#define FT_ABI_VERSION 2
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -60,6 +60,9 @@ enum { FT_ACT_NONE = 0, FT_ACT_RELU = 1, FT_ACT_LEAKY = 2 };
 enum { FT_CONV = 0, FT_DECONV_K4S2P1 = 1 };
 enum { FT_PREC_SPLIT = 0,  /* 3 tcgen05 MMAs per tile (hi*hi + lo*hi + hi*lo): fp32-grade results  */
        FT_PREC_FAST  = 1   /* 1 MMA on the hi planes only: fp16-operand results                    */ };
+enum { FT_K_PACKED = 0,    /* k = tap*in.c + ci, k_pad = round_up(taps*in.c, 64): im2col gathered by cp.async;
+                              for the small-Cin stems (a 64-channel TMA box per tap would be mostly padding)   */
+       FT_K_TAP64  = 1     /* k = tap*cin_k + ci with cin_k = round_up(in.c, 64): one TMA box per (tap, 64 ch)  */ };
 enum { FT_IMPL_TCGEN05 = 0,  /* tcgen05/TMEM implicit GEMM (the product path)                      */
        FT_IMPL_SIMT    = 1   /* fp32 CUDA-core kernel, same data formats (bring-up / cross-check)  */ };
 
@@ -68,7 +71,8 @@ enum { FT_IMPL_TCGEN05 = 0,  /* tcgen05/TMEM implicit GEMM (the product path)   
  *   w_gemm : fp32 [n_phase][k_pad][cout_pad], k = tap * in.c + ci  (taps row-major over the kernel
  *            window; for FT_DECONV_K4S2P1 the 4 output-parity phases each see a 2x2 tap subset);
  *   w_tile : the same matrix as tcgen05 operand tiles: for each (phase, n_tile, k_block of 64)
- *            two [block_n][64] fp16 K-major 128B-swizzled images (hi then lo), contiguous.
+ *            two [block_n][64] fp16 K-major 128B-swizzled images (hi then lo), contiguous; after the
+ *            k_pad/64 main blocks of a (phase, n_tile) come `res_blocks` residual blocks (see below).
  * scale/shift have cout_pad entries (zeros in the padding).                                        */
 typedef struct {
     ft_act in;
@@ -89,6 +93,12 @@ typedef struct {
     float   slope;          /* LeakyReLU slope                                                     */
     int32_t precision;      /* FT_PREC_*                                                           */
     int32_t impl;           /* FT_IMPL_*                                                           */
+    int32_t k_mode;         /* FT_K_*: K layout of w_gemm / w_tile                                 */
+    int32_t res_blocks;     /* residual k-blocks appended to every (phase, n_tile) of w_tile:
+                               ceil(block_n/64) when the layer is called with a residual, else 0.
+                               Block j holds diag(f) for channels [64j, 64j+64) of the tile, where
+                               f[c] = 1/scale[c] must be a power of two (the host folds BatchNorm's
+                               scale into the weights of such layers), so acc += res * f exactly.   */
 } ft_conv_desc;
 
 int         ft_abi_version(void);

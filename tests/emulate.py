@@ -34,7 +34,7 @@ def emulate_layer(layer, x, res=None):
         for dy, dx in taps:
             ys = torch.arange(Qh) * in_stride + dy + P
             xs = torch.arange(Qw) * in_stride + dx + P
-            cols.append(xp[:, ys][:, :, xs])
+            cols.append(torch.nn.functional.pad(xp[:, ys][:, :, xs], (0, layer.cin_k - C)))   # per-tap channel padding of the K layout
         A = torch.cat(cols, dim=-1)
         out[:, oy::out_mul, ox::out_mul] = A @ wg[ph][:A.shape[-1]]
     out = out * sc + sh
@@ -48,18 +48,24 @@ def emulate_layer(layer, x, res=None):
     return out.float()
 
 
-def untile(layer):
-    """Inverse of engine.tile_weights: uint8 image -> fp32 [P, k_pad, cout_pad] (hi + lo)."""
+def untile(layer, with_residual_blocks=False):
+    """Inverse of engine.tile_weights: uint8 image -> fp32 [P, k_pad, cout_pad] (hi + lo).  With
+    `with_residual_blocks` also returns the appended residual k-blocks as [P, nt, res_blocks*64, block_n]."""
     bn = layer.block_n
     P = layer.host["w_gemm"].shape[0]
-    t = layer.w_tile_host.view(np.float16).reshape(P, layer.cout_pad // bn, layer.k_pad // 64, 2, bn, 8, 8)
+    kb = layer.k_pad // 64 + layer.res_blocks
+    t = layer.w_tile_host.view(np.float16).reshape(P, layer.cout_pad // bn, kb, 2, bn, 8, 8)
     u = np.empty_like(t)
     r = np.arange(bn)
     for j in range(8):
         u[:, :, :, :, r, j, :] = t[:, :, :, :, r, j ^ (r % 8), :]
     u = u.astype(np.float32)
     u = u[:, :, :, 0] + u[:, :, :, 1]                  # [P, nt, kb, r, j, e]
-    return u.transpose(0, 2, 4, 5, 1, 3).reshape(P, layer.k_pad, layer.cout_pad)
+    main = u[:, :, :layer.k_pad // 64].transpose(0, 2, 4, 5, 1, 3).reshape(P, layer.k_pad, layer.cout_pad)
+    if not with_residual_blocks:
+        return main
+    resb = u[:, :, layer.k_pad // 64:].transpose(0, 1, 2, 4, 5, 3).reshape(P, layer.cout_pad // bn, layer.res_blocks * 64, bn)
+    return main, resb
 
 
 def nhwc(x, cpad):

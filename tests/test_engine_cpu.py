@@ -55,16 +55,40 @@ def test_deconv_four_phase_decomposition(cin, cout, hw, bias):
 
 
 def test_tile_image_roundtrip_and_split_precision():
-    conv = nn.Conv2d(72, 130, 3, 1, 1)          # K = 9*72 = 648 -> k_pad 704; cout 130 -> block 128, cout_pad 256
+    conv = nn.Conv2d(72, 130, 3, 1, 1)          # FT_K_TAP64: 72 -> 128 channels per tap, K = 9*128 = 1152; cout 130 -> block 128, cout_pad 256
     layer = engine.conv_from_modules(conv, None, keep_host=True)
-    assert layer.block_n == 128 and layer.cout_pad == 256 and layer.k_pad == 704
+    assert layer.k_mode == _lib.K_TAP64 and layer.cin_k == 128
+    assert layer.block_n == 128 and layer.cout_pad == 256 and layer.k_pad == 1152
     wg = layer.host["w_gemm"]
     back = emulate.untile(layer)
     rel = np.abs(back - wg).max() / np.abs(wg).max()
     assert rel < 2.0 ** -21                                # hi+lo carries >= 21 significant bits
-    assert layer.w_tile_host.size == 1 * 2 * 11 * 2 * 128 * 64 * 2
+    assert layer.w_tile_host.size == 1 * 2 * 18 * 2 * 128 * 64 * 2
     m = np.abs(wg).max(axis=(0, 1))[:130]
     assert np.all((m >= 1024) & (m < 2048))               # power-of-two column normalisation
+    stem = engine.conv_from_modules(nn.Conv2d(3, 64, 7, 2, 3, bias=False), None, cin_p=8, keep_host=True)
+    assert stem.k_mode == _lib.K_PACKED and stem.cin_k == 8 and stem.k_pad == 448      # K packed across taps: 49*8 = 392 -> 448
+
+
+def test_residual_identity_blocks():
+    """A layer packed for a residual call: BatchNorm's scale is folded into the weights, 1/scale is a power of two f,
+    and every (phase, n_tile) of the tile image ends with ceil(block_n/64) k-blocks holding diag(f)."""
+    g = torch.Generator().manual_seed(3)
+    conv, bn = nn.Conv2d(64, 256, 1, bias=False), _rand_bn(256, g)
+    layer = engine.conv_from_modules(conv, bn, _lib.ACT_RELU, keep_host=True, residual=True)
+    assert layer.res_blocks == 2 and layer.block_n == 128
+    sc = layer.host["scale"]
+    f = 1.0 / sc[:256]
+    assert np.all(np.log2(f) == np.round(np.log2(f))) and np.all(f <= 2.0 ** 14)
+    main, resb = emulate.untile(layer, with_residual_blocks=True)
+    assert np.abs(main - layer.host["w_gemm"]).max() / np.abs(main).max() < 2.0 ** -21
+    for nt in range(2):
+        np.testing.assert_array_equal(resb[0, nt], np.diag(f[nt * 128:(nt + 1) * 128]))
+    x, r = torch.randn(2, 64, 8, 6, generator=g), torch.randn(2, 256, 8, 6, generator=g)
+    with torch.no_grad():
+        ref = torch.relu(bn(conv(x)) + r)
+    out = emulate.emulate_layer(layer, emulate.nhwc(x, 64), res=emulate.nhwc(r, 256)).permute(0, 3, 1, 2)
+    assert (out - ref).abs().max() < 1e-5
 
 
 def test_pose_state_dict_layout_matches_reference(golden):
@@ -106,7 +130,7 @@ def test_library_exports_every_declared_symbol():
     declared -= {"ft_act", "ft_conv_desc"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     l = _lib.lib()                                         # loads the .so and resolves every symbol
-    assert l.ft_abi_version() == 1
+    assert l.ft_abi_version() == 2
     assert l.ft_sizeof(0) == ctypes.sizeof(_lib.FtAct) == 40 and l.ft_sizeof(1) == ctypes.sizeof(_lib.FtConvDesc)
 
 

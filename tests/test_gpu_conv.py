@@ -26,6 +26,12 @@ CASES = [
     ("deconv_2048", lambda: nn.ConvTranspose2d(2048, 256, 4, 2, 1, bias=False), (2, 2048, 8, 6), _lib.ACT_RELU),
     ("deconv_flow", lambda: nn.ConvTranspose2d(386, 64, 4, 2, 1), (1, 386, 12, 16), _lib.ACT_LEAKY),
     ("deconv_2to2", lambda: nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=False), (2, 2, 6, 8), _lib.ACT_NONE),
+    # pixel boxes that span several images (8x6 and 6x8 maps), ragged in every box dimension
+    ("l4_3x3_batch", lambda: nn.Conv2d(128, 64, 3, 1, 1, bias=False), (11, 128, 8, 6), _lib.ACT_RELU),
+    ("l4_3x3_s2_batch", lambda: nn.Conv2d(64, 128, 3, 2, 1, bias=False), (5, 64, 16, 12), _lib.ACT_RELU),
+    ("deconv_batch", lambda: nn.ConvTranspose2d(64, 32, 4, 2, 1), (9, 64, 6, 8), _lib.ACT_LEAKY),
+    ("stem3x3_cin16", lambda: nn.Conv2d(11, 64, 3, 1, 1), (1, 11, 24, 32), _lib.ACT_LEAKY),                # FlowNetFusion conv0 (packed-K gather variant)
+    ("wide_map_5x5", lambda: nn.Conv2d(64, 32, 5, 1, 2), (1, 64, 20, 150), _lib.ACT_NONE),                 # box wider than tall, ragged right edge
 ]
 
 
@@ -75,7 +81,7 @@ def test_bottleneck_tail_with_bn_and_residual(prec, tol):
     x, r = torch.randn(3, 64, 16, 12, generator=g), torch.randn(3, 256, 16, 12, generator=g)
     with torch.no_grad():
         ref = torch.relu(bn(conv(x)) + r)
-    layer = engine.conv_from_modules(conv, bn, _lib.ACT_RELU, device="cuda")
+    layer = engine.conv_from_modules(conv, bn, _lib.ACT_RELU, device="cuda", residual=True)
     xa, ra = gpu_util.pack_nchw(x.cuda()), gpu_util.pack_nchw(r.cuda())
     big = engine.Act(3, 16, 12, 256 + 64, "cuda", zero=True)                        # write into channels [64, 320) of a wider buffer
     out = gpu_util.run_layer(layer, xa, res=ra, precision=prec, out=big.view(64, 256))
