@@ -43,6 +43,7 @@ SIGNATURES = {
     "ft_conv2d_fprop": (c_int, [ctypes.POINTER(FtConvDesc), c_void_p]),
     "ft_maxpool3x3s2": (c_int, [ctypes.POINTER(FtAct)] * 2 + [c_void_p]),
     "ft_pack_image": (c_int, [c_void_p] + [c_ll] * 4 + [c_int, c_float, ctypes.POINTER(FtAct), c_void_p]),
+    "ft_pack_pair_ws_floats": (c_int, [c_int]),
     "ft_pack_pair": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, ctypes.POINTER(FtAct), c_void_p]),
     "ft_upsample4x": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_float, c_int, c_void_p]),
     "ft_warp_concat": (c_int, [c_void_p, c_void_p, c_float, c_int, c_int, c_int, ctypes.POINTER(FtAct), c_void_p]),

@@ -14,20 +14,21 @@
 //          R read through the same TMA pipeline as A, so the epilogue never waits on a global load
 //          (host side folds BatchNorm's scale into the weights for these layers; engine.py).
 //
-// CTA = 6 warps (10 for the gather variant), persistent over output tiles (static round-robin):
-//   warps 0-3  epilogue : tcgen05.ld the 128 x BN fp32 accumulator (lane = pixel row) in slabs of 16/32/64
-//                         columns, scale/shift (folded BN or bias), ReLU/LeakyReLU, re-split to fp16 hi/lo,
-//                         st.shared into a swizzled staging slab, then ONE TMA store per plane writes the slab
-//                         to the NHWC output (coalesced, clipped at tensor edges).  Double-buffered TMEM
-//                         accumulator and double-buffered staging: the epilogue of tile i overlaps the main
-//                         loop of tile i+1.  (fp32 NCHW network outputs are written straight from registers.)
-//   warp 4     MMA      : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) four
+// CTA = 10 warps (14 for the gather variant), persistent over output tiles (static round-robin):
+//   warps 0-7  epilogue : two groups of four warps (one warp per TMEM lane quarter); group g takes the accumulator
+//                         slabs g, g+2, ... of 16/32/64 columns: tcgen05.ld (lane = pixel row), scale/shift
+//                         (folded BN or bias), ReLU/LeakyReLU, re-split to fp16 hi/lo, st.shared into the group's
+//                         swizzled staging slab, then ONE TMA store per plane writes the slab to the NHWC output
+//                         (coalesced, clipped at tensor edges).  The TMEM accumulator is double buffered, so the
+//                         epilogue of tile i overlaps the main loop of tile i+1.  (fp32 NCHW network outputs are
+//                         written straight from registers.)
+//   warp 8     MMA      : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) four
 //                         times per 64-wide k-block -- three times that in split mode:
 //                         acc += A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  (fp16 hi/lo pairs carry 22 significant
 //                         bits, which is what the 1e-3 heat-map parity gate needs).
-//   warp 5     TMA      : one thread: per k-block one cp.async.bulk.tensor.4d per activation plane plus one
+//   warp 9     TMA      : one thread: per k-block one cp.async.bulk.tensor.4d per activation plane plus one
 //                         cp.async.bulk of the pre-swizzled weight tile, all completing on the stage's mbarrier.
-//   warps 6-9  gather   : only in the GATHER variant (Cin < 64: the 7x7 / 3x3 stems, where a 64-channel box per
+//   warps 10-13 gather  : only in the GATHER variant (Cin < 64: the 7x7 / 3x3 stems, where a 64-channel box per
 //                         tap would be mostly padding): im2col by 16-byte cp.async with K packed across taps.
 //   mbarriers: full[s] (TMA bytes -> MMA), empty[s] (tcgen05.commit -> producer),
 //              acc_full[a] (tcgen05.commit -> epilogue), acc_empty[a] (epilogue -> MMA).
@@ -187,7 +188,10 @@ __host__ __device__ constexpr uint32_t f16_idesc(int m, int n) { return (1u << 4
 constexpr int BM = 128;              // pixels per tile (UMMA M)
 constexpr int BK = 64;               // fp16 per k-block = one 128-byte swizzle row
 constexpr int A_TILE = BM * BK * 2;  // 16 KiB
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_WARPS = 8;            // two groups of 4 warps (one per TMEM lane quarter); group g takes slabs g, g+2, ...
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int MMA_WARP = EPI_WARPS, TMA_WARP = EPI_WARPS + 1, GATHER_WARP0 = EPI_WARPS + 2;
+constexpr int THREADS_TMA = (EPI_WARPS + 2) * 32, THREADS_GATHER = (EPI_WARPS + 6) * 32;
 constexpr int SMEM_LIMIT = 232448;   // 227 KiB opt-in maximum per CTA
 
 template <int BN, bool SPLIT>
@@ -196,7 +200,7 @@ struct Geo {
     static constexpr int B_TILE = BN * BK * 2;
     static constexpr int STAGE = PLANES * (A_TILE + B_TILE);
     // epilogue staging slab: SLAB output channels x 128 pixels x 2 planes, double buffered
-    static constexpr int SLAB = (!SPLIT && BN >= 64) ? 64 : (BN >= 32 ? 32 : 16);
+    static constexpr int SLAB = BN >= 64 ? 32 : 16;
     static constexpr int SLAB_PLANE = BM * SLAB * 2;
     static constexpr int STAGING = 2 * 2 * SLAB_PLANE;
     static constexpr int FIXED = 1024 /*align slack*/ + 512 /*barriers*/ + STAGING;
@@ -231,7 +235,7 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvK& p, int tile) {
 }
 
 template <int BN, bool SPLIT, bool GATHER>
-__global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const __grid_constant__ ConvK p) {
+__global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv_tc_kernel(const __grid_constant__ ConvK p) {
     using G = Geo<BN, SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const __
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)G::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const __
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp == 5) {
+    if (warp == TMA_WARP) {
         // =========================== TMA producer ===========================
         if (!GATHER && lane == 0) {
             int it = 0;
@@ -301,10 +305,10 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const __
                 }
             }
         }
-    } else if (warp >= 6) {
+    } else if (warp >= GATHER_WARP0) {
         // =========================== gather producers (GATHER variant only) ===========================
         if (GATHER) {
-            const int ptid = threadIdx.x - 192;
+            const int ptid = threadIdx.x - GATHER_WARP0 * 32;
             const int j = ptid & 7;             // 16-byte chunk (8 channels) inside the 64-wide k-block
             const int r0 = ptid >> 3;           // rows r0 + 16*i
             const uint32_t row_off = (uint32_t)r0 * 128u + (uint32_t)((j ^ (r0 & 7)) << 4);   // 128B swizzle: chunk ^= row%8
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const __
             fence_proxy_async();
             for (; arrived < it; ++arrived) mbar_arrive(full_bar(arrived % G::STAGES));
         }
-    } else if (warp == 4) {
+    } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             constexpr uint32_t idesc = f16_idesc(BM, BN);
@@ -404,13 +408,16 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const __
             }
         }
     } else {
-        // =========================== epilogue (warps 0-3) ===========================
+        // =========================== epilogue (warps 0-7) ===========================
         constexpr int SLAB = G::SLAB;
+        constexpr int NSLAB = BN / SLAB;
         constexpr int RB = SLAB * 2;                  // bytes per staged row per plane: 32 / 64 / 128 = the TMA swizzle span
         constexpr uint32_t SW_MASK = RB / 16 - 1;
-        const bool leader = threadIdx.x == 0;
-        const int row = warp * 32 + lane;
-        int local = 0, store_ctr = 0;                 // store_ctr: staging slabs stored so far (selects the buffer)
+        const int group = warp >> 2, quarter = warp & 3;      // TMEM lanes [32*quarter, +32) are this warp's
+        const bool leader = (threadIdx.x & 127) == 0;         // issues this group's TMA stores
+        const int row = quarter * 32 + lane;
+        const uint32_t buf = staging + (uint32_t)group * (2 * G::SLAB_PLANE);   // one staging slab (hi | lo) per group
+        int local = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
             const TileCoord tc = tile_coord<GATHER>(p, tile);
             const int a = local & 1;
@@ -430,9 +437,9 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const __
             }
             mbar_wait(accf_bar(a), (local >> 1) & 1);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN);
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN);
 #pragma unroll 1
-            for (int cc = 0; cc < BN / SLAB; ++cc) {
+            for (int cc = group; cc < NSLAB; cc += 2) {
                 const int cbase = tc.nt * BN + cc * SLAB;
                 uint32_t v[SLAB];
                 if constexpr (SLAB == 64) {
@@ -444,69 +451,72 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const __
                     TMEM_LD_16(t_row + cc * SLAB, v);
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cc == BN / SLAB - 1) {
-                    // every column of this accumulator stage is now in registers: hand TMEM back to the MMA warp
+                if (cc + 2 >= NSLAB) {
+                    // this thread's last read of the accumulator stage: hand TMEM back to the MMA warp
                     tc_fence_before();
                     mbar_arrive(acce_bar(a));
                 }
-                if (cbase >= p.cout_p8) continue;    // whole slab is channel padding (uniform across the CTA)
-                const uint32_t buf = staging + (uint32_t)(store_ctr & 1) * (2 * G::SLAB_PLANE);
-                // the TMA store that last read this staging buffer (two slabs ago) must have drained it
-                if (p.out_hi) {
-                    if (leader) bulk_wait_read<1>();
-                    named_bar_sync(1, EPI_THREADS);
-                }
+                if (cbase >= p.cout_p8) continue;    // whole slab is channel padding (uniform across the group)
+                float o[SLAB];
 #pragma unroll
                 for (int g8 = 0; g8 < SLAB / 8; ++g8) {
                     const int c0 = cbase + g8 * 8;
-                    if (c0 >= p.cout_p8) break;
-                    float o[8];
-                    const float4 sc0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0)), sc1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
-                    const float4 sh0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0)), sh1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
-                    const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-                    const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+                    if (c0 < p.cout_p8) {
+                        const float4 sc0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0)), sc1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+                        const float4 sh0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0)), sh1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+                        const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                        const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) o[k] = apply_act(fmaf(__uint_as_float(v[g8 * 8 + k]), scv[k], shv[k]), p.act, p.slope);
-                    if (p.out_hi) {
-                        Half8 hi, lo;
+                        for (int k = 0; k < 8; ++k) o[g8 * 8 + k] = apply_act(fmaf(__uint_as_float(v[g8 * 8 + k]), scv[k], shv[k]), p.act, p.slope);
+                        if (p.out_f32 && valid) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            __half h0, l0, h1, l1;
-                            split_f32(o[2 * k], h0, l0);
-                            split_f32(o[2 * k + 1], h1, l1);
-                            hi.v[k] = __halves2half2(h0, h1);
-                            lo.v[k] = __halves2half2(l0, l1);
+                            for (int k = 0; k < 8; ++k)
+                                if (c0 + k < p.cout) p.out_f32[(((size_t)n * p.cout + c0 + k) * p.Ho + oy) * p.Wo + ox] = o[g8 * 8 + k];
                         }
-                        uint32_t off = (uint32_t)row * RB + (uint32_t)g8 * 16u;
-                        off ^= ((off >> 7) & SW_MASK) << 4;
-                        const uint4 hv = *reinterpret_cast<const uint4*>(&hi), lv = *reinterpret_cast<const uint4*>(&lo);
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + off), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w) : "memory");
-                        if (p.out_lo)
-                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + G::SLAB_PLANE + off), "r"(lv.x), "r"(lv.y), "r"(lv.z), "r"(lv.w) : "memory");
-                    }
-                    if (p.out_f32 && valid) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (c0 + k < p.cout) p.out_f32[(((size_t)n * p.cout + c0 + k) * p.Ho + oy) * p.Wo + ox] = o[k];
                     }
                 }
                 if (p.out_hi) {
+                    // the TMA store that last read this group's staging slab must have drained it
+                    if (leader) bulk_wait_read<0>();
+                    named_bar_sync(1 + group, 128);
+#pragma unroll
+                    for (int g8 = 0; g8 < SLAB / 8; ++g8) {
+                        if (cbase + g8 * 8 >= p.cout_p8) break;
+                        uint32_t hv[4], lv[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            __half h0, l0, h1, l1;
+                            split_f32(o[g8 * 8 + 2 * k], h0, l0);
+                            split_f32(o[g8 * 8 + 2 * k + 1], h1, l1);
+                            const __half2 h2 = __halves2half2(h0, h1), l2 = __halves2half2(l0, l1);
+                            hv[k] = *reinterpret_cast<const uint32_t*>(&h2);
+                            lv[k] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                        uint32_t off = (uint32_t)row * RB + (uint32_t)g8 * 16u;
+                        off ^= ((off >> 7) & SW_MASK) << 4;
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + off), "r"(hv[0]), "r"(hv[1]), "r"(hv[2]), "r"(hv[3]) : "memory");
+                        if (p.out_lo)
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + G::SLAB_PLANE + off), "r"(lv[0]), "r"(lv[1]), "r"(lv[2]), "r"(lv[3]) : "memory");
+                    }
                     fence_proxy_async();              // generic-proxy smem writes -> visible to the TMA (async proxy)
-                    named_bar_sync(1, EPI_THREADS);
+                    named_bar_sync(1 + group, 128);
                     if (leader) {
-                        tma_store_4d(&p.out_map[tc.phase][0], buf, cc * SLAB + tc.nt * BN, tc.qx0, tc.qy0, tc.n0);
-                        if (p.out_lo) tma_store_4d(&p.out_map[tc.phase][1], buf + G::SLAB_PLANE, cc * SLAB + tc.nt * BN, tc.qx0, tc.qy0, tc.n0);
+                        tma_store_4d(&p.out_map[tc.phase][0], buf, cbase, tc.qx0, tc.qy0, tc.n0);
+                        if (p.out_lo) tma_store_4d(&p.out_map[tc.phase][1], buf + G::SLAB_PLANE, cbase, tc.qx0, tc.qy0, tc.n0);
                         bulk_commit();
                     }
-                    ++store_ctr;
                 }
+            }
+            if (group >= NSLAB) {                     // BN = 16: a single slab, group 1 only releases the accumulator
+                tc_fence_before();
+                mbar_arrive(acce_bar(a));
             }
         }
         if (leader) bulk_wait_all();                  // every output byte has left shared memory and is globally visible
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G::TMEM_COLS) : "memory");
     }
@@ -568,7 +578,7 @@ static int launch_tc(const ConvK& k, cudaStream_t s) {
     }
     const int sms = 148;
     const int grid = k.num_tiles < sms ? k.num_tiles : sms;
-    conv_tc_kernel<BN, SPLIT, GATHER><<<grid, GATHER ? 320 : 192, G::SMEM, s>>>(k);
+    conv_tc_kernel<BN, SPLIT, GATHER><<<grid, GATHER ? THREADS_GATHER : THREADS_TMA, G::SMEM, s>>>(k);
     return check_launch("conv_tc_kernel");
 }
 
@@ -724,7 +734,7 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     FT_REQUIRE(d->res_blocks == res_blocks, "conv2d: the weight image carries %d residual k-blocks per tile, this call needs %d (residual %s, block_n %d)",
                d->res_blocks, res_blocks, d->res.hi ? "given" : "absent", BN);
     k.kb_total = k.kb_main + res_blocks;
-    const int slab = (!split && BN >= 64) ? 64 : (BN >= 32 ? 32 : 16);
+    const int slab = BN >= 64 ? 32 : 16;
 
     if (gather) {
         FT_REQUIRE(d->kind == FT_CONV && !d->res.hi, "conv2d: FT_K_PACKED (gather variant) supports plain convolutions without residual only");

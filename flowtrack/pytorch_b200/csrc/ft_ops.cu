@@ -289,11 +289,20 @@ __global__ void maxpool3x3s2_kernel(ft_act in, ft_act out) {
     }
 }
 
-__global__ void pair_mean_kernel(const float* __restrict__ pair, int HW2, float* __restrict__ mean) {
-    // one block per (b, colour): mean over both frames and all pixels (models.py:112)
+#define PAIR_MEAN_CHUNKS 64
+// mean over both frames and all pixels per (b, colour) (models.py:112), in two deterministic steps:
+// blockIdx.y-th chunk partial sums in double, then one warp per (b, colour) folds the partials.
+__global__ void pair_mean_partial_kernel(const float* __restrict__ pair, int HW2, double* __restrict__ partial) {
     const float* p = pair + (size_t)blockIdx.x * HW2;
-    double s = 0.0;
-    for (int i = threadIdx.x; i < HW2; i += blockDim.x) s += (double)p[i];
+    const int per = (HW2 + PAIR_MEAN_CHUNKS - 1) / PAIR_MEAN_CHUNKS;
+    const int lo = blockIdx.y * per, hi = min(HW2, lo + per);
+    double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = lo + threadIdx.x;
+    for (; i + 3 * (int)blockDim.x < hi; i += 4 * blockDim.x) {
+        s += (double)p[i], s1 += (double)p[i + blockDim.x], s2 += (double)p[i + 2 * blockDim.x], s3 += (double)p[i + 3 * blockDim.x];
+    }
+    for (; i < hi; i += blockDim.x) s += (double)p[i];
+    s += s1 + s2 + s3;
     __shared__ double sh[32];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
@@ -301,8 +310,14 @@ __global__ void pair_mean_kernel(const float* __restrict__ pair, int HW2, float*
     if (threadIdx.x < 32) {
         s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (threadIdx.x == 0) mean[blockIdx.x] = (float)(s / (double)HW2);
+        if (threadIdx.x == 0) partial[blockIdx.x * PAIR_MEAN_CHUNKS + blockIdx.y] = s;
     }
+}
+__global__ void pair_mean_final_kernel(const double* __restrict__ partial, int HW2, float* __restrict__ mean) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < PAIR_MEAN_CHUNKS; i += 32) s += partial[blockIdx.x * PAIR_MEAN_CHUNKS + i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) mean[blockIdx.x] = (float)(s / (double)HW2);
 }
 
 __global__ void pack_pair_kernel(const float* __restrict__ pair, const float* __restrict__ mean, int B, int H, int W,
@@ -571,6 +586,8 @@ int ft_pack_image(const float* src, long long sb, long long sc, long long sh, lo
     return check_launch("pack_image_kernel");
 }
 
+int ft_pack_pair_ws_floats(int B) { return B * 3 * (2 * PAIR_MEAN_CHUNKS + 1); }
+
 int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* mean_ws, float* x_f32, const ft_act* dst, void* stream) {
     FT_REQUIRE(pair && mean_ws && B > 0 && H > 0 && W > 0, "pack_pair: bad arguments");
     ft_act d = {};
@@ -579,9 +596,14 @@ int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* m
         FT_REQUIRE(dst->c >= 8 && dst->n == B && dst->h == H && dst->w == W, "pack_pair: dst shape mismatch");
         d = *dst;
     }
-    pair_mean_kernel<<<B * 3, 512, 0, (cudaStream_t)stream>>>(pair, 2 * H * W, mean_ws);
-    if (check_launch("pair_mean_kernel")) return 1;
-    pack_pair_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(pair, mean_ws, B, H, W, rgb_max, x_f32, d, dst != nullptr);
+    FT_REQUIRE(((uintptr_t)mean_ws & 7) == 0, "pack_pair: workspace must be 8-byte aligned");
+    double* partial = reinterpret_cast<double*>(mean_ws);
+    float* mean = mean_ws + (size_t)B * 3 * PAIR_MEAN_CHUNKS * 2;
+    pair_mean_partial_kernel<<<dim3(B * 3, PAIR_MEAN_CHUNKS), 256, 0, (cudaStream_t)stream>>>(pair, 2 * H * W, partial);
+    if (check_launch("pair_mean_partial_kernel")) return 1;
+    pair_mean_final_kernel<<<B * 3, 32, 0, (cudaStream_t)stream>>>(partial, 2 * H * W, mean);
+    if (check_launch("pair_mean_final_kernel")) return 1;
+    pack_pair_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(pair, mean, B, H, W, rgb_max, x_f32, d, dst != nullptr);
     return check_launch("pack_pair_kernel");
 }
 

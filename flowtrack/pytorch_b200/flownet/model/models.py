@@ -99,7 +99,7 @@ class _FlowBase(nn.Module):
 def _normalise(p, pair, B, H, W, want_f32, want_act):
     """models.py:112-119: x = (pair - mean_bc)/rgb_max as [B,6,H,W] fp32 and/or split-fp16 NHWC (6 -> 8 channels)."""
     lib = _lib.lib()
-    ws = p.f32(B * 3)
+    ws = p.f32(lib.ft_pack_pair_ws_floats(B))
     xf = p.f32(B, 6, H, W) if want_f32 else None
     xa = p.act(B, H, W, 6) if want_act else None
     p.call("pack_pair", lib.ft_pack_pair, pair.data_ptr(), B, H, W, p.rgb_max, ws.data_ptr(),

@@ -130,7 +130,8 @@ int ft_pack_image(const float* src, long long sb, long long sc, long long sh, lo
                   float mul, const ft_act* dst, void* stream);
 /* FlowNet2 input normalisation: pair [B,3,2,H,W] (RGB 0..255) -> x = (pair - mean_bc) / rgb_max laid
  * out as [B,6,H,W] fp32 (x_f32, optional) and as split-fp16 NHWC (dst, optional, 6 -> 8 channels).
- * `mean_ws` is a [B,3] fp32 workspace.                                                              */
+ * `mean_ws` is an 8-byte aligned workspace of ft_pack_pair_ws_floats(B) floats (partial sums + means). */
+int ft_pack_pair_ws_floats(int B);
 int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* mean_ws, float* x_f32,
                  const ft_act* dst, void* stream);
 /* src: [B,C,h,w] fp32 -> dst: [B,C,4h,4w] fp32 times `mul`.  mode 0 = bilinear (align_corners=False),
