@@ -48,6 +48,8 @@ SIGNATURES = {
     "ft_upsample4x": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_float, c_int, c_void_p]),
     "ft_warp_concat": (c_int, [c_void_p, c_void_p, c_float, c_int, c_int, c_int, ctypes.POINTER(FtAct), c_void_p]),
     "ft_fusion_concat": (c_int, [c_void_p] * 3 + [c_int] * 3 + [ctypes.POINTER(FtAct), c_void_p]),
+    "ft_flow_head": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p]),
+    "ft_flow_upsample": (c_int, [c_void_p] * 3 + [c_int] * 3 + [ctypes.POINTER(FtAct), c_void_p]),
     "ft_decode_keypoints": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "ft_box_propagation": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }

@@ -425,6 +425,70 @@ __global__ void fusion_concat_kernel(const float* __restrict__ x6, const float* 
 }
 
 // =====================================================================================================
+// Flow prediction head.  predict_flow* is a 3x3 convolution with TWO output channels on a wide concat buffer
+// (submodules.py:20-21); as an implicit GEMM its A operand would be re-read nine times for two columns of
+// output.  The path instead runs it as a 1x1 convolution with 18 outputs on the tensor cores
+//   part[n, t*2 + c, y, x] = sum_ci W[c, ci, r, s] * in[n, ci, y, x],  t = r*3 + s
+// (the input is read once) and this kernel finishes the convolution by the shifted sum
+//   flow[n, c, y, x] = bias[c] + sum_t part[n, t*2 + c, y + r - 1, x + s - 1]   (zero outside the map).
+// =====================================================================================================
+__global__ void flow_head_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ flow, int B, int H, int W) {
+    const size_t plane = (size_t)H * W;
+    const size_t total = (size_t)B * plane;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / plane, p = i % plane;
+        const int x = (int)(p % W), y = (int)(p / W);
+        float u = bias ? bias[0] : 0.f, v = bias ? bias[1] : 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int yy = y + r - 1, xx = x + s - 1;
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                const float* q = part + ((b * 18 + (r * 3 + s) * 2) * H + yy) * W + xx;
+                u += q[0];
+                v += q[plane];
+            }
+        flow[(b * 2) * plane + p] = u;
+        flow[(b * 2 + 1) * plane + p] = v;
+    }
+}
+
+// upsampled_flow*_to_*: ConvTranspose2d(2, 2, 4, 2, 1) of the fp32 flow (FlowNetS.py:41-44), written as split-fp16
+// NHWC channels [0,2) (+6 zeros) of a slice of the next level's concat buffer.  w is the module's [2(in)][2(out)][4][4].
+__global__ void flow_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ w, const float* __restrict__ bias,
+                                     int B, int h, int wd, ft_act d) {
+    __shared__ float sw[64];
+    if (threadIdx.x < 64) sw[threadIdx.x] = w[threadIdx.x];
+    __syncthreads();
+    const int Ho = 2 * h, Wo = 2 * wd;
+    const size_t total = (size_t)B * Ho * Wo;
+    const size_t plane = (size_t)h * wd;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
+        const size_t b = i / ((size_t)Wo * Ho);
+        float o[8] = {bias ? bias[0] : 0.f, bias ? bias[1] : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // oy = 2*iy - 1 + ky  ->  ky = oy + 1 - 2*iy in [0,4)
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int iy = (oy + 1) / 2 - a, ky = oy + 1 - 2 * iy;
+            if (iy < 0 || iy >= h) continue;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int ix = (ox + 1) / 2 - c, kx = ox + 1 - 2 * ix;
+                if (ix < 0 || ix >= wd) continue;
+                const float f0 = flow[(b * 2) * plane + (size_t)iy * wd + ix], f1 = flow[(b * 2 + 1) * plane + (size_t)iy * wd + ix];
+                o[0] = fmaf(f0, sw[(0 * 2 + 0) * 16 + ky * 4 + kx], o[0]);
+                o[0] = fmaf(f1, sw[(1 * 2 + 0) * 16 + ky * 4 + kx], o[0]);
+                o[1] = fmaf(f0, sw[(0 * 2 + 1) * 16 + ky * 4 + kx], o[1]);
+                o[1] = fmaf(f1, sw[(1 * 2 + 1) * 16 + ky * 4 + kx], o[1]);
+            }
+        }
+        store8(d, i, 0, o);
+    }
+}
+
+// =====================================================================================================
 // Decode (A9) and box propagation (A10)
 // =====================================================================================================
 __global__ void decode_kernel(const float* __restrict__ hm, int C, int h, int w, const float* __restrict__ center,
@@ -625,6 +689,20 @@ int ft_fusion_concat(const float* x6, const float* flow_sd, const float* flow_s2
     FT_REQUIRE(x6 && flow_sd && flow_s2 && dst->c == 16 && dst->n == B && dst->h == H && dst->w == W, "fusion_concat: bad arguments");
     fusion_concat_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x6, flow_sd, flow_s2, B, H, W, *dst);
     return check_launch("fusion_concat_kernel");
+}
+
+int ft_flow_head(const float* part, const float* bias, float* flow, int B, int H, int W, void* stream) {
+    FT_REQUIRE(part && flow && B > 0 && H > 0 && W > 0, "flow_head: bad arguments");
+    flow_head_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(part, bias, flow, B, H, W);
+    return check_launch("flow_head_kernel");
+}
+
+int ft_flow_upsample(const float* flow, const float* w, const float* bias, int B, int h, int wd, const ft_act* dst, void* stream) {
+    if (int e = check_act(dst, "flow_upsample.dst", false)) return e;
+    FT_REQUIRE(flow && w && B > 0 && h > 0 && wd > 0, "flow_upsample: bad arguments");
+    FT_REQUIRE(dst->c == 8 && dst->n == B && dst->h == 2 * h && dst->w == 2 * wd, "flow_upsample: dst must be an 8-channel view of a [%d,%d,%d] map", B, 2 * h, 2 * wd);
+    flow_upsample_kernel<<<grid_for((size_t)B * h * wd * 4, 256), 256, 0, (cudaStream_t)stream>>>(flow, w, bias, B, h, wd, *dst);
+    return check_launch("flow_upsample_kernel");
 }
 
 int ft_decode_keypoints(const float* hm, int N, int C, int h, int w, const float* center, const float* scale, int adjust, float* kps, void* stream) {

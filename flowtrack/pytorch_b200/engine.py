@@ -255,6 +255,33 @@ def conv_from_modules(conv, bn=None, act=_lib.ACT_NONE, cin_p=None, device=None,
                      cin_p=cin_p, device=device, keep_host=keep_host, residual=residual)
 
 
+class FlowHead:
+    """predict_flow = Conv2d(C, 2, 3, 1, 1) (lib/flownet/networks/submodules.py:20-21) as a 1x1 convolution with 18
+    outputs on the tensor cores, part[(r*3+s)*2 + c] = W[c,:,r,s] . x, finished by ft_flow_head's shifted 9-term sum.
+    As a 3x3 implicit GEMM the wide concat input would be re-read nine times for two output columns."""
+
+    def __init__(self, conv, device=None, keep_host=False):
+        w = conv.weight.detach()
+        assert tuple(w.shape[2:]) == (3, 3) and w.shape[0] == 2 and conv.stride == (1, 1) and conv.padding == (1, 1)
+        self.cin, self.cout = w.shape[1], 2
+        w18 = w.permute(2, 3, 0, 1).reshape(18, self.cin, 1, 1).contiguous()
+        self.gemm = ConvLayer(_lib.KIND_CONV, w18, np.ones(18, np.float32), np.zeros(18, np.float32), device=device, keep_host=keep_host)
+        self.cin_p = self.gemm.cin_p
+        self.bias_host = conv.bias.detach().float().cpu().contiguous() if conv.bias is not None else None
+        self.bias = self.bias_host.to(device) if (self.bias_host is not None and device is not None) else None
+
+
+class FlowUp:
+    """upsampled_flowX_to_Y = ConvTranspose2d(2, 2, 4, 2, 1) on the fp32 flow (FlowNetS.py:41-44) -> ft_flow_upsample."""
+
+    def __init__(self, deconv, device=None):
+        assert tuple(deconv.weight.shape) == (2, 2, 4, 4) and deconv.stride == (2, 2) and deconv.padding == (1, 1)
+        self.w_host = deconv.weight.detach().float().cpu().contiguous()
+        self.bias_host = deconv.bias.detach().float().cpu().contiguous() if deconv.bias is not None else None
+        self.w = self.w_host.to(device) if device is not None else None
+        self.bias = self.bias_host.to(device) if (self.bias_host is not None and device is not None) else None
+
+
 # --------------------------------------------------------------------------------------------------
 # plans: a forward pass = a fixed list of C-ABI calls over pre-allocated buffers (CUDA-graph friendly)
 # --------------------------------------------------------------------------------------------------
@@ -287,6 +314,26 @@ class Plan:
 
     def call(self, what, fn, *args):
         self.calls.append((what, fn, args, args))
+
+    def flow_head(self, head, x, out=None, name=None):
+        """predict_flow on the split-fp16 view x -> fp32 NCHW flow [B,2,h,w] (a new static tensor unless `out` is given)."""
+        part = self.f32(x.n, 18, x.h, x.w)
+        self.conv(head.gemm, x, None, out_f32=part)
+        flow = out if out is not None else self.f32(x.n, 2, x.h, x.w)
+        self.call("flow_head", _lib.lib().ft_flow_head, part.data_ptr(), head.bias.data_ptr() if head.bias is not None else None,
+                  flow.data_ptr(), x.n, x.h, x.w)
+        self.keep.append(head)
+        if name:
+            self.taps[name] = flow
+        return flow
+
+    def flow_up(self, up, flow, dst):
+        """ConvTranspose2d(2,2,4,2,1) of an fp32 NCHW flow into the 8-channel split-fp16 view dst (a concat-buffer slice)."""
+        B, _, h, w = flow.shape
+        self.call("flow_upsample", _lib.lib().ft_flow_upsample, flow.data_ptr(), up.w.data_ptr(), up.bias.data_ptr() if up.bias is not None else None,
+                  B, h, w, dst.struct())
+        self.keep.append(up)
+        return dst
 
     def enqueue(self):
         """Issue every call of the plan on the current stream (also what graph capture records)."""

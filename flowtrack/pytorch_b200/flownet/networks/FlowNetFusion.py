@@ -28,13 +28,12 @@ def build(p, L, x, B, out_f32):
     c1 = p.conv(L["conv1_1"], t, cat1.view(0, 128))
     t = p.conv(L["conv2"], c1, p.act(B, H // 4, W // 4, 128))
     c2 = p.conv(L["conv2_1"], t, p.act(B, H // 4, W // 4, 128))
-    f = p.conv(L["predict_flow2"], c2, p.act(B, c2.h, c2.w, 2))
-    p.conv(L["upsampled_flow2_to_1"], f, cat1.view(160, 2))
+    f = p.flow_head(L["predict_flow2"], c2)
+    p.flow_up(L["upsampled_flow2_to_1"], f, cat1.view(160, 2))
     p.conv(L["deconv1"], c2, cat1.view(128, 32))
     t = p.conv(L["inter_conv1"], cat1, p.act(B, cat1.h, cat1.w, 32))
-    f = p.conv(L["predict_flow1"], t, p.act(B, cat1.h, cat1.w, 2))
-    p.conv(L["upsampled_flow1_to_0"], f, cat0.view(80, 2))
+    f = p.flow_head(L["predict_flow1"], t)
+    p.flow_up(L["upsampled_flow1_to_0"], f, cat0.view(80, 2))
     p.conv(L["deconv0"], cat1, cat0.view(64, 16))
     t = p.conv(L["inter_conv0"], cat0, p.act(B, H, W, 16))
-    p.conv(L["predict_flow0"], t, None, out_f32=out_f32, name="fusion")
-    return out_f32
+    return p.flow_head(L["predict_flow0"], t, out=out_f32, name="fusion")

@@ -49,10 +49,15 @@ def pack(mod, device, keep_host=False):
 
 
 def pack_all(net, device, keep_host=False):
-    """Every direct child that is a conv-like block -> {attribute name: ConvLayer}."""
+    """Every direct child that is a conv-like block -> {attribute name: ConvLayer}; the two-channel flow heads and the
+    2->2 flow up-samplers get their own packed forms (engine.FlowHead / engine.FlowUp)."""
     out = {}
     for name, child in net.named_children():
-        if isinstance(child, (nn.Conv2d, nn.ConvTranspose2d)) or (isinstance(child, nn.Sequential) and len(child) and isinstance(child[0], (nn.Conv2d, nn.ConvTranspose2d))):
+        if name.startswith("predict_flow"):
+            out[name] = engine.FlowHead(child, device=device, keep_host=keep_host)
+        elif name.startswith("upsampled_flow"):
+            out[name] = engine.FlowUp(child, device=device)
+        elif isinstance(child, (nn.Conv2d, nn.ConvTranspose2d)) or (isinstance(child, nn.Sequential) and len(child) and isinstance(child[0], (nn.Conv2d, nn.ConvTranspose2d))):
             out[name] = pack(child, device, keep_host)
     return out
 
@@ -68,21 +73,19 @@ def alloc_concats(p, B, H, W):
 
 def decoder(p, L, cat, c6, B, inter, tag=""):
     """Adds the ladder to plan `p`; returns the fp32 NCHW flow2 tensor [B,2,H/4,W/4]."""
-    f = p.conv(L["predict_flow6"], c6, p.act(B, c6.h, c6.w, 2))
-    p.conv(L["upsampled_flow6_to_5"], f, cat[5].view(1024, 2))
+    f = p.flow_head(L["predict_flow6"], c6)
+    p.flow_up(L["upsampled_flow6_to_5"], f, cat[5].view(1024, 2))
     p.conv(L["deconv5"], c6, cat[5].view(512, 512))
     for lvl in (5, 4, 3):
         src = cat[lvl]
         s, d = SKIP[lvl - 1]
         head_in = p.conv(L["inter_conv%d" % lvl], src, p.act(B, src.h, src.w, L["inter_conv%d" % lvl].cout)) if inter else src
-        f = p.conv(L["predict_flow%d" % lvl], head_in, p.act(B, src.h, src.w, 2))
-        p.conv(L["upsampled_flow%d_to_%d" % (lvl, lvl - 1)], f, cat[lvl - 1].view(s + d, 2))
+        f = p.flow_head(L["predict_flow%d" % lvl], head_in)
+        p.flow_up(L["upsampled_flow%d_to_%d" % (lvl, lvl - 1)], f, cat[lvl - 1].view(s + d, 2))
         p.conv(L["deconv%d" % (lvl - 1)], src, cat[lvl - 1].view(s, d))
     src = cat[2]
     head_in = p.conv(L["inter_conv2"], src, p.act(B, src.h, src.w, L["inter_conv2"].cout)) if inter else src
-    flow2 = p.f32(B, 2, src.h, src.w)
-    p.conv(L["predict_flow2"], head_in, None, out_f32=flow2, name=tag + "flow2")
-    return flow2
+    return p.flow_head(L["predict_flow2"], head_in, name=tag + "flow2")
 
 
 def add_decoder_modules(net, bn, up_bias, inter):

@@ -146,6 +146,17 @@ int ft_warp_concat(const float* x6, const float* flow, float div_flow, int B, in
 int ft_fusion_concat(const float* x6, const float* flow_sd, const float* flow_s2, int B, int H, int W,
                      const ft_act* dst, void* stream);
 
+/* Flow prediction head (lib/flownet/networks/submodules.py:20-21, predict_flow = Conv2d(C, 2, 3, 1, 1)).  The path
+ * runs the 3x3 two-channel convolution as a 1x1 convolution with 18 outputs through ft_conv2d_fprop (out_f32),
+ * part[n, (r*3+s)*2 + c, y, x] = W[c,:,r,s] . in[n,:,y,x], and this call finishes it:
+ * flow[n,c,y,x] = bias[c] + sum_{r,s} part[n, (r*3+s)*2 + c, y+r-1, x+s-1].  part: [B,18,H,W], flow: [B,2,H,W] fp32. */
+int ft_flow_head(const float* part, const float* bias, float* flow, int B, int H, int W, void* stream);
+/* upsampled_flowX_to_Y = ConvTranspose2d(2, 2, 4, 2, 1) (FlowNetS.py:41-44): flow [B,2,h,w] fp32, w = the module's
+ * weight [2][2][4][4], bias [2] or NULL -> split-fp16 NHWC channels [0,2) (+6 zeros) of the 8-channel view dst
+ * at [B,2h,2w].                                                                                          */
+int ft_flow_upsample(const float* flow, const float* w, const float* bias, int B, int h, int wd,
+                     const ft_act* dst, void* stream);
+
 /* ---- decode -------------------------------------------------------------------------------------- */
 /* hm: [N,C,h,w] fp32; center: [N,2], scale: [N] fp32 -> kps: [N,C,3] = (x, y, score) in image
  * coordinates (max_preds + optional quarter-pixel shift + inverse crop transform).                   */

@@ -160,4 +160,4 @@ def test_fusion_plan_builds_on_cpu():
     net = FlowNetFusion.FlowNetFusion(None, batchNorm=False)
     p = engine.Plan("cpu")
     out = FlowNetFusion.build(p, submodules.pack_all(net, "cpu"), p.act(1, 64, 128, 11), 1, p.f32(1, 2, 64, 128))
-    assert len(p.calls) == 14 and tuple(out.shape) == (1, 2, 64, 128)
+    assert len(p.calls) == 17 and tuple(out.shape) == (1, 2, 64, 128)

@@ -104,3 +104,38 @@ def test_tc_matches_simt_bitwise_scale_on_large_tile_count():
         ref = F.leaky_relu(conv.cuda()(x.cuda()), 0.1)
     assert (a - b).abs().max() < 2e-5 * ref.abs().max()
     assert (a - ref).abs().max() < 2e-5 * ref.abs().max()
+
+
+@pytest.mark.parametrize("cin,hw,B", [(1026, (6, 8), 2), (194, (24, 32), 3), (16, (32, 64), 1)])
+def test_flow_head_1x1_plus_shifted_sum(cin, hw, B):
+    """predict_flow (3x3, two outputs) run as an 18-output 1x1 GEMM + ft_flow_head equals the 3x3 convolution."""
+    torch.manual_seed(cin)
+    conv = nn.Conv2d(cin, 2, 3, 1, 1)
+    x = torch.randn(B, cin, *hw)
+    with torch.no_grad():
+        ref = conv.double()(x.double()).float()
+    head = engine.FlowHead(conv.float(), device="cuda")
+    p = engine.Plan(torch.device("cuda"))
+    xa = gpu_util.pack_nchw(x.cuda(), head.cin_p)
+    flow = p.flow_head(head, xa)
+    p.enqueue()
+    torch.cuda.synchronize()
+    assert (flow.cpu() - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("bias", [False, True])
+def test_flow_upsample_deconv(bias):
+    torch.manual_seed(3)
+    dc = nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=bias)
+    f = torch.randn(3, 2, 6, 8) * 5
+    with torch.no_grad():
+        ref = dc(f)
+    up = engine.FlowUp(dc, device="cuda")
+    p = engine.Plan(torch.device("cuda"))
+    big = engine.Act(3, 12, 16, 64 + 2, "cuda", zero=True)
+    p.flow_up(up, f.cuda(), big.view(64, 2))
+    p.enqueue()
+    torch.cuda.synchronize()
+    got = big.view(64, 2).to_nchw(2).cpu()
+    assert (got - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item())
+    assert big.to_nchw()[:, :64].abs().max() == 0 and big.view(64, 2).to_nchw()[:, 2:].abs().max() == 0
