@@ -58,7 +58,8 @@ struct alignas(64) ConvK {
     const float* w_gemm;
     const float* scale;
     const float* shift;
-    int N, H, W, in_ld, in_coff, cin_p, cin_k, cpt;
+    int N, H, W, Wp, xoff, in_ld, in_coff, cin_p, cin_k, cpt;   // Wp/xoff: physical row pitch (pixels) and left padding of the input
+    int kw, pad, row_pad, row_mode;                                   // FT_K_ROW: one k-block per kernel row
     int Qh, Qw, Ho, Wo, out_ld, out_coff, cout, cout_p8, cout_pad;
     int res_ld, res_coff;
     int in_stride, out_mul;
@@ -285,7 +286,8 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                     const uint32_t stage = smem_base + s * G::STAGE;
                     mbar_arrive_expect_tx(full_bar(s), (uint32_t)G::STAGE);
                     if (kb < p.kb_main) {
-                        const int dy = p.tap_dy[tc.phase][tap], dx = p.tap_dx[tc.phase][tap];
+                        // FT_K_ROW: k-block `tap` is kernel row tap (all kw taps of it, contiguous in the x-padded input)
+                        const int dy = p.row_mode ? tap - p.pad : p.tap_dy[tc.phase][tap], dx = p.row_mode ? 0 : p.tap_dx[tc.phase][tap];
                         int view = 0, cx = tc.qx0 + dx, cy = tc.qy0 + dy;
                         if (p.in_stride == 2) {      // input pixel 2q+d lives in parity view (d&1) at index q + (d - (d&1))/2
                             const int py = dy & 1, px = dx & 1;
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                         const int qy = t2 % p.Qh, n = t2 / p.Qh;
                         iy0[i] = qy * p.in_stride;
                         ix0[i] = qx * p.in_stride;
-                        pix[i] = (n * p.H + iy0[i]) * p.W + ix0[i];
+                        pix[i] = (n * p.H + iy0[i]) * p.Wp + ix0[i] + p.xoff;
                     } else {
                         iy0[i] = -(1 << 20);    // fails every bounds test -> zero fill
                         ix0[i] = 0;
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                     const bool tap_ok = tap < p.taps;
                     const int dy = tap_ok ? p.tap_dy[tc.phase][tap] : 0;
                     const int dx = tap_ok ? p.tap_dx[tc.phase][tap] : 0;
-                    const int doff = dy * p.W + dx;
+                    const int doff = dy * p.Wp + dx;
                     const int coff = p.in_coff + c8 * 8;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -538,8 +540,8 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvK p) {
         for (int t = 0; t < p.taps; ++t) {
             const int iy = qy * p.in_stride + p.tap_dy[ph][t], ix = qx * p.in_stride + p.tap_dx[ph][t];
             if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
-            const size_t off = ((size_t)(n * p.H + iy) * p.W + ix) * p.in_ld + p.in_coff;
-            const float* wt = wp + (size_t)t * p.cin_k * p.cout_pad;
+            const size_t off = ((size_t)(n * p.H + iy) * p.Wp + ix + p.xoff) * p.in_ld + p.in_coff;
+            const float* wt = wp + ((size_t)t * p.cin_k + (size_t)(t / p.kw) * p.row_pad) * p.cout_pad;
             for (int ci = 0; ci < p.cin_p; ++ci) {
                 float a = __half2float(p.in_hi[off + ci]);
                 if (p.in_lo) a += __half2float(p.in_lo[off + ci]);
@@ -651,14 +653,16 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     FT_REQUIRE(d->cout > 0 && d->cout_pad >= d->cout && d->cout_pad % 8 == 0, "conv2d: bad cout/cout_pad (%d/%d)", d->cout, d->cout_pad);
     FT_REQUIRE(d->precision == FT_PREC_SPLIT || d->precision == FT_PREC_FAST, "conv2d: bad precision %d", d->precision);
     FT_REQUIRE(d->precision == FT_PREC_FAST || d->in.lo, "conv2d: split precision needs the input lo plane");
-    FT_REQUIRE(d->k_mode == FT_K_PACKED || d->k_mode == FT_K_TAP64, "conv2d: bad k_mode %d", d->k_mode);
+    FT_REQUIRE(d->k_mode == FT_K_PACKED || d->k_mode == FT_K_TAP64 || d->k_mode == FT_K_ROW, "conv2d: bad k_mode %d", d->k_mode);
     const bool split = d->precision == FT_PREC_SPLIT;
 
     ConvK k = {};
     k.in_hi = (const __half*)d->in.hi;
     k.in_lo = split ? (const __half*)d->in.lo : nullptr;
-    k.N = d->in.n, k.H = d->in.h, k.W = d->in.w;
+    FT_REQUIRE(d->in_xpad_l >= 0 && d->in_xpad_r >= 0 && d->in.w > d->in_xpad_l + d->in_xpad_r, "conv2d: bad input x-padding %d/%d for width %d", d->in_xpad_l, d->in_xpad_r, d->in.w);
+    k.N = d->in.n, k.H = d->in.h, k.Wp = d->in.w, k.xoff = d->in_xpad_l, k.W = d->in.w - d->in_xpad_l - d->in_xpad_r;
     k.in_ld = d->in.ld, k.in_coff = d->in.coff, k.cin_p = d->in.c, k.cpt = d->in.c / 8;
+    k.kw = d->kind == FT_CONV ? d->kw : 2, k.pad = d->pad;
     if (d->kind == FT_CONV) {
         FT_REQUIRE(d->kh > 0 && d->kw > 0 && d->kh * d->kw <= 64 && d->stride > 0 && d->pad >= 0, "conv2d: unsupported window %dx%d s%d p%d", d->kh, d->kw, d->stride, d->pad);
         k.n_phase = 1, k.taps = d->kh * d->kw;
@@ -688,11 +692,22 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
         FT_REQUIRE(false, "conv2d: unknown kind %d", d->kind);
     }
     FT_REQUIRE(k.Ho > 0 && k.Wo > 0, "conv2d: empty output");
-    // K layout: FT_K_PACKED k = tap*cin_p + ci ; FT_K_TAP64 k = tap*cin_k + ci with cin_k = cin_p rounded up to 64
+    // K layout: FT_K_PACKED k = tap*cin_p + ci ; FT_K_TAP64 k = tap*cin_k + ci with cin_k = cin_p rounded up to 64 ;
+    //           FT_K_ROW    k = r*64 + s*cin_p + ci (kernel row r, column s)
     k.cin_k = d->k_mode == FT_K_TAP64 ? round_up(k.cin_p, BK) : k.cin_p;
     k.cb = k.cin_k / BK;
     k.k_pad = d->k_pad;
-    FT_REQUIRE(k.k_pad == round_up(k.taps * k.cin_k, BK), "conv2d: k_pad %d does not match taps*cin_k = %d (k_mode %d)", k.k_pad, k.taps * k.cin_k, d->k_mode);
+    if (d->k_mode == FT_K_ROW) {
+        FT_REQUIRE(d->kind == FT_CONV && d->kw * k.cin_p <= BK && (d->stride == 1 || d->stride == 2), "conv2d: FT_K_ROW needs a plain convolution with kw*Cin <= 64 and stride 1 or 2");
+        FT_REQUIRE(d->in.ld == d->in.c && d->in.coff == 0, "conv2d: FT_K_ROW needs a dense input view (ld == c)");
+        FT_REQUIRE(d->in_xpad_l >= d->pad && d->in_xpad_r * k.cin_p >= d->pad * k.cin_p + BK - d->kw * k.cin_p,
+                   "conv2d: FT_K_ROW needs zero columns in the input rows: left >= pad, right >= pad + (64 - kw*Cin)/Cin (got %d/%d)", d->in_xpad_l, d->in_xpad_r);
+        FT_REQUIRE(!d->res.hi, "conv2d: FT_K_ROW does not take a residual");
+        k.row_mode = 1, k.row_pad = BK - d->kw * k.cin_p, k.cb = 1;
+        FT_REQUIRE(k.k_pad == d->kh * BK, "conv2d: k_pad %d does not match kh*64 = %d (FT_K_ROW)", k.k_pad, d->kh * BK);
+    } else {
+        FT_REQUIRE(k.k_pad == round_up(k.taps * k.cin_k, BK), "conv2d: k_pad %d does not match taps*cin_k = %d (k_mode %d)", k.k_pad, k.taps * k.cin_k, d->k_mode);
+    }
     k.kb_main = k.k_pad / BK;
     k.cout = d->cout, k.cout_p8 = round_up(d->cout, 8), k.cout_pad = d->cout_pad;
     k.scale = d->scale, k.shift = d->shift, k.act = d->act, k.slope = d->slope;
@@ -754,12 +769,24 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
         k.m_tiles = k.tiles_w * k.tiles_h * ceil_div(k.N, k.bn);
         const int abox[4] = {BK, k.bw, k.bh, k.bn};
         const int st = k.in_stride;
-        for (int view = 0; view < st * st; ++view) {
+        if (k.row_mode) {
+            // rows of the A tile = 64 contiguous fp16 of the x-padded input starting at pixel (s*qy + r - pad, s*qx - pad):
+            // dim1 walks qx with an (overlapping) stride of s pixels, dim2 walks the input rows of one parity, dim3 images
+            for (int py = 0; py < st; ++py) {
+                const long long dim[4] = {BK, k.Qw, (k.H - py + st - 1) / st, k.N};
+                const long long str[3] = {(long long)st * k.in_ld, (long long)st * k.Wp * k.in_ld, (long long)k.H * k.Wp * k.in_ld};
+                const size_t off = (size_t)(py * k.Wp + k.xoff - k.pad) * k.in_ld;
+                if (int e = make_map(&k.in_map[py * 2][0], k.in_hi + off, dim, str, abox, 128, "in.hi(row)")) return e;
+                if (split)
+                    if (int e = make_map(&k.in_map[py * 2][1], k.in_lo + off, dim, str, abox, 128, "in.lo(row)")) return e;
+            }
+        }
+        for (int view = 0; view < st * st && !k.row_mode; ++view) {
             const int py = view / st, px = view % st;
             if (px >= k.W || py >= k.H) continue;
             const long long dim[4] = {k.cin_p, (k.W - px + st - 1) / st, (k.H - py + st - 1) / st, k.N};
-            const long long str[3] = {(long long)st * k.in_ld, (long long)st * k.W * k.in_ld, (long long)k.H * k.W * k.in_ld};
-            const size_t off = (size_t)(py * k.W + px) * k.in_ld + k.in_coff;
+            const long long str[3] = {(long long)st * k.in_ld, (long long)st * k.Wp * k.in_ld, (long long)k.H * k.Wp * k.in_ld};
+            const size_t off = (size_t)(py * k.Wp + px + k.xoff) * k.in_ld + k.in_coff;
             if (int e = make_map(&k.in_map[view][0], k.in_hi + off, dim, str, abox, 128, "in.hi")) return e;
             if (split)
                 if (int e = make_map(&k.in_map[view][1], k.in_lo + off, dim, str, abox, 128, "in.lo")) return e;

@@ -236,14 +236,16 @@ __device__ __forceinline__ void store8(const ft_act& d, size_t pix, int c8, cons
 }
 
 __global__ void pack_image_kernel(const float* __restrict__ src, long long sb, long long sc, long long sh, long long sw,
-                                  int C, float mul, ft_act d) {
-    const size_t npix = (size_t)d.n * d.h * d.w;
+                                  int C, float mul, ft_act d, int W, int xl) {
+    // d.w is the physical row pitch of the destination (image width W plus zero columns left/right); xl = left padding
+    const size_t npix = (size_t)d.n * d.h * W;
     const int groups = d.c / 8;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix * groups; i += (size_t)gridDim.x * blockDim.x) {
         // consecutive threads walk x first so the strided NCHW reads coalesce per channel
-        const size_t pix = i % npix;
+        const size_t spix = i % npix;
         const int g = (int)(i / npix);
-        const int x = (int)(pix % d.w), y = (int)((pix / d.w) % d.h), b = (int)(pix / ((size_t)d.w * d.h));
+        const int x = (int)(spix % W), y = (int)((spix / W) % d.h), b = (int)(spix / ((size_t)W * d.h));
+        const size_t pix = ((size_t)b * d.h + y) * d.w + x + xl;
         float v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -321,7 +323,7 @@ __global__ void pair_mean_final_kernel(const double* __restrict__ partial, int H
 }
 
 __global__ void pack_pair_kernel(const float* __restrict__ pair, const float* __restrict__ mean, int B, int H, int W,
-                                 float rgb_max, float* __restrict__ x_f32, ft_act d, int has_dst) {
+                                 float rgb_max, float* __restrict__ x_f32, ft_act d, int has_dst, int xl) {
     const size_t plane = (size_t)H * W;
     const size_t total = (size_t)B * plane;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -338,9 +340,10 @@ __global__ void pack_pair_kernel(const float* __restrict__ pair, const float* __
             }
         v[6] = v[7] = 0.f;
         if (has_dst) {
-            store8(d, i, 0, v);
+            const size_t dpix = (b * H + p / W) * d.w + p % W + xl;       // d.w = physical row pitch (W + zero columns)
+            store8(d, dpix, 0, v);
             const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int g = 1; g < d.c / 8; ++g) store8(d, i, g * 8, z);
+            for (int g = 1; g < d.c / 8; ++g) store8(d, dpix, g * 8, z);
         }
     }
 }
@@ -643,21 +646,26 @@ int ft_maxpool3x3s2(const ft_act* in, const ft_act* out, void* stream) {
     return check_launch("maxpool3x3s2_kernel");
 }
 
-int ft_pack_image(const float* src, long long sb, long long sc, long long sh, long long sw, int C, float mul, const ft_act* dst, void* stream) {
+int ft_pack_image(const float* src, long long sb, long long sc, long long sh, long long sw, int C, float mul, const ft_act* dst, int xpad_l, int xpad_r,
+                  void* stream) {
     if (int e = check_act(dst, "pack_image.dst", false)) return e;
     FT_REQUIRE(src && C > 0 && C <= dst->c, "pack_image: bad channel count %d (view has %d)", C, dst ? dst->c : -1);
-    pack_image_kernel<<<grid_for((size_t)dst->n * dst->h * dst->w * (dst->c / 8), 256), 256, 0, (cudaStream_t)stream>>>(src, sb, sc, sh, sw, C, mul, *dst);
+    FT_REQUIRE(xpad_l >= 0 && xpad_r >= 0 && dst->w > xpad_l + xpad_r, "pack_image: bad x-padding %d/%d for a %d-pixel row", xpad_l, xpad_r, dst->w);
+    const int W = dst->w - xpad_l - xpad_r;
+    pack_image_kernel<<<grid_for((size_t)dst->n * dst->h * W * (dst->c / 8), 256), 256, 0, (cudaStream_t)stream>>>(src, sb, sc, sh, sw, C, mul, *dst, W, xpad_l);
     return check_launch("pack_image_kernel");
 }
 
 int ft_pack_pair_ws_floats(int B) { return B * 3 * (2 * PAIR_MEAN_CHUNKS + 1); }
 
-int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* mean_ws, float* x_f32, const ft_act* dst, void* stream) {
+int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* mean_ws, float* x_f32, const ft_act* dst, int xpad_l, int xpad_r,
+                 void* stream) {
     FT_REQUIRE(pair && mean_ws && B > 0 && H > 0 && W > 0, "pack_pair: bad arguments");
     ft_act d = {};
     if (dst) {
         if (int e = check_act(dst, "pack_pair.dst", false)) return e;
-        FT_REQUIRE(dst->c >= 8 && dst->n == B && dst->h == H && dst->w == W, "pack_pair: dst shape mismatch");
+        FT_REQUIRE(xpad_l >= 0 && xpad_r >= 0, "pack_pair: bad x-padding");
+        FT_REQUIRE(dst->c >= 8 && dst->n == B && dst->h == H && dst->w == W + xpad_l + xpad_r, "pack_pair: dst shape mismatch");
         d = *dst;
     }
     FT_REQUIRE(((uintptr_t)mean_ws & 7) == 0, "pack_pair: workspace must be 8-byte aligned");
@@ -667,7 +675,7 @@ int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* m
     if (check_launch("pair_mean_partial_kernel")) return 1;
     pair_mean_final_kernel<<<B * 3, 32, 0, (cudaStream_t)stream>>>(partial, 2 * H * W, mean);
     if (check_launch("pair_mean_final_kernel")) return 1;
-    pack_pair_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(pair, mean, B, H, W, rgb_max, x_f32, d, dst != nullptr);
+    pack_pair_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(pair, mean, B, H, W, rgb_max, x_f32, d, dst != nullptr, xpad_l);
     return check_launch("pack_pair_kernel");
 }
 

@@ -46,6 +46,16 @@ def gemm_weights_conv(weight, cin_k):
     return g
 
 
+def gemm_weights_conv_rows(weight, cin_p):
+    """FT_K_ROW layout: Conv2d weight [Cout,Cin,kh,kw] -> [1, kh*64, Cout] with k = r*64 + s*cin_p + ci (kw*cin_p <= 64)."""
+    w = weight.detach().float().cpu().numpy()
+    cout, cin, kh, kw = w.shape
+    assert kw * cin_p <= BK
+    g = np.zeros((1, kh, BK, cout), np.float32)
+    g[0, :, :kw * cin_p].reshape(kh, kw, cin_p, cout)[:, :, :cin] = w.transpose(2, 3, 1, 0)
+    return g.reshape(1, kh * BK, cout)
+
+
 def gemm_weights_deconv(weight, cin_k):
     """ConvTranspose2d(k4,s2,p1) weight [Cin,Cout,4,4] -> [4, k_pad, Cout].
     out[oy] += in[iy]*w[ky] with oy = 2*iy - 1 + ky, so output parity py only sees ky = 1 - py + 2a (a=0,1), read at
@@ -122,12 +132,15 @@ def tile_weights(g, block_n, res_f=None):
 class Act:
     """Split-fp16 NHWC activation buffer on the GPU: value = hi + lo.  `view(coff, c)` selects a channel slice."""
 
-    def __init__(self, n, h, w, c, device, split=True, zero=False):
+    def __init__(self, n, h, w, c, device, split=True, zero=False, xpad=(0, 0)):
+        """`xpad` = (left, right) zero columns physically stored in every row (the FT_K_ROW stem convolutions read their
+        zero border from them); w stays the image width, struct() reports the physical row pitch."""
         self.n, self.h, self.w, self.c = n, h, w, pad8(c)
         self.ld, self.coff = self.c, 0
-        mk = torch.zeros if zero else torch.empty
-        self.hi = mk((n, h, w, self.ld), dtype=torch.float16, device=device)
-        self.lo = mk((n, h, w, self.ld), dtype=torch.float16, device=device) if split else None
+        self.xl, self.xr = xpad
+        mk = torch.zeros if (zero or self.xl or self.xr) else torch.empty
+        self.hi = mk((n, h, w + self.xl + self.xr, self.ld), dtype=torch.float16, device=device)
+        self.lo = mk((n, h, w + self.xl + self.xr, self.ld), dtype=torch.float16, device=device) if split else None
         self._base = self
 
     def view(self, coff, c, n0=0, n=None):
@@ -140,17 +153,19 @@ class Act:
 
     def struct(self):
         n0 = getattr(self, "_n0", 0)
-        off = n0 * self.h * self.w * self.ld * 2
+        wp = self.w + self.xl + self.xr
+        off = n0 * self.h * wp * self.ld * 2
         return FtAct(self.hi.data_ptr() + off, (self.lo.data_ptr() + off) if self.lo is not None else None,
-                     self.n, self.h, self.w, self.c, self.ld, self.coff)
+                     self.n, self.h, wp, self.c, self.ld, self.coff)
 
     def to_nchw(self, c=None):
         """Debug/test helper: materialise the view as fp32 NCHW."""
         n0 = getattr(self, "_n0", 0)
         c = self.c if c is None else c
-        t = self.hi[n0:n0 + self.n, :, :, self.coff:self.coff + c].float()
+        xs = slice(self.xl, self.xl + self.w)
+        t = self.hi[n0:n0 + self.n, :, xs, self.coff:self.coff + c].float()
         if self.lo is not None:
-            t = t + self.lo[n0:n0 + self.n, :, :, self.coff:self.coff + c].float()
+            t = t + self.lo[n0:n0 + self.n, :, xs, self.coff:self.coff + c].float()
         return t.permute(0, 3, 1, 2).contiguous()
 
 
@@ -168,7 +183,7 @@ class ConvLayer:
     """conv / deconv(k4,s2,p1) + per-channel scale/shift + optional residual + activation, weights resident on the GPU."""
 
     def __init__(self, kind, weight, scale, shift, stride=1, pad=0, act=_lib.ACT_NONE, slope=0.1, cin_p=None, device=None, block_n=None, keep_host=False,
-                 residual=False):
+                 residual=False, k_mode=None):
         if kind == _lib.KIND_CONV:
             self.cout, cin, self.kh, self.kw = weight.shape
         else:
@@ -178,11 +193,19 @@ class ConvLayer:
         assert self.cin_p % 8 == 0 and self.cin_p >= cin
         # K layout: small-Cin plain convolutions (the stems) pack K across taps and are gathered by cp.async;
         # everything else gives each tap a whole number of 64-channel blocks so a k-block is one TMA box.
+        # The 7x7 stems (kw*Cin between 49 and 64) use FT_K_ROW: one k-block per kernel row of an x-padded input.
         packed = kind == _lib.KIND_CONV and not residual and (self.cin_p < 32 or stride not in (1, 2))
-        self.k_mode = _lib.K_PACKED if packed else _lib.K_TAP64
-        self.cin_k = self.cin_p if self.k_mode == _lib.K_PACKED else round_up(self.cin_p, BK)
+        rows = packed and stride in (1, 2) and 48 < self.kw * self.cin_p <= BK and k_mode != _lib.K_PACKED
+        self.k_mode = _lib.K_ROW if rows else (_lib.K_PACKED if packed else _lib.K_TAP64)
+        self.cin_k = round_up(self.cin_p, BK) if self.k_mode == _lib.K_TAP64 else self.cin_p
+        self.row_pad = BK - self.kw * self.cin_p if rows else 0
+        # zero columns the input rows must carry for FT_K_ROW (left, right)
+        self.in_xpad = (round_up(pad, 4), round_up(pad + (BK - self.kw * self.cin_p + self.cin_p - 1) // self.cin_p, 4)) if rows else (0, 0)
         self.residual = residual
-        g = gemm_weights_conv(weight, self.cin_k) if kind == _lib.KIND_CONV else gemm_weights_deconv(weight, self.cin_k)
+        if rows:
+            g = gemm_weights_conv_rows(weight, self.cin_p)
+        else:
+            g = gemm_weights_conv(weight, self.cin_k) if kind == _lib.KIND_CONV else gemm_weights_deconv(weight, self.cin_k)
         self.block_n = block_n or choose_block_n(self.cout)
         self.cout_pad = round_up(self.cout, self.block_n)
         self.k_pad = g.shape[1]
@@ -219,6 +242,7 @@ class ConvLayer:
     def desc(self, x, out=None, out_f32=None, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05):
         assert x.c == self.cin_p, "input view has %d channels, layer expects %d" % (x.c, self.cin_p)
         assert (res is not None) == self.residual, "layer was packed %s residual blocks" % ("with" if self.residual else "without")
+        assert (x.xl, x.xr) == self.in_xpad, "layer expects input rows padded by %s zero columns, view has %s" % (self.in_xpad, (x.xl, x.xr))
         d = FtConvDesc()
         d.in_ = x.struct()
         d.out = out.struct() if out is not None else NULL_ACT
@@ -230,10 +254,11 @@ class ConvLayer:
         d.cout, d.cout_pad, d.k_pad, d.block_n = self.cout, self.cout_pad, self.k_pad, self.block_n
         d.act, d.slope, d.precision, d.impl = self.act, self.slope, precision, impl
         d.k_mode, d.res_blocks = self.k_mode, self.res_blocks
+        d.in_xpad_l, d.in_xpad_r = x.xl, x.xr
         return d
 
 
-def conv_from_modules(conv, bn=None, act=_lib.ACT_NONE, cin_p=None, device=None, keep_host=False, residual=False):
+def conv_from_modules(conv, bn=None, act=_lib.ACT_NONE, cin_p=None, device=None, keep_host=False, residual=False, k_mode=None):
     """nn.Conv2d / nn.ConvTranspose2d (+ eval BatchNorm2d) -> ConvLayer.  `residual`: the layer will be called with a
     residual tensor (bottleneck conv3); its weight image then carries the identity k-blocks the kernel needs."""
     is_deconv = isinstance(conv, torch.nn.ConvTranspose2d)
@@ -252,7 +277,7 @@ def conv_from_modules(conv, bn=None, act=_lib.ACT_NONE, cin_p=None, device=None,
     assert conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
     assert conv.dilation == (1, 1) and conv.groups == 1
     return ConvLayer(_lib.KIND_CONV, conv.weight, scale, shift, stride=conv.stride[0], pad=conv.padding[0], act=act,
-                     cin_p=cin_p, device=device, keep_host=keep_host, residual=residual)
+                     cin_p=cin_p, device=device, keep_host=keep_host, residual=residual, k_mode=k_mode)
 
 
 class FlowHead:
@@ -294,8 +319,8 @@ class Plan:
         self.taps = {}       # name -> Act / tensor, for layer-by-layer tests
         self.flops = {}      # call index -> algorithmic FLOPs (convolutions only)
 
-    def act(self, n, h, w, c, zero=False):
-        a = Act(n, h, w, c, self.device, split=True, zero=zero)
+    def act(self, n, h, w, c, zero=False, xpad=(0, 0)):
+        a = Act(n, h, w, c, self.device, split=True, zero=zero, xpad=xpad)
         self.keep.append(a)
         return a
 

@@ -96,14 +96,15 @@ class _FlowBase(nn.Module):
 
 
 # ---- plan fragments ---------------------------------------------------------------------------------
-def _normalise(p, pair, B, H, W, want_f32, want_act):
-    """models.py:112-119: x = (pair - mean_bc)/rgb_max as [B,6,H,W] fp32 and/or split-fp16 NHWC (6 -> 8 channels)."""
+def _normalise(p, pair, B, H, W, want_f32, want_act, xpad=(0, 0)):
+    """models.py:112-119: x = (pair - mean_bc)/rgb_max as [B,6,H,W] fp32 and/or split-fp16 NHWC (6 -> 8 channels).
+    `xpad`: zero columns the consuming stem convolution wants around every row of the NHWC copy (ConvLayer.in_xpad)."""
     lib = _lib.lib()
     ws = p.f32(lib.ft_pack_pair_ws_floats(B))
     xf = p.f32(B, 6, H, W) if want_f32 else None
-    xa = p.act(B, H, W, 6) if want_act else None
+    xa = p.act(B, H, W, 6, xpad=xpad) if want_act else None
     p.call("pack_pair", lib.ft_pack_pair, pair.data_ptr(), B, H, W, p.rgb_max, ws.data_ptr(),
-           xf.data_ptr() if want_f32 else None, xa.struct() if want_act else None)
+           xf.data_ptr() if want_f32 else None, xa.struct() if want_act else None, xpad[0], xpad[1])
     return xf, xa
 
 
@@ -115,12 +116,13 @@ def _up4(p, flow2, B, mul, mode):
     return out
 
 
-def _frames(p, xf, B, H, W):
+def _frames(p, xf, B, H, W, xpad=(0, 0)):
     """[B,6,H,W] fp32 -> split-fp16 NHWC [2B,H,W,8]: first frames then second frames (FlowNetC's two streams)."""
     lib = _lib.lib()
-    fr = p.act(2 * B, H, W, 3)
+    fr = p.act(2 * B, H, W, 3, xpad=xpad)
     for f in range(2):
-        p.call("pack_image", lib.ft_pack_image, xf.data_ptr() + f * 3 * H * W * 4, 6 * H * W, H * W, W, 1, 3, 1.0, fr.view(0, 3, f * B, B).struct())
+        p.call("pack_image", lib.ft_pack_image, xf.data_ptr() + f * 3 * H * W * 4, 6 * H * W, H * W, W, 1, 3, 1.0, fr.view(0, 3, f * B, B).struct(),
+               xpad[0], xpad[1])
     return fr
 
 
@@ -139,7 +141,7 @@ class FlowNet2S(FlowNetS.FlowNetS, _FlowBase):
 
     def _build(self, p, L, pair, B, H, W):
         p.rgb_max = self.rgb_max
-        _, xa = _normalise(p, pair, B, H, W, False, True)
+        _, xa = _normalise(p, pair, B, H, W, False, True, xpad=L[""]["conv1"].in_xpad)
         return _up4(p, FlowNetS.build(p, L[""], xa, B), B, self.div_flow, "bilinear")
 
 
@@ -152,7 +154,7 @@ class FlowNet2C(FlowNetC.FlowNetC, _FlowBase):
     def _build(self, p, L, pair, B, H, W):
         p.rgb_max = self.rgb_max
         xf, _ = _normalise(p, pair, B, H, W, True, False)
-        return _up4(p, FlowNetC.build(p, L[""], _frames(p, xf, B, H, W), B), B, self.div_flow, "bilinear")
+        return _up4(p, FlowNetC.build(p, L[""], _frames(p, xf, B, H, W, L[""]["conv1"].in_xpad), B), B, self.div_flow, "bilinear")
 
 
 class FlowNet2SD(FlowNetSD.FlowNetSD, _FlowBase):
@@ -163,7 +165,7 @@ class FlowNet2SD(FlowNetSD.FlowNetSD, _FlowBase):
 
     def _build(self, p, L, pair, B, H, W):
         p.rgb_max = self.rgb_max
-        _, xa = _normalise(p, pair, B, H, W, False, True)
+        _, xa = _normalise(p, pair, B, H, W, False, True, xpad=L[""]["conv0"].in_xpad)
         return _up4(p, FlowNetSD.build(p, L[""], xa, B), B, self.div_flow, "bilinear")
 
 
@@ -174,8 +176,8 @@ class _Stacked(_FlowBase):
     def _c_then_s1(self, p, L, pair, B, H, W):
         """FlowNetC -> warp -> FlowNetS_1 (models.py:121-135); returns x (fp32), x (act) and the 2nd full-res flow."""
         p.rgb_max = self.rgb_max
-        xf, xa = _normalise(p, pair, B, H, W, True, True)
-        flow = _up4(p, FlowNetC.build(p, L["flownetc"], _frames(p, xf, B, H, W), B, "c_"), B, self.div_flow, "bilinear")
+        xf, xa = _normalise(p, pair, B, H, W, True, True, xpad=L["flownets_d"]["conv0"].in_xpad if "flownets_d" in L else (0, 0))
+        flow = _up4(p, FlowNetC.build(p, L["flownetc"], _frames(p, xf, B, H, W, L["flownetc"]["conv1"].in_xpad), B, "c_"), B, self.div_flow, "bilinear")
         p.taps["flownetc_flow"] = flow
         cat = _warp_concat(p, xf, flow, B, H, W, self.div_flow)
         flow = _up4(p, FlowNetS.build(p, L["flownets_1"], cat, B, "s1_"), B, self.div_flow, "bilinear")

@@ -41,7 +41,7 @@ def build(p, L, frames, B, tag=""):
     corr = p.f32(B, 441, h8, w8)
     p.call("correlation", lib.ft_correlation_forward, a3f.data_ptr(), b3f.data_ptr(), corr.data_ptr(), B, 256, h8, w8, 20, 1, 20, 1, 2, 1)
     st = corr.stride()
-    p.call("pack_image", lib.ft_pack_image, corr.data_ptr(), st[0], st[1], st[2], st[3], 441, 1.0, merged.view(32, 441).struct())
+    p.call("pack_image", lib.ft_pack_image, corr.data_ptr(), st[0], st[1], st[2], st[3], 441, 1.0, merged.view(32, 441).struct(), 0, 0)
     p.conv(L["conv_redir"], c3a, merged.view(0, 32))
     p.taps[tag + "corr"] = corr
     c3 = p.conv(L["conv3_1"], merged, cat[3].view(0, 256))

@@ -127,9 +127,9 @@ class DeconvResnet(nn.Module):
         L = self._layers
         p = engine.Plan(device, precision, impl)
         src = p.f32(B, 3, H, W)                                 # static fp32 NCHW input (graph-capturable)
-        x = p.act(B, H, W, 8)                                   # packed input, 3 -> 8 channels
+        x = p.act(B, H, W, 8, xpad=L["stem"].in_xpad)           # packed input, 3 -> 8 channels, rows zero-padded for the FT_K_ROW stem
         xs, st = x.struct(), src.stride()
-        p.call("pack_image", _lib.lib().ft_pack_image, src.data_ptr(), st[0], st[1], st[2], st[3], 3, 1.0, xs)
+        p.call("pack_image", _lib.lib().ft_pack_image, src.data_ptr(), st[0], st[1], st[2], st[3], 3, 1.0, xs, x.xl, x.xr)
         h, w = L["stem"].out_hw(H, W)
         y = p.conv(L["stem"], x, p.act(B, h, w, 64), name="stem")
         h, w = (h + 1) // 2, (w + 1) // 2

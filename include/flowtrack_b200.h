@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 2
+#define FT_ABI_VERSION 3
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -62,7 +62,11 @@ enum { FT_PREC_SPLIT = 0,  /* 3 tcgen05 MMAs per tile (hi*hi + lo*hi + hi*lo): f
        FT_PREC_FAST  = 1   /* 1 MMA on the hi planes only: fp16-operand results                    */ };
 enum { FT_K_PACKED = 0,    /* k = tap*in.c + ci, k_pad = round_up(taps*in.c, 64): im2col gathered by cp.async;
                               for the small-Cin stems (a 64-channel TMA box per tap would be mostly padding)   */
-       FT_K_TAP64  = 1     /* k = tap*cin_k + ci with cin_k = round_up(in.c, 64): one TMA box per (tap, 64 ch)  */ };
+       FT_K_TAP64  = 1,    /* k = tap*cin_k + ci with cin_k = round_up(in.c, 64): one TMA box per (tap, 64 ch)  */
+       FT_K_ROW    = 2     /* k = r*64 + s*in.c + ci (kernel row r, column s; kw*in.c <= 64, k_pad = kh*64): one TMA
+                              box per kernel row -- the kw taps of a row are contiguous in an NHWC image, so a
+                              tensor map whose pixel stride is smaller than its 128-byte box row reads them in one
+                              go (the 7x7 stems).  Needs in_xpad_l/r zero columns in the input rows.             */ };
 enum { FT_IMPL_TCGEN05 = 0,  /* tcgen05/TMEM implicit GEMM (the product path)                      */
        FT_IMPL_SIMT    = 1   /* fp32 CUDA-core kernel, same data formats (bring-up / cross-check)  */ };
 
@@ -94,6 +98,8 @@ typedef struct {
     int32_t precision;      /* FT_PREC_*                                                           */
     int32_t impl;           /* FT_IMPL_*                                                           */
     int32_t k_mode;         /* FT_K_*: K layout of w_gemm / w_tile                                 */
+    int32_t in_xpad_l;      /* the rows of `in` physically start with in_xpad_l and end with in_xpad_r */
+    int32_t in_xpad_r;      /* zero pixels: in.w counts them, the image is in.w - l - r wide (0/0 normally) */
     int32_t res_blocks;     /* residual k-blocks appended to every (phase, n_tile) of w_tile:
                                ceil(block_n/64) when the layer is called with a residual, else 0.
                                Block j holds diag(f) for channels [64j, 64j+64) of the tile, where
@@ -125,15 +131,17 @@ int ft_channelnorm_forward(const float* x, float* out, int B, int C, int H, int 
 int ft_conv2d_fprop(const ft_conv_desc* d, void* stream);
 int ft_maxpool3x3s2(const ft_act* in, const ft_act* out, void* stream);
 /* src: [B,C,H,W] fp32 (arbitrary strides given in elements) -> split-fp16 NHWC view `dst` channels
- * [0,C), multiplied by `mul`; channels [C, dst->c) are zero-filled.                                   */
+ * [0,C), multiplied by `mul`; channels [C, dst->c) are zero-filled.  dst->w = xpad_l + W + xpad_r: the
+ * image is written at column xpad_l of every destination row, the padding columns are left untouched
+ * (the caller zero-fills them once; FT_K_ROW convolutions read them as the convolution's zero border). */
 int ft_pack_image(const float* src, long long sb, long long sc, long long sh, long long sw, int C,
-                  float mul, const ft_act* dst, void* stream);
+                  float mul, const ft_act* dst, int xpad_l, int xpad_r, void* stream);
 /* FlowNet2 input normalisation: pair [B,3,2,H,W] (RGB 0..255) -> x = (pair - mean_bc) / rgb_max laid
  * out as [B,6,H,W] fp32 (x_f32, optional) and as split-fp16 NHWC (dst, optional, 6 -> 8 channels).
  * `mean_ws` is an 8-byte aligned workspace of ft_pack_pair_ws_floats(B) floats (partial sums + means). */
 int ft_pack_pair_ws_floats(int B);
 int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* mean_ws, float* x_f32,
-                 const ft_act* dst, void* stream);
+                 const ft_act* dst, int xpad_l, int xpad_r, void* stream);   /* dst->w = xpad_l + W + xpad_r, as above */
 /* src: [B,C,h,w] fp32 -> dst: [B,C,4h,4w] fp32 times `mul`.  mode 0 = bilinear (align_corners=False),
  * 1 = nearest.                                                                                        */
 int ft_upsample4x(const float* src, float* dst, int B, int C, int h, int w, float mul, int mode, void* stream);

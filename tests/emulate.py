@@ -31,10 +31,12 @@ def emulate_layer(layer, x, res=None):
     xp = torch.nn.functional.pad(x.double(), (0, 0, P, P, P, P))
     for ph, (taps, (oy, ox)) in enumerate(phases):
         cols = []
-        for dy, dx in taps:
+        for t, (dy, dx) in enumerate(taps):
             ys = torch.arange(Qh) * in_stride + dy + P
             xs = torch.arange(Qw) * in_stride + dx + P
             cols.append(torch.nn.functional.pad(xp[:, ys][:, :, xs], (0, layer.cin_k - C)))   # per-tap channel padding of the K layout
+            if layer.k_mode == _lib.K_ROW and (t + 1) % layer.kw == 0:                          # FT_K_ROW: every kernel row is padded to 64
+                cols.append(torch.zeros(N, Qh, Qw, layer.row_pad, dtype=torch.float64))
         A = torch.cat(cols, dim=-1)
         out[:, oy::out_mul, ox::out_mul] = A @ wg[ph][:A.shape[-1]]
     out = out * sc + sh

@@ -10,12 +10,12 @@ def sp():
     return engine.stream_ptr()
 
 
-def pack_nchw(x, cpad=None):
-    """fp32 NCHW cuda tensor -> split-fp16 NHWC Act via ft_pack_image."""
+def pack_nchw(x, cpad=None, xpad=(0, 0)):
+    """fp32 NCHW cuda tensor -> split-fp16 NHWC Act via ft_pack_image (optionally with zero columns around every row)."""
     B, C, H, W = x.shape
-    a = engine.Act(B, H, W, cpad or C, x.device)
+    a = engine.Act(B, H, W, cpad or C, x.device, xpad=xpad)
     st = x.stride()
-    _lib.check(_lib.lib().ft_pack_image(x.data_ptr(), st[0], st[1], st[2], st[3], C, 1.0, a.struct(), sp()), "pack_image")
+    _lib.check(_lib.lib().ft_pack_image(x.data_ptr(), st[0], st[1], st[2], st[3], C, 1.0, a.struct(), xpad[0], xpad[1], sp()), "pack_image")
     return a
 
 

@@ -67,7 +67,11 @@ def test_tile_image_roundtrip_and_split_precision():
     m = np.abs(wg).max(axis=(0, 1))[:130]
     assert np.all((m >= 1024) & (m < 2048))               # power-of-two column normalisation
     stem = engine.conv_from_modules(nn.Conv2d(3, 64, 7, 2, 3, bias=False), None, cin_p=8, keep_host=True)
+    assert stem.k_mode == _lib.K_ROW and stem.k_pad == 7 * 64 and stem.row_pad == 8 and stem.in_xpad == (4, 4)   # one k-block per kernel row
+    stem = engine.conv_from_modules(nn.Conv2d(3, 64, 7, 2, 3, bias=False), None, cin_p=8, keep_host=True, k_mode=_lib.K_PACKED)
     assert stem.k_mode == _lib.K_PACKED and stem.cin_k == 8 and stem.k_pad == 448      # K packed across taps: 49*8 = 392 -> 448
+    sd0 = engine.conv_from_modules(nn.Conv2d(6, 64, 3, 1, 1), None, keep_host=True)
+    assert sd0.k_mode == _lib.K_PACKED and sd0.in_xpad == (0, 0)
 
 
 def test_residual_identity_blocks():
@@ -130,7 +134,7 @@ def test_library_exports_every_declared_symbol():
     declared -= {"ft_act", "ft_conv_desc"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     l = _lib.lib()                                         # loads the .so and resolves every symbol
-    assert l.ft_abi_version() == 2
+    assert l.ft_abi_version() == 3
     assert l.ft_sizeof(0) == ctypes.sizeof(_lib.FtAct) == 40 and l.ft_sizeof(1) == ctypes.sizeof(_lib.FtConvDesc)
 
 

@@ -19,6 +19,8 @@ CASES = [
     ("3x3_s2_128", lambda: nn.Conv2d(128, 128, 3, 2, 1, bias=False), (2, 128, 16, 12), _lib.ACT_RELU),
     ("1x1_s2_down", lambda: nn.Conv2d(256, 512, 1, 2, bias=False), (2, 256, 16, 12), _lib.ACT_NONE),
     ("stem7x7", lambda: nn.Conv2d(3, 64, 7, 2, 3, bias=False), (2, 3, 64, 48), _lib.ACT_RELU),
+    ("stem7x7_s1_cin6", lambda: nn.Conv2d(6, 32, 7, 1, 3), (3, 6, 20, 28), _lib.ACT_LEAKY),                  # FT_K_ROW, stride 1, batch > 1
+    ("stem7x7_flow", lambda: nn.Conv2d(6, 64, 7, 2, 3), (2, 6, 64, 128), _lib.ACT_LEAKY),                  # FlowNetS conv1
     ("flow5x5_s2", lambda: nn.Conv2d(64, 128, 5, 2, 2), (1, 64, 24, 32), _lib.ACT_LEAKY),
     ("cin1032_pred", lambda: nn.Conv2d(1026, 2, 3, 1, 1), (1, 1026, 6, 8), _lib.ACT_NONE),                 # odd concat width, Cout 2
     ("head17", lambda: nn.Conv2d(256, 17, 1), (2, 256, 16, 12), _lib.ACT_NONE),
@@ -54,7 +56,7 @@ def test_conv_layer(name, ctor, shape, act, impl, prec, tol):
     x = torch.randn(*shape, dtype=torch.float64)
     ref = _ref(mod, x, act).float()
     layer = engine.conv_from_modules(mod.float(), None, act, device="cuda")
-    xa = gpu_util.pack_nchw(x.float().cuda(), layer.cin_p)
+    xa = gpu_util.pack_nchw(x.float().cuda(), layer.cin_p, xpad=layer.in_xpad)
     out, f32 = gpu_util.run_layer(layer, xa, precision=prec, impl=impl, want_f32=True)
     got = out.to_nchw(layer.cout).cpu()
     scale = max(1.0, ref.abs().max().item())
@@ -139,3 +141,20 @@ def test_flow_upsample_deconv(bias):
     got = big.view(64, 2).to_nchw(2).cpu()
     assert (got - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item())
     assert big.to_nchw()[:, :64].abs().max() == 0 and big.view(64, 2).to_nchw()[:, 2:].abs().max() == 0
+
+
+def test_stem_packed_gather_variant_still_matches():
+    """The cp.async gather variant (FT_K_PACKED) stays available for small-Cin layers that are not 7x7 stems; force it
+    on the stem shape and compare with the FT_K_ROW result."""
+    torch.manual_seed(2)
+    conv = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+    x = torch.randn(2, 3, 64, 48)
+    with torch.no_grad():
+        ref = torch.relu(conv.double()(x.double())).float()
+    outs = []
+    for km in (None, _lib.K_PACKED):
+        layer = engine.conv_from_modules(conv.float(), None, _lib.ACT_RELU, cin_p=8, device="cuda", k_mode=km)
+        assert layer.k_mode == (_lib.K_ROW if km is None else _lib.K_PACKED)
+        xa = gpu_util.pack_nchw(x.cuda(), 8, xpad=layer.in_xpad)
+        outs.append(gpu_util.run_layer(layer, xa).to_nchw(64).cpu())
+        assert (outs[-1] - ref).abs().max() <= 2e-5 * ref.abs().max()

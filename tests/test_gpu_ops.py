@@ -110,7 +110,7 @@ def test_pack_pair_and_layout_roundtrip():
     xf = torch.empty(B, 6, H, W, device="cuda")
     ws = torch.empty(L().ft_pack_pair_ws_floats(B), device="cuda")
     pair_d = pair.cuda()
-    _lib.check(L().ft_pack_pair(pair_d.data_ptr(), B, H, W, 255.0, ws.data_ptr(), xf.data_ptr(), d.struct(), gpu_util.sp()), "pack_pair")
+    _lib.check(L().ft_pack_pair(pair_d.data_ptr(), B, H, W, 255.0, ws.data_ptr(), xf.data_ptr(), d.struct(), 0, 0, gpu_util.sp()), "pack_pair")
     ref = flow_oracle.normalise_pair(pair, 255.0)
     assert (xf.cpu() - ref).abs().max() < 1e-6
     back = d.to_nchw().cpu()
