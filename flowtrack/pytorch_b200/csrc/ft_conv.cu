@@ -63,7 +63,7 @@ struct alignas(64) ConvK {
     int Qh, Qw, Ho, Wo, out_ld, out_coff, cout, cout_p8, cout_pad;
     int res_ld, res_coff;
     int in_stride, out_mul;
-    int n_phase, taps, cb, kb_main, kb_total, k_pad;
+    int n_phase, taps, cb, kb_main, kb_total, k_pad, chunk;
     int M, m_tiles, n_tiles, num_tiles;
     int bw, bh, bn, lg_bw, lg_bh, tiles_w, tiles_h;
     int act;
@@ -193,6 +193,7 @@ constexpr int EPI_WARPS = 8;            // two groups of 4 warps (one per TMEM l
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS, TMA_WARP = EPI_WARPS + 1, GATHER_WARP0 = EPI_WARPS + 2;
 constexpr int THREADS_TMA = (EPI_WARPS + 2) * 32, THREADS_GATHER = (EPI_WARPS + 6) * 32;
+constexpr int ACC_CHUNK = 4;         // split mode: k-blocks (of 64) per tensor-core accumulation chain
 constexpr int SMEM_LIMIT = 232448;   // 227 KiB opt-in maximum per CTA
 
 template <int BN, bool SPLIT>
@@ -378,35 +379,41 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             constexpr uint32_t idesc = f16_idesc(BM, BN);
-            int it = 0, local = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
-                const int a = local & 1;
-                mbar_wait(acce_bar(a), ((local >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
-                for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
-                    const int s = it % G::STAGES;
-                    mbar_wait(full_bar(s), (it / G::STAGES) & 1);
+            int it = 0, acc_it = 0;                     // k-block and accumulator-stage counters (across tiles)
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                // The tensor core truncates (rounds toward zero) when it adds to the fp32 accumulator, a bias that grows
+                // with the length of the chain.  Split mode therefore accumulates at most `chunk` k-blocks per TMEM
+                // stage and lets the epilogue warps add the chunks in registers with round-to-nearest.
+                for (int kb0 = 0; kb0 < p.kb_total; kb0 += p.chunk, ++acc_it) {
+                    const int a = acc_it & 1;
+                    mbar_wait(acce_bar(a), ((acc_it >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_base + s * G::STAGE;
-                    const uint32_t b_hi = a_hi + G::PLANES * A_TILE;
-                    const bool main_block = kb < p.kb_main;     // residual blocks multiply by (identity * f): the W_lo term is zero
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+                    const int kb1 = min(kb0 + p.chunk, p.kb_total);
+                    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                        const int s = it % G::STAGES;
+                        mbar_wait(full_bar(s), (it / G::STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_base + s * G::STAGE;
+                        const uint32_t b_hi = a_hi + G::PLANES * A_TILE;
+                        const bool main_block = kb < p.kb_main;     // residual blocks multiply by (identity * f): the W_lo term is zero
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = sw128_desc(a_hi + k * 32), db = sw128_desc(b_hi + k * 32);
-                        tc_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
-                        if (SPLIT) {
-                            const uint64_t dal = sw128_desc(a_hi + A_TILE + k * 32);
-                            tc_mma_f16(d_tmem, dal, db, idesc, 1);
-                            if (main_block) {
-                                const uint64_t dbl = sw128_desc(b_hi + G::B_TILE + k * 32);
-                                tc_mma_f16(d_tmem, da, dbl, idesc, 1);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t da = sw128_desc(a_hi + k * 32), db = sw128_desc(b_hi + k * 32);
+                            tc_mma_f16(d_tmem, da, db, idesc, (kb > kb0) || (k != 0));
+                            if (SPLIT) {
+                                const uint64_t dal = sw128_desc(a_hi + A_TILE + k * 32);
+                                tc_mma_f16(d_tmem, dal, db, idesc, 1);
+                                if (main_block) {
+                                    const uint64_t dbl = sw128_desc(b_hi + G::B_TILE + k * 32);
+                                    tc_mma_f16(d_tmem, da, dbl, idesc, 1);
+                                }
                             }
                         }
+                        tc_commit(empty_bar(s));          // smem slot reusable once these MMAs retire
                     }
-                    tc_commit(empty_bar(s));          // smem slot reusable once these MMAs retire
+                    tc_commit(accf_bar(a));               // chunk complete -> epilogue
                 }
-                tc_commit(accf_bar(a));               // accumulator complete -> epilogue
             }
         }
     } else {
@@ -419,10 +426,10 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         const bool leader = (threadIdx.x & 127) == 0;         // issues this group's TMA stores
         const int row = quarter * 32 + lane;
         const uint32_t buf = staging + (uint32_t)group * (2 * G::SLAB_PLANE);   // one staging slab (hi | lo) per group
-        int local = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+        constexpr int MINE = (NSLAB + 1) / 2;         // slabs per group
+        int acc_it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const TileCoord tc = tile_coord<GATHER>(p, tile);
-            const int a = local & 1;
             bool valid;
             int n, oy, ox;
             if (GATHER) {
@@ -437,28 +444,52 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                 oy = qy * p.out_mul + p.ph_oy[tc.phase];
                 ox = qx * p.out_mul + p.ph_ox[tc.phase];
             }
-            mbar_wait(accf_bar(a), (local >> 1) & 1);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN);
-#pragma unroll 1
-            for (int cc = group; cc < NSLAB; cc += 2) {
-                const int cbase = tc.nt * BN + cc * SLAB;
-                uint32_t v[SLAB];
-                if constexpr (SLAB == 64) {
-                    TMEM_LD_32(t_row + cc * SLAB, v);
-                    TMEM_LD_32(t_row + cc * SLAB + 32, (v + 32));
-                } else if constexpr (SLAB == 32) {
-                    TMEM_LD_32(t_row + cc * SLAB, v);
+            // ---- drain the accumulator chunks of this tile into registers (fp32, round-to-nearest adds) ----
+            uint32_t acc[MINE * SLAB];
+            for (int kb0 = 0; kb0 < p.kb_total; kb0 += p.chunk, ++acc_it) {
+                const int a = acc_it & 1;
+                mbar_wait(accf_bar(a), (acc_it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN);
+                if (kb0 == 0) {
+#pragma unroll
+                    for (int j = 0; j < MINE; ++j) {
+                        const int cc = group + 2 * j;
+                        if (cc < NSLAB) {
+                            if constexpr (SLAB == 32) {
+                                TMEM_LD_32(t_row + cc * SLAB, (acc + j * SLAB));
+                            } else {
+                                TMEM_LD_16(t_row + cc * SLAB, (acc + j * SLAB));
+                            }
+                        }
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 } else {
-                    TMEM_LD_16(t_row + cc * SLAB, v);
+#pragma unroll
+                    for (int j = 0; j < MINE; ++j) {
+                        const int cc = group + 2 * j;
+                        if (cc < NSLAB) {
+                            uint32_t v[SLAB];
+                            if constexpr (SLAB == 32) {
+                                TMEM_LD_32(t_row + cc * SLAB, v);
+                            } else {
+                                TMEM_LD_16(t_row + cc * SLAB, v);
+                            }
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int i = 0; i < SLAB; ++i) acc[j * SLAB + i] = __float_as_uint(__uint_as_float(acc[j * SLAB + i]) + __uint_as_float(v[i]));
+                        }
+                    }
                 }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cc + 2 >= NSLAB) {
-                    // this thread's last read of the accumulator stage: hand TMEM back to the MMA warp
-                    tc_fence_before();
-                    mbar_arrive(acce_bar(a));
-                }
-                if (cbase >= p.cout_p8) continue;    // whole slab is channel padding (uniform across the group)
+                tc_fence_before();
+                mbar_arrive(acce_bar(a));             // this thread is done with the TMEM stage
+            }
+            // ---- finalize: scale/shift, activation, split, store ----
+#pragma unroll
+            for (int j = 0; j < MINE; ++j) {
+                const int cc = group + 2 * j;
+                const int cbase = tc.nt * BN + cc * SLAB;
+                if (cc >= NSLAB || cbase >= p.cout_p8) continue;    // no such slab / whole slab is channel padding (uniform across the group)
                 float o[SLAB];
 #pragma unroll
                 for (int g8 = 0; g8 < SLAB / 8; ++g8) {
@@ -469,7 +500,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                         const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
                         const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) o[g8 * 8 + k] = apply_act(fmaf(__uint_as_float(v[g8 * 8 + k]), scv[k], shv[k]), p.act, p.slope);
+                        for (int k = 0; k < 8; ++k) o[g8 * 8 + k] = apply_act(fmaf(__uint_as_float(acc[j * SLAB + g8 * 8 + k]), scv[k], shv[k]), p.act, p.slope);
                         if (p.out_f32 && valid) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k)
@@ -508,10 +539,6 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                         bulk_commit();
                     }
                 }
-            }
-            if (group >= NSLAB) {                     // BN = 16: a single slab, group 1 only releases the accumulator
-                tc_fence_before();
-                mbar_arrive(acce_bar(a));
             }
         }
         if (leader) bulk_wait_all();                  // every output byte has left shared memory and is globally visible
@@ -749,6 +776,7 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     FT_REQUIRE(d->res_blocks == res_blocks, "conv2d: the weight image carries %d residual k-blocks per tile, this call needs %d (residual %s, block_n %d)",
                d->res_blocks, res_blocks, d->res.hi ? "given" : "absent", BN);
     k.kb_total = k.kb_main + res_blocks;
+    k.chunk = (split && k.kb_total > ACC_CHUNK) ? ACC_CHUNK : k.kb_total;   // k-blocks accumulated per TMEM stage (see the MMA warp)
     const int slab = BN >= 64 ? 32 : 16;
 
     if (gather) {
