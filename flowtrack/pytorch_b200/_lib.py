@@ -29,6 +29,7 @@ KIND_CONV, KIND_DECONV = 0, 1
 PREC_SPLIT, PREC_FAST = 0, 1
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
 K_PACKED, K_TAP64, K_ROW = 0, 1, 2
+ABI_VERSION = 3        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
 
 # name -> (restype, argtypes): every symbol include/flowtrack_b200.h declares
 SIGNATURES = {
@@ -69,7 +70,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)        # AttributeError if the symbol is missing
             fn.restype, fn.argtypes = res, args
-        if l.ft_sizeof(0) != ctypes.sizeof(FtAct) or l.ft_sizeof(1) != ctypes.sizeof(FtConvDesc):
+        if l.ft_abi_version() != ABI_VERSION or l.ft_sizeof(0) != ctypes.sizeof(FtAct) or l.ft_sizeof(1) != ctypes.sizeof(FtConvDesc):
             raise RuntimeError("libflowtrack_b200.so struct layout differs from the ctypes binding (stale build?)")
         _lib = l
     return _lib

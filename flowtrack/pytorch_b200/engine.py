@@ -87,6 +87,10 @@ def normalise_columns(g, scale, max_exp=None):
 
 
 def choose_block_n(cout, precision=_lib.PREC_SPLIT):
+    import os
+    force = int(os.environ.get("FT_DEV_BLOCK_N", "0"))      # dev knob for tile-shape experiments (tools/dev/layer_times.py)
+    if force and cout >= force:
+        return force
     if cout >= 128:
         return 128
     if cout > 32:

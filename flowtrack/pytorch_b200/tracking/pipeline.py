@@ -61,13 +61,20 @@ class FramePairPipeline:
         self.use_cuda_graph, self.concurrent = use_cuda_graph, concurrent
         self.graph, self.launches_per_step = None, 0
         self._side = torch.cuda.Stream(device=dev)
-        # pinned staging for the host-facing call
+        # host-facing call: two slots of pinned host staging + device staging, so the host->device copy of batch i+1
+        # (copy stream) overlaps the graph replay of batch i (main stream); see submit() / collect()
         pin = dict(dtype=torch.float32, pin_memory=True)
-        self._h_pair, self._h_crops = torch.empty(self.pair.shape, **pin), torch.empty(self.crops.shape, **pin)
-        self._h_meta = torch.empty(self.n * (2 + 1 + self.num_joints * 3), **pin)
-        self._d_meta = torch.empty(self._h_meta.shape, **f32)
-        self._h_out = torch.empty(self.n * (self.num_joints * 3 + 4), **pin)
-        self._d_out = torch.empty(self._h_out.shape, **f32)
+        n_meta, n_out = self.n * (2 + 1 + self.num_joints * 3), self.n * (self.num_joints * 3 + 4)
+        self._slots = []
+        for _ in range(2):
+            self._slots.append(dict(
+                h_pair=torch.empty(self.pair.shape, **pin), h_crops=torch.empty(self.crops.shape, **pin), h_meta=torch.empty(n_meta, **pin),
+                h_out=torch.empty(n_out, **pin),
+                d_pair=torch.empty(self.pair.shape, **f32), d_crops=torch.empty(self.crops.shape, **f32), d_meta=torch.empty(n_meta, **f32),
+                d_out=torch.empty(n_out, **f32),
+                copied=torch.cuda.Event(), done=torch.cuda.Event(), consumed=torch.cuda.Event(), busy=False))
+        self._copy = torch.cuda.Stream(device=dev)
+        self._next = 0
 
     # ---- device-side step ------------------------------------------------------------------------------
     def _enqueue(self):
@@ -115,38 +122,76 @@ class FramePairPipeline:
     # ---- host-facing step --------------------------------------------------------------------------------
     @property
     def h2d_bytes(self):
-        return 4 * (self._h_pair.numel() + self._h_crops.numel() + self._h_meta.numel())
+        sl = self._slots[0]
+        return 4 * (sl["h_pair"].numel() + sl["h_crops"].numel() + sl["h_meta"].numel())
 
     @property
     def d2h_bytes(self):
-        return 4 * self._h_out.numel()
+        return 4 * self._slots[0]["h_out"].numel()
 
-    @torch.no_grad()
-    def process(self, pairs, crops, centers, scales, prev_keypoints):
-        """Host tensors in, host tensors out: pairs [pairs,3,2,H,W] (RGB 0..255), crops [pairs*people,3,h,w], centers
-        [n,2], scales [n], prev_keypoints [n,K,3] (all fp32) -> (keypoints [n,K,3], boxes [n,4]) CPU tensors."""
-        n, K = self.n, self.num_joints
-        self._h_pair.copy_(pairs)
-        self._h_crops.copy_(crops)
-        m = self._h_meta
+    def stage(self, pairs, crops, centers, scales, prev_keypoints, slot=None):
+        """Fill the pinned host staging buffers of a slot (the next one by default) with one batch; returns the slot index.
+        pairs [pairs,3,2,H,W] (RGB 0..255), crops [n,3,h,w], centers [n,2], scales [n], prev_keypoints [n,K,3] (fp32)."""
+        k = self._next if slot is None else slot
+        sl, n = self._slots[k], self.n
+        if sl["busy"]:
+            raise RuntimeError("slot %d still holds an uncollected batch" % k)
+        sl["h_pair"].copy_(pairs)
+        sl["h_crops"].copy_(crops)
+        m = sl["h_meta"]
         m[:2 * n].copy_(torch.as_tensor(centers, dtype=torch.float32).reshape(-1))
         m[2 * n:3 * n].copy_(torch.as_tensor(scales, dtype=torch.float32).reshape(-1))
         m[3 * n:].copy_(torch.as_tensor(prev_keypoints, dtype=torch.float32).reshape(-1))
-        return self.process_staged()
+        return k
 
     @torch.no_grad()
-    def process_staged(self):
-        """The timed part of process(): pinned host staging buffers -> device, one step, results -> pinned host."""
-        n, K = self.n, self.num_joints
-        self.pair.copy_(self._h_pair, non_blocking=True)
-        self.crops.copy_(self._h_crops, non_blocking=True)
-        self._d_meta.copy_(self._h_meta, non_blocking=True)
-        self.centers.copy_(self._d_meta[:2 * n].view(n, 2))
-        self.scales.copy_(self._d_meta[2 * n:3 * n])
-        self.prev_kps.copy_(self._d_meta[3 * n:].view(n, K, 3))
+    def submit(self, slot=None):
+        """Enqueue one batch from a staged slot: pinned host -> device on the copy stream, then (main stream) move it into
+        the graph's static inputs, replay, and send the results back to the slot's pinned output.  Returns the slot index;
+        nothing blocks the host, so the copy-in of the next submit() overlaps this batch's kernels."""
+        k = self._next if slot is None else slot
+        sl, n, K = self._slots[k], self.n, self.num_joints
+        if sl["busy"]:
+            raise RuntimeError("slot %d still holds an uncollected batch: collect() it first" % k)
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy):
+            self._copy.wait_event(sl["consumed"])            # the previous batch of this slot has left the device staging
+            sl["d_pair"].copy_(sl["h_pair"], non_blocking=True)
+            sl["d_crops"].copy_(sl["h_crops"], non_blocking=True)
+            sl["d_meta"].copy_(sl["h_meta"], non_blocking=True)
+            sl["copied"].record(self._copy)
+        main.wait_event(sl["copied"])
+        self.pair.copy_(sl["d_pair"])
+        self.crops.copy_(sl["d_crops"])
+        self.centers.copy_(sl["d_meta"][:2 * n].view(n, 2))
+        self.scales.copy_(sl["d_meta"][2 * n:3 * n])
+        self.prev_kps.copy_(sl["d_meta"][3 * n:].view(n, K, 3))
+        sl["consumed"].record(main)
         self.step_device()
-        self._d_out[:n * K * 3].copy_(self.keypoints.view(-1))
-        self._d_out[n * K * 3:].copy_(self.boxes.view(-1))
-        self._h_out.copy_(self._d_out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return self._h_out[:n * K * 3].view(n, K, 3), self._h_out[n * K * 3:].view(n, 4)
+        sl["d_out"][:n * K * 3].copy_(self.keypoints.view(-1))
+        sl["d_out"][n * K * 3:].copy_(self.boxes.view(-1))
+        sl["h_out"].copy_(sl["d_out"], non_blocking=True)
+        sl["done"].record(main)
+        sl["busy"] = True
+        self._next = k ^ 1
+        return k
+
+    def collect(self, slot):
+        """Wait for a submitted batch; returns (keypoints [n,K,3], boxes [n,4]) as views of the slot's pinned host buffer
+        (valid until the slot is staged again)."""
+        sl, n, K = self._slots[slot], self.n, self.num_joints
+        if not sl["busy"]:
+            raise RuntimeError("slot %d has no batch in flight" % slot)
+        sl["done"].synchronize()
+        sl["busy"] = False
+        return sl["h_out"][:n * K * 3].view(n, K, 3), sl["h_out"][n * K * 3:].view(n, 4)
+
+    @torch.no_grad()
+    def process(self, pairs, crops, centers, scales, prev_keypoints):
+        """Host tensors in, host tensors out (one synchronous batch): stage -> submit -> collect."""
+        return self.collect(self.submit(self.stage(pairs, crops, centers, scales, prev_keypoints)))
+
+    @torch.no_grad()
+    def process_staged(self, slot=None):
+        """The synchronous timed part of process(): pinned host staging buffers -> device, one step, results -> pinned host."""
+        return self.collect(self.submit(slot))
