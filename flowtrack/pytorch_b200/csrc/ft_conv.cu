@@ -147,6 +147,58 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // waits for arrivals that may come from the peer CTA
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` (same offset) in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; both operands K-major, fp16 in, fp32 accumulate
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -196,16 +248,18 @@ constexpr int THREADS_TMA = (EPI_WARPS + 2) * 32, THREADS_GATHER = (EPI_WARPS + 
 constexpr int ACC_CHUNK = 4;         // split mode: k-blocks (of 64) per tensor-core accumulation chain
 constexpr int SMEM_LIMIT = 232448;   // 227 KiB opt-in maximum per CTA
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool PAIR = false>
 struct Geo {
     static constexpr int PLANES = SPLIT ? 2 : 1;
-    static constexpr int B_TILE = BN * BK * 2;
-    static constexpr int STAGE = PLANES * (A_TILE + B_TILE);
+    static constexpr int B_TILE = BN * BK * 2;                     // whole weight k-block of the n-tile (one plane)
+    static constexpr int B_LOCAL = PAIR ? B_TILE / 2 : B_TILE;     // pair: each CTA stages its half of the BN rows
+    static constexpr int STAGE = PLANES * (A_TILE + B_LOCAL);
     // epilogue staging slab: SLAB output channels x 128 pixels x 2 planes, double buffered
     static constexpr int SLAB = BN >= 64 ? 32 : 16;
     static constexpr int SLAB_PLANE = BM * SLAB * 2;
     static constexpr int STAGING = 2 * 2 * SLAB_PLANE;
     static constexpr int FIXED = 1024 /*align slack*/ + 512 /*barriers*/ + STAGING;
+    static_assert(STAGE % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
     static constexpr int STAGES_FIT = (SMEM_LIMIT - FIXED) / STAGE;
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int LAG = STAGES >= 3 ? 2 : 1;       // gather variant: cp.async groups a producer keeps in flight
@@ -218,13 +272,19 @@ struct TileCoord {
     int phase, mt, nt;
     int qx0, qy0, n0;    // TMA variant: origin of the pixel box
 };
-template <bool GATHER>
-__device__ __forceinline__ TileCoord tile_coord(const ConvK& p, int tile) {
+template <bool GATHER, bool PAIR = false>
+__device__ __forceinline__ TileCoord tile_coord(const ConvK& p, int tile, int cta_rank = 0) {
     TileCoord t;
     t.nt = tile % p.n_tiles;               // consecutive CTAs share the A tile (L2 reuse), differ in weights
     const int r = tile / p.n_tiles;
-    t.mt = r % p.m_tiles;
-    t.phase = r / p.m_tiles;
+    if (PAIR) {                            // a pair tile = two consecutive m-tiles (one per CTA) x one n-tile
+        const int mp = (p.m_tiles + 1) >> 1;
+        t.mt = (r % mp) * 2 + cta_rank;    // may be == m_tiles for the odd tail: an all-padding box (zero loads, clipped stores)
+        t.phase = r / mp;
+    } else {
+        t.mt = r % p.m_tiles;
+        t.phase = r / p.m_tiles;
+    }
     if (GATHER) {
         t.qx0 = t.mt * BM, t.qy0 = 0, t.n0 = 0;   // linear pixel index; the output map is [C, M]
     } else {
@@ -236,19 +296,30 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvK& p, int tile) {
     return t;
 }
 
-template <int BN, bool SPLIT, bool GATHER>
+// PAIR: two CTAs of a cluster (the two SMs of a TPC) work on one 256-pixel x BN tile with tcgen05.mma.cta_group::2:
+// each CTA stages its own 128 pixel rows of A and HALF of the BN weight rows, the tensor cores of both SMs read both
+// halves, and each CTA's TMEM receives its 128 rows of the result.  Per MMA cycle a CTA then needs half the weight
+// bytes -- the main loop of the single-CTA variant is bound by shared-memory fill bandwidth (~48 B/clk/SM measured),
+// not by the tensor pipe.  CTA rank 0 (the leader) issues every MMA; the peer's MMA warp only relays "my stage is
+// full" to the leader.
+template <int BN, bool SPLIT, bool GATHER, bool PAIR>
 __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv_tc_kernel(const __grid_constant__ ConvK p) {
-    using G = Geo<BN, SPLIT>;
+    static_assert(!(GATHER && PAIR), "the gather variant is single-CTA");
+    using G = Geo<BN, SPLIT, PAIR>;
+    const int cta_rank = PAIR ? (int)cluster_ctarank() : 0;
+    const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // pair: a cluster owns a tile
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t staging = smem_base + G::STAGES * G::STAGE;         // 1024-aligned (STAGE is a multiple of 1024)
     const uint32_t bar_base = staging + G::STAGING;
-    // barrier slots (8 bytes each): full[STAGES] | empty[STAGES] | acc_full[2] | acc_empty[2] | tmem ptr
+    // barrier slots (8 bytes each): full[STAGES] | empty[STAGES] | acc_full[2] | acc_empty[2] | tmem ptr | peer_full[STAGES]
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (G::STAGES + s); };
     auto accf_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + a); };
     auto acce_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * G::STAGES + 4);
+    auto peer_full_bar = [&](int s) { return bar_base + 8u * (2 * G::STAGES + 5 + s); };   // leader only: the peer's stage s is full
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -259,16 +330,24 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(accf_bar(a), 1);
-            mbar_init(acce_bar(a), EPI_THREADS);
+            mbar_init(acce_bar(a), PAIR ? 2 * EPI_THREADS : EPI_THREADS);   // pair: the epilogue threads of both CTAs release the stage
         }
+        if (PAIR)
+            for (int s = 0; s < G::STAGES; ++s) mbar_init(peer_full_bar(s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)G::TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)G::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)G::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();          // both CTAs' barriers exist before any cross-CTA arrive / multicast commit
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -277,9 +356,10 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         // =========================== TMA producer ===========================
         if (!GATHER && lane == 0) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const TileCoord tc = tile_coord<false>(p, tile);
-                const uint8_t* wsrc = p.w_tile + ((size_t)(tc.phase * p.n_tiles + tc.nt) * p.kb_total) * (size_t)(2 * G::B_TILE);
+            for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+                const TileCoord tc = tile_coord<false, PAIR>(p, tile, cta_rank);
+                // weight image: per (phase, n_tile, k_block) [hi | lo][BN rows][64]; a pair CTA copies rows [rank*BN/2, +BN/2) of each plane
+                const uint8_t* wsrc = p.w_tile + ((size_t)(tc.phase * p.n_tiles + tc.nt) * p.kb_total) * (size_t)(2 * G::B_TILE) + (size_t)cta_rank * G::B_LOCAL;
                 int tap = 0, cblk = 0;
                 for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
                     const int s = it % G::STAGES;
@@ -304,7 +384,12 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                         tma_load_4d(stage, &p.res_map[0], full_bar(s), c0, tc.qx0, tc.qy0, tc.n0);
                         if (SPLIT) tma_load_4d(stage + A_TILE, &p.res_map[1], full_bar(s), c0, tc.qx0, tc.qy0, tc.n0);
                     }
-                    bulk_g2s(stage + G::PLANES * A_TILE, wsrc + (size_t)kb * (2 * G::B_TILE), G::PLANES * G::B_TILE, full_bar(s));
+                    if (PAIR) {
+                        bulk_g2s(stage + G::PLANES * A_TILE, wsrc + (size_t)kb * (2 * G::B_TILE), G::B_LOCAL, full_bar(s));
+                        if (SPLIT) bulk_g2s(stage + G::PLANES * A_TILE + G::B_LOCAL, wsrc + (size_t)kb * (2 * G::B_TILE) + G::B_TILE, G::B_LOCAL, full_bar(s));
+                    } else {
+                        bulk_g2s(stage + G::PLANES * A_TILE, wsrc + (size_t)kb * (2 * G::B_TILE), G::PLANES * G::B_TILE, full_bar(s));
+                    }
                 }
             }
         }
@@ -377,22 +462,24 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         }
     } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            constexpr uint32_t idesc = f16_idesc(BM, BN);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = f16_idesc(PAIR ? 2 * BM : BM, BN);
             int it = 0, acc_it = 0;                     // k-block and accumulator-stage counters (across tiles)
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
                 // The tensor core truncates (rounds toward zero) when it adds to the fp32 accumulator, a bias that grows
                 // with the length of the chain.  Split mode therefore accumulates at most `chunk` k-blocks per TMEM
                 // stage and lets the epilogue warps add the chunks in registers with round-to-nearest.
                 for (int kb0 = 0; kb0 < p.kb_total; kb0 += p.chunk, ++acc_it) {
                     const int a = acc_it & 1;
-                    mbar_wait(acce_bar(a), ((acc_it >> 1) & 1) ^ 1);
+                    if (PAIR) mbar_wait_cluster(acce_bar(a), ((acc_it >> 1) & 1) ^ 1);
+                    else mbar_wait(acce_bar(a), ((acc_it >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
                     const int kb1 = min(kb0 + p.chunk, p.kb_total);
                     for (int kb = kb0; kb < kb1; ++kb, ++it) {
                         const int s = it % G::STAGES;
                         mbar_wait(full_bar(s), (it / G::STAGES) & 1);
+                        if (PAIR) mbar_wait_cluster(peer_full_bar(s), (it / G::STAGES) & 1);
                         tc_fence_after();
                         const uint32_t a_hi = smem_base + s * G::STAGE;
                         const uint32_t b_hi = a_hi + G::PLANES * A_TILE;
@@ -400,21 +487,36 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint64_t da = sw128_desc(a_hi + k * 32), db = sw128_desc(b_hi + k * 32);
-                            tc_mma_f16(d_tmem, da, db, idesc, (kb > kb0) || (k != 0));
+                            const uint32_t accum = (kb > kb0) || (k != 0);
+                            if (PAIR) tc_mma_f16_pair(d_tmem, da, db, idesc, accum);
+                            else tc_mma_f16(d_tmem, da, db, idesc, accum);
                             if (SPLIT) {
                                 const uint64_t dal = sw128_desc(a_hi + A_TILE + k * 32);
-                                tc_mma_f16(d_tmem, dal, db, idesc, 1);
+                                if (PAIR) tc_mma_f16_pair(d_tmem, dal, db, idesc, 1);
+                                else tc_mma_f16(d_tmem, dal, db, idesc, 1);
                                 if (main_block) {
-                                    const uint64_t dbl = sw128_desc(b_hi + G::B_TILE + k * 32);
-                                    tc_mma_f16(d_tmem, da, dbl, idesc, 1);
+                                    const uint64_t dbl = sw128_desc(b_hi + G::B_LOCAL + k * 32);
+                                    if (PAIR) tc_mma_f16_pair(d_tmem, da, dbl, idesc, 1);
+                                    else tc_mma_f16(d_tmem, da, dbl, idesc, 1);
                                 }
                             }
                         }
-                        tc_commit(empty_bar(s));          // smem slot reusable once these MMAs retire
+                        if (PAIR) tc_commit_pair(empty_bar(s));   // smem slot reusable in BOTH CTAs once these MMAs retire
+                        else tc_commit(empty_bar(s));
                     }
-                    tc_commit(accf_bar(a));               // chunk complete -> epilogue
+                    if (PAIR) tc_commit_pair(accf_bar(a));        // chunk complete -> both CTAs' epilogues
+                    else tc_commit(accf_bar(a));
                 }
             }
+        } else if (PAIR && lane == 0) {
+            // peer CTA: tell the leader's MMA thread when this CTA's half of a stage has landed
+            int it = 0;
+            for (int tile = first_tile; tile < p.num_tiles; tile += tile_step)
+                for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
+                    const int s = it % G::STAGES;
+                    mbar_wait(full_bar(s), (it / G::STAGES) & 1);
+                    mbar_arrive_remote(map_to_cta(peer_full_bar(s), 0));
+                }
         }
     } else {
         // =========================== epilogue (warps 0-7) ===========================
@@ -428,8 +530,9 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         const uint32_t buf = staging + (uint32_t)group * (2 * G::SLAB_PLANE);   // one staging slab (hi | lo) per group
         constexpr int MINE = (NSLAB + 1) / 2;         // slabs per group
         int acc_it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const TileCoord tc = tile_coord<GATHER>(p, tile);
+        const uint32_t acce_remote0 = PAIR ? map_to_cta(acce_bar(0), 0) : 0u;     // the leader's acc_empty barriers, as cluster addresses
+        for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+            const TileCoord tc = tile_coord<GATHER, PAIR>(p, tile, cta_rank);
             bool valid;
             int n, oy, ox;
             if (GATHER) {
@@ -482,7 +585,8 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(acce_bar(a));             // this thread is done with the TMEM stage
+                if (PAIR) mbar_arrive_remote(acce_remote0 + 8u * a);   // leader's barrier counts the epilogue threads of both CTAs
+                else mbar_arrive(acce_bar(a));        // this thread is done with the TMEM stage
             }
             // ---- finalize: scale/shift, activation, split, store ----
 #pragma unroll
@@ -545,9 +649,11 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();          // neither CTA may leave (or free TMEM) while its peer can still touch its smem / barriers
     if (warp == MMA_WARP) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G::TMEM_COLS) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G::TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G::TMEM_COLS) : "memory");
     }
 }
 
@@ -593,21 +699,37 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvK p) {
     }
 }
 
-template <int BN, bool SPLIT, bool GATHER>
+template <int BN, bool SPLIT, bool GATHER, bool PAIR>
 static int launch_tc(const ConvK& k, cudaStream_t s) {
-    using G = Geo<BN, SPLIT>;
+    using G = Geo<BN, SPLIT, PAIR>;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, GATHER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         if (e != cudaSuccess) {
-            set_error("conv_tc_kernel<%d,%d,%d>: cannot opt in to %d B of shared memory: %s", BN, (int)SPLIT, (int)GATHER, G::SMEM, cudaGetErrorString(e));
+            set_error("conv_tc_kernel<%d,%d,%d,%d>: cannot opt in to %d B of shared memory: %s", BN, (int)SPLIT, (int)GATHER, (int)PAIR, G::SMEM, cudaGetErrorString(e));
             return 1;
         }
         attr_set = true;
     }
     const int sms = 148;
+    if (PAIR) {
+        // one cluster of two CTAs (the two SMs of a TPC) per tile; k.num_tiles already counts pair tiles
+        const int clusters = k.num_tiles < sms / 2 ? k.num_tiles : sms / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(THREADS_TMA), cfg.dynamicSmemBytes = G::SMEM, cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, GATHER, PAIR>, k);
+        if (e != cudaSuccess) {
+            set_error("conv_tc_kernel<%d,%d,pair>: cluster launch failed: %s", BN, (int)SPLIT, cudaGetErrorString(e));
+            return 1;
+        }
+        return check_launch("conv_tc_kernel(pair)");
+    }
     const int grid = k.num_tiles < sms ? k.num_tiles : sms;
-    conv_tc_kernel<BN, SPLIT, GATHER><<<grid, GATHER ? THREADS_GATHER : THREADS_TMA, G::SMEM, s>>>(k);
+    conv_tc_kernel<BN, SPLIT, GATHER, PAIR><<<grid, GATHER ? THREADS_GATHER : THREADS_TMA, G::SMEM, s>>>(k);
     return check_launch("conv_tc_kernel");
 }
 
@@ -839,19 +961,27 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
                 if (int e = make_map(&k.res_map[1], k.res_lo + k.res_coff, dim, str, abox, 128, "res.lo")) return e;
         }
     }
-    k.num_tiles = k.n_phase * k.m_tiles * k.n_tiles;
+    const bool pair = d->cta_pair != 0;
+    FT_REQUIRE(!pair || (!gather && BN >= 64), "conv2d: cta_pair needs the TMA variant and block_n >= 64");
+    k.num_tiles = k.n_phase * (pair ? (k.m_tiles + 1) / 2 : k.m_tiles) * k.n_tiles;
 
-#define FT_CASE(BN_)                                                                                             \
-    case BN_:                                                                                                    \
-        if (gather) return split ? launch_tc<BN_, true, true>(k, s) : launch_tc<BN_, false, true>(k, s);         \
-        return split ? launch_tc<BN_, true, false>(k, s) : launch_tc<BN_, false, false>(k, s);
+#define FT_CASE(BN_)                                                                                                          \
+    case BN_:                                                                                                                 \
+        if (gather) return split ? launch_tc<BN_, true, true, false>(k, s) : launch_tc<BN_, false, true, false>(k, s);        \
+        return split ? launch_tc<BN_, true, false, false>(k, s) : launch_tc<BN_, false, false, false>(k, s);
+#define FT_CASE_PAIR(BN_)                                                                                                     \
+    case BN_:                                                                                                                 \
+        if (pair) return split ? launch_tc<BN_, true, false, true>(k, s) : launch_tc<BN_, false, false, true>(k, s);          \
+        if (gather) return split ? launch_tc<BN_, true, true, false>(k, s) : launch_tc<BN_, false, true, false>(k, s);        \
+        return split ? launch_tc<BN_, true, false, false>(k, s) : launch_tc<BN_, false, false, false>(k, s);
     switch (BN) {
         FT_CASE(16)
         FT_CASE(32)
-        FT_CASE(64)
-        FT_CASE(128)
-        FT_CASE(256)
+        FT_CASE_PAIR(64)
+        FT_CASE_PAIR(128)
+        FT_CASE_PAIR(256)
     }
 #undef FT_CASE
+#undef FT_CASE_PAIR
     return 0;
 }

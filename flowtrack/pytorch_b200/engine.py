@@ -86,6 +86,18 @@ def normalise_columns(g, scale, max_exp=None):
     return g * f[None, None, :], (scale / f).astype(np.float32), f
 
 
+def box_tiles(qw, qh, n):
+    """Number of 128-pixel box tiles ft_conv2d_fprop cuts an n x qh x qw output grid into (mirror of choose_box in ft_conv.cu)."""
+    best = None
+    for lw in range(7, -1, -1):
+        for lh in range(7 - lw, -1, -1):
+            w, h = 1 << lw, 1 << lh
+            t = -(-qw // w) * -(-qh // h) * -(-n // (128 // (w * h)))
+            if best is None or t < best:
+                best = t
+    return best
+
+
 def choose_block_n(cout, precision=_lib.PREC_SPLIT):
     import os
     force = int(os.environ.get("FT_DEV_BLOCK_N", "0"))      # dev knob for tile-shape experiments (tools/dev/layer_times.py)
@@ -210,10 +222,11 @@ class ConvLayer:
             g = gemm_weights_conv_rows(weight, self.cin_p)
         else:
             g = gemm_weights_conv(weight, self.cin_k) if kind == _lib.KIND_CONV else gemm_weights_deconv(weight, self.cin_k)
-        self.block_n = block_n or choose_block_n(self.cout)
-        self.cout_pad = round_up(self.cout, self.block_n)
+        self.block_n = block_n or choose_block_n(self.cout)                    # default tile width (single-CTA tiles)
+        # cout is padded so that every tile width the scheduler may pick (64 / 128 / 256) divides it
+        self.cout_pad = round_up(self.cout, 256 if (self.cout > 128 and block_n is None) else self.block_n)
         self.k_pad = g.shape[1]
-        self.res_blocks = -(-self.block_n // BK) if residual else 0
+        self.res_blocks = -(-self.block_n // BK) if residual else 0            # of the default tile image
         gp = np.zeros((g.shape[0], self.k_pad, self.cout_pad), np.float32)
         sc = np.zeros(self.cout_pad, np.float32)
         sh = np.zeros(self.cout_pad, np.float32)
@@ -223,13 +236,54 @@ class ConvLayer:
             gp = (gp.astype(np.float64) * sc.astype(np.float64)[None, None, :]).astype(np.float32)
             sc = np.where(np.arange(self.cout_pad) < self.cout, 1.0, 0.0).astype(np.float32)
         gp, sc, f = normalise_columns(gp, sc, max_exp=14 if residual else None)
-        res_f = np.where(sc != 0, f, 0.0) if residual else None
+        self._res_f = np.where(sc != 0, f, 0.0) if residual else None
+        self._gp = gp                                                          # host fp32 GEMM weights: tile images are cut from it on demand
+        self._tiles = {}                                                       # block_n -> device tile image
+        self.device = device
         self.host = dict(w_gemm=gp, scale=sc, shift=sh) if keep_host else None
-        self.w_tile_host = tile_weights(gp, self.block_n, res_f) if keep_host else None
+        self.w_tile_host = tile_weights(gp, self.block_n, self._res_f) if keep_host else None
         if device is not None:
             self.w_gemm = torch.from_numpy(gp).to(device)
-            self.w_tile = torch.from_numpy(self.w_tile_host if keep_host else tile_weights(gp, self.block_n, res_f)).to(device)
             self.scale, self.shift = torch.from_numpy(sc).to(device), torch.from_numpy(sh).to(device)
+
+    def tile_image(self, block_n):
+        """Device tile image of the weights for tiles `block_n` channels wide (built once per width)."""
+        if block_n not in self._tiles:
+            assert self.cout_pad % block_n == 0
+            self._tiles[block_n] = torch.from_numpy(tile_weights(self._gp, block_n, self._res_f)).to(self.device)
+        return self._tiles[block_n]
+
+    def choose_tiling(self, n, h, w, precision=_lib.PREC_SPLIT):
+        """(block_n, cta_pair) for an n x h x w input: a small cycle model of the kernel -- per k-block a CTA needs
+        max(tensor-pipe cycles, operand bytes / measured smem-fill bandwidth), tiles run in waves over 148 SMs (74 CTA
+        pairs) -- evaluated for single-CTA tiles of the default width and CTA-pair tiles 64/128/256 wide."""
+        import os
+        ho, wo = (h, w) if self.kind == _lib.KIND_DECONV else self.out_hw(h, w)
+        phases = 4 if self.kind == _lib.KIND_DECONV else 1
+        if self.k_mode == _lib.K_PACKED:
+            return self.block_n, 0
+        m_tiles = box_tiles(wo, ho, n)
+        split = precision == _lib.PREC_SPLIT
+        kb = self.k_pad // BK
+        fill_bw = 46.0                                     # bytes / clk / SM into shared memory (measured, profiles/)
+        best = None
+        cands = [(self.block_n, 0)] + [(b, 1) for b in (64, 128, 256) if b <= self.cout_pad and self.cout_pad % b == 0 and b >= min(self.block_n, 64)]
+        force = os.environ.get("FT_DEV_PAIR")              # dev knob: "0" = never pair, "1" = always pair when legal
+        if force == "0" or self.block_n < 64:
+            cands = cands[:1]
+        elif force == "1" and len(cands) > 1:
+            cands = cands[1:]
+        for bn, pair in cands:
+            kbt = kb + (-(-bn // BK) if self.residual else 0)
+            mma = (12 if split else 4) * bn / 2.0
+            byts = (2 if split else 1) * (16384 + bn * 128 / (2 if pair else 1))
+            per_tile = max(kbt * max(mma, byts / fill_bw), 14.0 * bn + 600.0) + 400.0
+            tiles = phases * (-(-m_tiles // 2) if pair else m_tiles) * (self.cout_pad // bn)
+            waves = -(-tiles // (74 if pair else 148))
+            cost = waves * per_tile
+            if best is None or cost < best[0] * 0.97:      # prefer the earlier (simpler) candidate on near-ties
+                best = (cost, bn, pair)
+        return best[1], best[2]
 
     def out_hw(self, h, w):
         if self.kind == _lib.KIND_DECONV:
@@ -243,7 +297,8 @@ class ConvLayer:
         ho, wo = self.out_hw(h, w)
         return 2 * n * ho * wo * self.cin * self.cout * self.kh * self.kw
 
-    def desc(self, x, out=None, out_f32=None, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05):
+    def desc(self, x, out=None, out_f32=None, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05, tiling=None):
+        """`tiling` = (block_n, cta_pair); default: choose_tiling() for this input shape."""
         assert x.c == self.cin_p, "input view has %d channels, layer expects %d" % (x.c, self.cin_p)
         assert (res is not None) == self.residual, "layer was packed %s residual blocks" % ("with" if self.residual else "without")
         assert (x.xl, x.xr) == self.in_xpad, "layer expects input rows padded by %s zero columns, view has %s" % (self.in_xpad, (x.xl, x.xr))
@@ -252,12 +307,13 @@ class ConvLayer:
         d.out = out.struct() if out is not None else NULL_ACT
         d.res = res.struct() if res is not None else NULL_ACT
         d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
-        d.w_tile, d.w_gemm = self.w_tile.data_ptr(), self.w_gemm.data_ptr()
+        bn, pair = tiling if tiling is not None else self.choose_tiling(x.n, x.h, x.w, precision)
+        d.w_tile, d.w_gemm = self.tile_image(bn).data_ptr(), self.w_gemm.data_ptr()
         d.scale, d.shift = self.scale.data_ptr(), self.shift.data_ptr()
         d.kind, d.kh, d.kw, d.stride, d.pad = self.kind, self.kh, self.kw, self.stride, self.pad
-        d.cout, d.cout_pad, d.k_pad, d.block_n = self.cout, self.cout_pad, self.k_pad, self.block_n
+        d.cout, d.cout_pad, d.k_pad, d.block_n = self.cout, self.cout_pad, self.k_pad, bn
         d.act, d.slope, d.precision, d.impl = self.act, self.slope, precision, impl
-        d.k_mode, d.res_blocks = self.k_mode, self.res_blocks
+        d.k_mode, d.res_blocks, d.cta_pair = self.k_mode, (-(-bn // BK) if self.residual else 0), pair
         d.in_xpad_l, d.in_xpad_r = x.xl, x.xr
         return d
 

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 3
+#define FT_ABI_VERSION 4
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -100,6 +100,8 @@ typedef struct {
     int32_t k_mode;         /* FT_K_*: K layout of w_gemm / w_tile                                 */
     int32_t in_xpad_l;      /* the rows of `in` physically start with in_xpad_l and end with in_xpad_r */
     int32_t in_xpad_r;      /* zero pixels: in.w counts them, the image is in.w - l - r wide (0/0 normally) */
+    int32_t cta_pair;       /* != 0: run 256-pixel x block_n tiles on CTA pairs (tcgen05 cta_group::2, clusters of 2);
+                               needs FT_K_TAP64 / FT_K_ROW and block_n >= 64                          */
     int32_t res_blocks;     /* residual k-blocks appended to every (phase, n_tile) of w_tile:
                                ceil(block_n/64) when the layer is called with a residual, else 0.
                                Block j holds diag(f) for channels [64j, 64j+64) of the tile, where

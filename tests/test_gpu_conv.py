@@ -158,3 +158,46 @@ def test_stem_packed_gather_variant_still_matches():
         xa = gpu_util.pack_nchw(x.cuda(), 8, xpad=layer.in_xpad)
         outs.append(gpu_util.run_layer(layer, xa).to_nchw(64).cpu())
         assert (outs[-1] - ref).abs().max() <= 2e-5 * ref.abs().max()
+
+
+PAIR_CASES = [
+    # name, module ctor, input shape, act, residual
+    ("1x1_256_128", lambda: nn.Conv2d(256, 128, 1, bias=False), (3, 256, 16, 12), _lib.ACT_RELU, False),       # 5 m-tiles: odd tail pair
+    ("3x3_128_256", lambda: nn.Conv2d(128, 256, 3, 1, 1), (2, 128, 32, 24), _lib.ACT_LEAKY, False),
+    ("3x3_s2_128_256", lambda: nn.Conv2d(128, 256, 3, 2, 1), (3, 128, 16, 12), _lib.ACT_RELU, False),
+    ("l4_3x3_batch", lambda: nn.Conv2d(256, 512, 3, 1, 1, bias=False), (11, 256, 8, 6), _lib.ACT_RELU, False),
+    ("deconv_256", lambda: nn.ConvTranspose2d(512, 256, 4, 2, 1, bias=False), (4, 512, 8, 6), _lib.ACT_RELU, False),
+    ("expand_res", lambda: nn.Conv2d(64, 256, 1, bias=False), (5, 64, 16, 12), _lib.ACT_RELU, True),
+    ("cin776_deconv", lambda: nn.ConvTranspose2d(770, 128, 4, 2, 1), (1, 770, 12, 16), _lib.ACT_LEAKY, False),
+    ("cout64", lambda: nn.Conv2d(64, 64, 3, 1, 1, bias=False), (2, 64, 32, 24), _lib.ACT_RELU, False),
+]
+
+
+@pytest.mark.parametrize("name,ctor,shape,act,residual", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("prec,tol", [(_lib.PREC_SPLIT, 2e-5), (_lib.PREC_FAST, 3e-3)], ids=["split", "fast"])
+def test_conv_cta_pair_tiles(name, ctor, shape, act, residual, bn, prec, tol):
+    """tcgen05 cta_group::2 tiles (two CTAs per 256-pixel x bn tile) against torch, every legal tile width."""
+    torch.manual_seed(len(name) * 7 + bn)
+    mod = ctor().double()
+    x = torch.randn(*shape, dtype=torch.float64)
+    with torch.no_grad():
+        ref = mod(x)
+    layer = engine.conv_from_modules(mod.float(), None, act, device="cuda", residual=residual)
+    if layer.cout_pad % bn:
+        pytest.skip("tile width does not divide the padded channel count")
+    xa = gpu_util.pack_nchw(x.float().cuda(), layer.cin_p)
+    ra = None
+    with torch.no_grad():
+        if residual:
+            r = torch.randn(shape[0], layer.cout, shape[2], shape[3], dtype=torch.float64)
+            ref = ref + r
+            ra = gpu_util.pack_nchw(r.float().cuda())
+        ref = (torch.relu(ref) if act == _lib.ACT_RELU else (F.leaky_relu(ref, 0.1) if act == _lib.ACT_LEAKY else ref)).float()
+    out, f32 = gpu_util.run_layer(layer, xa, res=ra, precision=prec, want_f32=True, tiling=(bn, 1))
+    got = out.to_nchw(layer.cout).cpu()
+    scale = max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max() <= tol * scale, (got - ref).abs().max().item()
+    assert (f32.cpu() - ref).abs().max() <= tol * scale
+    single = gpu_util.run_layer(layer, xa, res=ra, precision=prec, tiling=(layer.block_n, 0)).to_nchw(layer.cout).cpu()
+    assert (got - single).abs().max() <= (2e-6 if prec == _lib.PREC_SPLIT else 1e-5) * scale     # same arithmetic, different tiling
