@@ -64,6 +64,7 @@ struct alignas(64) ConvK {
     int res_ld, res_coff;
     int in_stride, out_mul;
     int n_phase, taps, cb, kb_main, kb_total, k_pad, chunk;
+    int dbg_skip;   // bring-up/profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no weight loads, 4 = no MMAs (results are garbage)
     int M, m_tiles, n_tiles, num_tiles;
     int bw, bh, bn, lg_bw, lg_bh, tiles_w, tiles_h;
     int act;
@@ -164,14 +165,16 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default .release.cta semantics: the hand-offs made with it carry no generic-proxy data (TMEM reads / TMA-written smem
+    // consumed by the tensor core); a cluster-scope release would cost a MEMBAR.ALL.GPU per arrive
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"   /* default scope: .acquire.cluster would add a CCTL.IVALL per wait */
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
@@ -365,8 +368,10 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                     const int s = it % G::STAGES;
                     mbar_wait(empty_bar(s), ((it / G::STAGES) & 1) ^ 1);
                     const uint32_t stage = smem_base + s * G::STAGE;
-                    mbar_arrive_expect_tx(full_bar(s), (uint32_t)G::STAGE);
-                    if (kb < p.kb_main) {
+                    const bool ldA = !(p.dbg_skip & 1), ldB = !(p.dbg_skip & 2);
+                    mbar_arrive_expect_tx(full_bar(s), (uint32_t)((ldA ? G::PLANES * A_TILE : 0) + (ldB ? G::PLANES * G::B_LOCAL : 0)));
+                    if (!ldA) {
+                    } else if (kb < p.kb_main) {
                         // FT_K_ROW: k-block `tap` is kernel row tap (all kw taps of it, contiguous in the x-padded input)
                         const int dy = p.row_mode ? tap - p.pad : p.tap_dy[tc.phase][tap], dx = p.row_mode ? 0 : p.tap_dx[tc.phase][tap];
                         int view = 0, cx = tc.qx0 + dx, cy = tc.qy0 + dy;
@@ -384,7 +389,8 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                         tma_load_4d(stage, &p.res_map[0], full_bar(s), c0, tc.qx0, tc.qy0, tc.n0);
                         if (SPLIT) tma_load_4d(stage + A_TILE, &p.res_map[1], full_bar(s), c0, tc.qx0, tc.qy0, tc.n0);
                     }
-                    if (PAIR) {
+                    if (!ldB) {
+                    } else if (PAIR) {
                         bulk_g2s(stage + G::PLANES * A_TILE, wsrc + (size_t)kb * (2 * G::B_TILE), G::B_LOCAL, full_bar(s));
                         if (SPLIT) bulk_g2s(stage + G::PLANES * A_TILE + G::B_LOCAL, wsrc + (size_t)kb * (2 * G::B_TILE) + G::B_TILE, G::B_LOCAL, full_bar(s));
                     } else {
@@ -486,6 +492,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                         const bool main_block = kb < p.kb_main;     // residual blocks multiply by (identity * f): the W_lo term is zero
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
+                            if (p.dbg_skip & 4) break;
                             const uint64_t da = sw128_desc(a_hi + k * 32), db = sw128_desc(b_hi + k * 32);
                             const uint32_t accum = (kb > kb0) || (k != 0);
                             if (PAIR) tc_mma_f16_pair(d_tmem, da, db, idesc, accum);
@@ -898,7 +905,10 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     FT_REQUIRE(d->res_blocks == res_blocks, "conv2d: the weight image carries %d residual k-blocks per tile, this call needs %d (residual %s, block_n %d)",
                d->res_blocks, res_blocks, d->res.hi ? "given" : "absent", BN);
     k.kb_total = k.kb_main + res_blocks;
-    k.chunk = (split && k.kb_total > ACC_CHUNK) ? ACC_CHUNK : k.kb_total;   // k-blocks accumulated per TMEM stage (see the MMA warp)
+    if (const char* e = getenv("FT_DEV_SKIP")) k.dbg_skip = atoi(e);
+    int acc_chunk = ACC_CHUNK;
+    if (const char* e = getenv("FT_DEV_CHUNK")) acc_chunk = atoi(e) > 0 ? atoi(e) : ACC_CHUNK;   // dev knob (tools/dev/conv_bench.py)
+    k.chunk = (split && k.kb_total > acc_chunk) ? acc_chunk : k.kb_total;   // k-blocks accumulated per TMEM stage (see the MMA warp)
     const int slab = BN >= 64 ? 32 : 16;
 
     if (gather) {

@@ -254,36 +254,17 @@ class ConvLayer:
         return self._tiles[block_n]
 
     def choose_tiling(self, n, h, w, precision=_lib.PREC_SPLIT):
-        """(block_n, cta_pair) for an n x h x w input: a small cycle model of the kernel -- per k-block a CTA needs
-        max(tensor-pipe cycles, operand bytes / measured smem-fill bandwidth), tiles run in waves over 148 SMs (74 CTA
-        pairs) -- evaluated for single-CTA tiles of the default width and CTA-pair tiles 64/128/256 wide."""
+        """(block_n, cta_pair) for an n x h x w input.  Measured on B200 (profiles/r01c_conv_tilings.txt): single-CTA tiles
+        of the default width win or tie everywhere in split mode -- the main loop is bound by the tensor pipe's own
+        shared-memory reads (128x128x16 MMAs need 128 B/clk of smem bandwidth), and CTA-pair 256-wide tiles only gain
+        ~10 % on the largest layers when accumulation is not chunked -- so pairs stay opt-in (FT_DEV_PAIR=1 picks the
+        widest legal pair tile) until the chunk drain of 256-column accumulators is cheaper."""
         import os
-        ho, wo = (h, w) if self.kind == _lib.KIND_DECONV else self.out_hw(h, w)
-        phases = 4 if self.kind == _lib.KIND_DECONV else 1
-        if self.k_mode == _lib.K_PACKED:
-            return self.block_n, 0
-        m_tiles = box_tiles(wo, ho, n)
-        split = precision == _lib.PREC_SPLIT
-        kb = self.k_pad // BK
-        fill_bw = 46.0                                     # bytes / clk / SM into shared memory (measured, profiles/)
-        best = None
-        cands = [(self.block_n, 0)] + [(b, 1) for b in (64, 128, 256) if b <= self.cout_pad and self.cout_pad % b == 0 and b >= min(self.block_n, 64)]
-        force = os.environ.get("FT_DEV_PAIR")              # dev knob: "0" = never pair, "1" = always pair when legal
-        if force == "0" or self.block_n < 64:
-            cands = cands[:1]
-        elif force == "1" and len(cands) > 1:
-            cands = cands[1:]
-        for bn, pair in cands:
-            kbt = kb + (-(-bn // BK) if self.residual else 0)
-            mma = (12 if split else 4) * bn / 2.0
-            byts = (2 if split else 1) * (16384 + bn * 128 / (2 if pair else 1))
-            per_tile = max(kbt * max(mma, byts / fill_bw), 14.0 * bn + 600.0) + 400.0
-            tiles = phases * (-(-m_tiles // 2) if pair else m_tiles) * (self.cout_pad // bn)
-            waves = -(-tiles // (74 if pair else 148))
-            cost = waves * per_tile
-            if best is None or cost < best[0] * 0.97:      # prefer the earlier (simpler) candidate on near-ties
-                best = (cost, bn, pair)
-        return best[1], best[2]
+        if os.environ.get("FT_DEV_PAIR") == "1" and self.k_mode != _lib.K_PACKED and self.block_n >= 64:
+            for b in (256, 128, 64):
+                if b <= self.cout_pad and self.cout_pad % b == 0:
+                    return b, 1
+        return self.block_n, 0
 
     def out_hw(self, h, w):
         if self.kind == _lib.KIND_DECONV:
