@@ -1,0 +1,35 @@
+"""max_preds / final_preds with the reference signatures (lib/pose/utils/evaluation.py:11-35), computed by
+ft_decode_keypoints on the GPU (no CPU path: heat-maps must be CUDA tensors)."""
+import numpy as np
+import torch
+
+from ...tracking.net_utils import final_preds_cuda
+
+
+def _as_dev(a, dev):
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(dev)
+
+
+def max_preds(heatmaps):
+    """evaluation.py:11-20: heat-maps CUDA fp32 [N,C,h,w] -> (coords [N,C,2] float in heat-map pixels, scores [N,C,1]).
+    y = idx // w (torch-0.4 integer division semantics); coordinates are zeroed where score <= 0."""
+    if not heatmaps.is_cuda:
+        raise RuntimeError("max_preds: heat-maps must be CUDA tensors (there is no CPU path)")
+    N, C, h, w = heatmaps.shape
+    # identity transform: scale = h  ->  s = 1, centre = (w/2, h/2)
+    centers = torch.tensor([[0.5 * w, 0.5 * h]], device=heatmaps.device, dtype=torch.float32).repeat(N, 1)
+    scales = torch.full((N,), float(h), device=heatmaps.device, dtype=torch.float32)
+    out = final_preds_cuda(heatmaps.contiguous().float(), centers, scales, adjust_coords=False)
+    return out[:, :, :2].clone(), out[:, :, 2:3].clone()
+
+
+def final_preds(heatmaps, center, scale, adjust_coords=True):
+    """evaluation.py:22-35: heat-maps CUDA fp32 [N,C,h,w], center [N,2], scale [N] (tensors or arrays)
+    -> (preds ndarray [N,C,2] in image pixels, scores ndarray [N,C,1])."""
+    if not heatmaps.is_cuda:
+        raise RuntimeError("final_preds: heat-maps must be CUDA tensors (there is no CPU path)")
+    dev = heatmaps.device
+    c = center.to(dev).float().contiguous() if torch.is_tensor(center) else _as_dev(center, dev)
+    s = scale.to(dev).float().contiguous() if torch.is_tensor(scale) else _as_dev(scale, dev)
+    out = final_preds_cuda(heatmaps.contiguous().float(), c.reshape(-1, 2), s.reshape(-1), adjust_coords).cpu().numpy()
+    return out[:, :, :2].astype(np.float64), out[:, :, 2:3]
