@@ -293,32 +293,56 @@ def run_ours(args):
 
 
 def bench_correlation(torch, _lib, peaks):
-    """FlowNetC correlation at BASELINE config 3: two [32,256,48,64] fp32 maps -> [32,441,48,64]; algorithmic bytes =
-    inputs once + output once = 11.71 MB per pair."""
+    """FlowNetC correlation at BASELINE config 3: two [32,256,48,64] maps -> [32,441,48,64] fp32; algorithmic bytes =
+    inputs once + output once at 4 B per element = 11.71 MB per pair.  Headline = the tcgen05 banded-GEMM
+    kernel on the conv stack's split-fp16 NHWC activations (hi+lo = 4 B per element, the layout it reads inside FlowNetC);
+    also timed: the same kernel behind the reference's fp32 NCHW signature (re-layout into the scratch buffer + kernel)
+    and the CUDA-core kernel."""
+    from flowtrack.pytorch_b200 import engine
     B, C, H, W = 32, 256, 48, 64
     g = torch.Generator(device="cuda").manual_seed(0)
     a = torch.randn(B, C, H, W, device="cuda", generator=g)
     b = torch.randn(B, C, H, W, device="cuda", generator=g)
     o = torch.empty(B, 441, H, W, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    fn = lambda: _lib.check(_lib.lib().ft_correlation_forward(a.data_ptr(), b.data_ptr(), o.data_ptr(), B, C, H, W, 20, 1, 20, 1, 2, 1,
-                                                             torch.cuda.current_stream().cuda_stream), "correlation")
-    for _ in range(3):
-        fn()
-    ts = []
-    for _ in range(10):
-        flush.zero_()                                    # evict the inputs from L2 between iterations
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ms = statistics.median(ts)
+    L = _lib.lib()
+    sp = lambda: torch.cuda.current_stream().cuda_stream
+    acts = []
+    for t in (a, b):
+        act = engine.Act(B, H, W, C, "cuda")
+        st = t.stride()
+        _lib.check(L.ft_pack_image(t.data_ptr(), st[0], st[1], st[2], st[3], C, 1.0, act.struct(), 0, 0, sp()), "pack_image")
+        acts.append(act)
+    nws = L.ft_correlation_workspace_bytes(B, C, H, W)
+    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    fns = {
+        "tcgen05": lambda: _lib.check(L.ft_correlation_act(acts[0].struct(), acts[1].struct(), o.data_ptr(), 1, _lib.PREC_SPLIT, sp()), "correlation_act"),
+        "tcgen05_fast": lambda: _lib.check(L.ft_correlation_act(acts[0].struct(), acts[1].struct(), o.data_ptr(), 1, _lib.PREC_FAST, sp()), "correlation_act"),
+        "tcgen05_nchw_abi": lambda: _lib.check(L.ft_correlation_forward_ws(a.data_ptr(), b.data_ptr(), o.data_ptr(), B, C, H, W, 20, 1, 20, 1, 2, 1,
+                                                                           _lib.PREC_SPLIT, ws.data_ptr(), nws, sp()), "correlation_ws"),
+        "simt": lambda: _lib.check(L.ft_correlation_forward(a.data_ptr(), b.data_ptr(), o.data_ptr(), B, C, H, W, 20, 1, 20, 1, 2, 1, sp()), "correlation"),
+    }
+    res = {}
+    for name, fn in fns.items():
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10 if name != "simt" else 3):
+            flush.zero_()                                    # evict the inputs from L2 between iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        res[name] = statistics.median(ts)
+    ms = res["tcgen05"]
     byts = (2 * B * C * H * W + B * 441 * H * W) * 4
     ach = byts / (ms * 1e-3) / 1e9
-    return {"kernel": "corr kernel, [32,256,48,64]x2 -> [32,441,48,64] fp32, L2 flushed between launches", "bound": "hbm", "achieved": ach,
-            "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "ms": ms, "algorithmic_bytes": byts, "gflop": 2 * B * 441 * C * H * W / 1e9}
+    return {"kernel": "corr_tc_kernel (tcgen05 banded GEMM, split-fp16 NHWC [32,48,64,256] x2 -> fp32 NCHW [32,441,48,64], LeakyReLU fused), L2 flushed between launches",
+            "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "ms": ms, "algorithmic_bytes": byts,
+            "gflop": 2 * B * 441 * C * H * W / 1e9, "ms_fast_precision": res["tcgen05_fast"], "ms_fp32_nchw_abi_with_relayout": res["tcgen05_nchw_abi"],
+            "ms_cuda_core_kernel": res["simt"]}
 
 
 def main():

@@ -29,7 +29,7 @@ KIND_CONV, KIND_DECONV = 0, 1
 PREC_SPLIT, PREC_FAST = 0, 1
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
 K_PACKED, K_TAP64, K_ROW = 0, 1, 2
-ABI_VERSION = 4        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
+ABI_VERSION = 5        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
 
 # name -> (restype, argtypes): every symbol include/flowtrack_b200.h declares
 SIGNATURES = {
@@ -40,13 +40,17 @@ SIGNATURES = {
     "ft_reset_launch_count": (None, []),
     "ft_correlation_shape": (c_int, [c_int] * 7 + [ctypes.POINTER(c_int)] * 3),
     "ft_correlation_forward": (c_int, [c_void_p] * 3 + [c_int] * 10 + [c_void_p]),
+    "ft_correlation_tc_supported": (c_int, [c_int] * 8),
+    "ft_correlation_act": (c_int, [ctypes.POINTER(FtAct)] * 2 + [c_void_p, c_int, c_int, c_void_p]),
+    "ft_correlation_workspace_bytes": (ctypes.c_size_t, [c_int] * 4),
+    "ft_correlation_forward_ws": (c_int, [c_void_p] * 3 + [c_int] * 11 + [c_void_p, ctypes.c_size_t, c_void_p]),
     "ft_resample2d_forward": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "ft_channelnorm_forward": (c_int, [c_void_p] * 2 + [c_int] * 4 + [c_void_p]),
     "ft_conv2d_fprop": (c_int, [ctypes.POINTER(FtConvDesc), c_void_p]),
     "ft_maxpool3x3s2": (c_int, [ctypes.POINTER(FtAct)] * 2 + [c_void_p]),
-    "ft_pack_image": (c_int, [c_void_p] + [c_ll] * 4 + [c_int, c_float, ctypes.POINTER(FtAct), c_void_p]),
+    "ft_pack_image": (c_int, [c_void_p] + [c_ll] * 4 + [c_int, c_float, ctypes.POINTER(FtAct), c_int, c_int, c_void_p]),
     "ft_pack_pair_ws_floats": (c_int, [c_int]),
-    "ft_pack_pair": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, ctypes.POINTER(FtAct), c_void_p]),
+    "ft_pack_pair": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, ctypes.POINTER(FtAct), c_int, c_int, c_void_p]),
     "ft_upsample4x": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_float, c_int, c_void_p]),
     "ft_warp_concat": (c_int, [c_void_p, c_void_p, c_float, c_int, c_int, c_int, ctypes.POINTER(FtAct), c_void_p]),
     "ft_fusion_concat": (c_int, [c_void_p] * 3 + [c_int] * 3 + [ctypes.POINTER(FtAct), c_void_p]),

@@ -1,0 +1,326 @@
+// ft_corr.cu -- the FlowNetC cost volume (Correlation: pad 20, kernel 1, max displacement 20, stride1 1,
+// stride2 2; reference: correlation_package/src/correlation_cuda_kernel.cu:34-106) as a banded GEMM on the
+// tcgen05 tensor cores.  sm_100a only.
+//
+//   out[n, (tj+10)*21 + (ti+10), y, x] = 1/C * sum_c in1[n,c,y,x] * in2[n,c,y+2tj,x+2ti]     (zero outside the image)
+//
+// Because stride2 = 2, pixel (y,x) only ever meets pixels of its own row/column parity.  Each of the four parity
+// classes (py,px) is therefore an independent stride-1 correlation (displacements |tj|,|ti| <= 10) between the
+// sub-images in1' = in1[:, py::2, px::2] and in2' likewise ([H/2, W/2] pixels of C channels).  A work tile is
+//   (image n, parity class, 4 rows a0..a0+3 of in1')  =  128 pixels x C channels  -> the GEMM's A operand (M = 128),
+// and it needs in2' rows a0-10 .. a0+13: they are streamed as "chunks" of 4 rows x 32 columns = 128 pixels (N = 128):
+//   D[128 x 128] = A . B^T  (K = C), the all-pairs dot products of the 128 in1' pixels with the 128 in2' pixels;
+//   the 21-wide diagonal band |b2 - b| <= 10 of every (row a, row a+tj) block is the wanted output, the rest is dropped
+//   (useful fraction about 2/3 x 21/32; the operands are read ONCE from HBM and re-read from L2).
+// Operands are the split-fp16 NHWC activations of the conv stack (float = hi + lo), read through one TMA tensor map
+// per parity class (pixel strides doubled), so no thread ever computes an operand address; products are
+// A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (fp32-grade, FT_PREC_SPLIT) or A_hi*B_hi (FT_PREC_FAST), accumulated in TMEM.
+//
+// CTA = 10 warps, persistent over tiles:
+//   warp 9  TMA   : per (chunk, 64-channel k-block) one stage = A box + B box (hi and lo planes), 3 stages of 64 KiB
+//   warp 8  MMA   : one thread, tcgen05.mma.cta_group::1.kind::f16 M=128 N=128 K=16; one TMEM accumulator stage
+//                   (128 columns) per chunk, 4 stages in flight
+//   warps 0-7 epilogue: warp (q, h) owns TMEM lanes 32q.. (= in1' row a0+q, lane = column b) and chunk rows 2h, 2h+1.
+//                   tcgen05.ld 32 columns (one in2' row) -> per-warp smem slab S[b][b2] -> lane b reads the band
+//                   S[b][b+ti], scales by 1/C, LeakyReLU, and stores out[n, ch, 2a+py, 2b+px] (fp32 NCHW).
+#include <cuda.h>
+
+#include "ft_tc.cuh"
+
+namespace ft {
+
+constexpr int CD = 10;                 // displacement radius in parity-class pixels (max_displacement 20 / stride2 2)
+constexpr int CDS = 2 * CD + 1;        // 21
+constexpr int CORR_BM = 128, CORR_BN = 128, CORR_BK = 64;
+constexpr int CORR_TILE = CORR_BM * CORR_BK * 2;      // 16 KiB: one operand plane of one k-block
+constexpr int CORR_ROWS = 4, CORR_COLS = 32;          // pixel box of a tile / chunk
+constexpr int CORR_EPI_WARPS = 8;
+constexpr int CORR_THREADS = (CORR_EPI_WARPS + 2) * 32;
+constexpr int CORR_ACC_STAGES = 4;                    // x 128 TMEM columns = all 512
+constexpr int CORR_SLAB = 32 * 33 * 4;                // per epilogue warp: S[32][33] floats
+
+template <bool SPLIT>
+struct CorrGeo {
+    static constexpr int PLANES = SPLIT ? 2 : 1;
+    static constexpr int STAGE = 2 * PLANES * CORR_TILE;           // A + B
+    static constexpr int STAGES = SPLIT ? 3 : 6;
+    static constexpr int SMEM = 1024 + STAGES * STAGE + CORR_EPI_WARPS * CORR_SLAB + 512;
+    static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+struct alignas(64) CorrK {
+    CUtensorMap a_map[4][2];     // [parity class][hi, lo] of in1
+    CUtensorMap b_map[4][2];     // of in2
+    float* out;
+    int B, H, W, C, kb;
+    int a_tiles, num_tiles;
+    float inv;
+    int leaky;
+};
+
+struct CorrTile {
+    int n, cls, py, px, a0, H2c, r_lo, chunks;
+};
+__device__ __forceinline__ CorrTile corr_tile(const CorrK& p, int tile) {
+    CorrTile t;
+    const int at = tile % p.a_tiles, r = tile / p.a_tiles;     // consecutive CTAs share the in2' sub-image through L2
+    t.cls = r & 3, t.n = r >> 2;
+    t.py = t.cls >> 1, t.px = t.cls & 1;
+    t.a0 = at * CORR_ROWS;
+    t.H2c = (p.H - t.py + 1) >> 1;
+    t.r_lo = max(0, t.a0 - CD);
+    const int r_end = min(t.H2c, t.a0 + CORR_ROWS + CD);
+    t.chunks = r_end > t.r_lo ? (r_end - t.r_lo + CORR_ROWS - 1) / CORR_ROWS : 0;
+    return t;
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_constant__ CorrK p) {
+    using G = CorrGeo<SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t slabs = smem_base + G::STAGES * G::STAGE;
+    const uint32_t bar_base = slabs + CORR_EPI_WARPS * CORR_SLAB;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (G::STAGES + s); };
+    auto accf_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + a); };
+    auto acce_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + CORR_ACC_STAGES + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * G::STAGES + 2 * CORR_ACC_STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < CORR_ACC_STAGES; ++a) {
+            mbar_init(accf_bar(a), 1);
+            mbar_init(acce_bar(a), CORR_EPI_WARPS * 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == CORR_EPI_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == CORR_EPI_WARPS + 1) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const CorrTile t = corr_tile(p, tile);
+                for (int j = 0; j < t.chunks; ++j) {
+                    const int r0 = t.r_lo + j * CORR_ROWS;
+                    for (int kb = 0; kb < p.kb; ++kb, ++it) {
+                        const int s = it % G::STAGES;
+                        mbar_wait(empty_bar(s), ((it / G::STAGES) & 1) ^ 1);
+                        const uint32_t stage = smem_base + s * G::STAGE;
+                        mbar_arrive_expect_tx(full_bar(s), (uint32_t)G::STAGE);
+                        tma_load_4d(stage, &p.a_map[t.cls][0], full_bar(s), kb * CORR_BK, 0, t.a0, t.n);
+                        if (SPLIT) tma_load_4d(stage + CORR_TILE, &p.a_map[t.cls][1], full_bar(s), kb * CORR_BK, 0, t.a0, t.n);
+                        tma_load_4d(stage + G::PLANES * CORR_TILE, &p.b_map[t.cls][0], full_bar(s), kb * CORR_BK, 0, r0, t.n);
+                        if (SPLIT) tma_load_4d(stage + G::PLANES * CORR_TILE + CORR_TILE, &p.b_map[t.cls][1], full_bar(s), kb * CORR_BK, 0, r0, t.n);
+                    }
+                }
+            }
+        }
+    } else if (warp == CORR_EPI_WARPS) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            constexpr uint32_t idesc = f16_idesc(CORR_BM, CORR_BN);
+            int it = 0, acc_it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const CorrTile t = corr_tile(p, tile);
+                for (int j = 0; j < t.chunks; ++j, ++acc_it) {
+                    const int a = acc_it % CORR_ACC_STAGES;
+                    mbar_wait(acce_bar(a), ((acc_it / CORR_ACC_STAGES) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(a * CORR_BN);
+                    for (int kb = 0; kb < p.kb; ++kb, ++it) {
+                        const int s = it % G::STAGES;
+                        mbar_wait(full_bar(s), (it / G::STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_base + s * G::STAGE;
+                        const uint32_t b_hi = a_hi + G::PLANES * CORR_TILE;
+#pragma unroll
+                        for (int k = 0; k < CORR_BK / 16; ++k) {
+                            const uint64_t da = sw128_desc(a_hi + k * 32), db = sw128_desc(b_hi + k * 32);
+                            tc_mma_f16(d_tmem, da, db, idesc, (kb > 0) || (k != 0));
+                            if (SPLIT) {
+                                tc_mma_f16(d_tmem, sw128_desc(a_hi + CORR_TILE + k * 32), db, idesc, 1);
+                                tc_mma_f16(d_tmem, da, sw128_desc(b_hi + CORR_TILE + k * 32), idesc, 1);
+                            }
+                        }
+                        tc_commit(empty_bar(s));
+                    }
+                    tc_commit(accf_bar(a));
+                }
+            }
+        }
+    } else {
+        // =========================== epilogue (warps 0-7) ===========================
+        const int q = warp & 3, h = warp >> 2;
+        float* S = reinterpret_cast<float*>(smem_raw + (slabs - smem_u32(smem_raw))) + warp * (32 * 33);
+        const size_t plane = (size_t)p.H * p.W;
+        int acc_it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const CorrTile t = corr_tile(p, tile);
+            const int a = t.a0 + q;
+            const int y = 2 * a + t.py, x = 2 * lane + t.px;
+            const bool valid = y < p.H && x < p.W;
+            float* o = p.out + (size_t)t.n * (CDS * CDS) * plane + (size_t)y * p.W + x;
+            // displacement rows that fall outside the image: the correlation is zero there (never visited by a chunk)
+            for (int tj = -CD + h; tj <= CD; tj += 2) {
+                const int row = a + tj;
+                if (row >= 0 && row < t.H2c) continue;
+                if (valid) {
+#pragma unroll
+                    for (int ti = 0; ti < CDS; ++ti) o[(size_t)((tj + CD) * CDS + ti) * plane] = 0.f;
+                }
+            }
+            for (int j = 0; j < t.chunks; ++j, ++acc_it) {
+                const int as = acc_it % CORR_ACC_STAGES;
+                const int r0 = t.r_lo + j * CORR_ROWS;
+                mbar_wait(accf_bar(as), (acc_it / CORR_ACC_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * CORR_BN);
+                uint32_t v0[32], v1[32];
+                const int row0 = r0 + 2 * h, row1 = row0 + 1;
+                const int tj0 = row0 - a, tj1 = row1 - a;
+                const bool use0 = tj0 >= -CD && tj0 <= CD && row0 < t.H2c;     // warp-uniform
+                const bool use1 = tj1 >= -CD && tj1 <= CD && row1 < t.H2c;
+                if (use0) TMEM_LD_32(t_row + (2 * h) * 32, v0);
+                if (use1) TMEM_LD_32(t_row + (2 * h + 1) * 32, v1);
+                if (use0 || use1) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(acce_bar(as));                  // this thread is done with the TMEM stage
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const bool use = rr ? use1 : use0;
+                    if (!use) continue;
+                    const int tj = rr ? tj1 : tj0;
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) S[lane * 33 + c] = __uint_as_float(rr ? v1[c] : v0[c]);
+                    __syncwarp();
+                    if (valid) {
+                        float* oc = o + (size_t)((tj + CD) * CDS) * plane;
+#pragma unroll
+                        for (int ti = 0; ti < CDS; ++ti) {
+                            const int b2 = lane + ti - CD;
+                            float val = (b2 >= 0 && b2 < 32) ? S[lane * 33 + b2] : 0.f;   // columns >= W/2 were zero-filled by TMA
+                            val *= p.inv;
+                            if (p.leaky) val = val > 0.f ? val : 0.1f * val;
+                            oc[(size_t)ti * plane] = val;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == CORR_EPI_WARPS) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+template <bool SPLIT>
+static int launch_corr(const CorrK& k, cudaStream_t s) {
+    using G = CorrGeo<SPLIT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(corr_tc_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e != cudaSuccess) {
+            set_error("corr_tc_kernel<%d>: cannot opt in to %d B of shared memory: %s", (int)SPLIT, G::SMEM, cudaGetErrorString(e));
+            return 1;
+        }
+        attr_set = true;
+    }
+    const int grid = k.num_tiles < 148 ? k.num_tiles : 148;
+    corr_tc_kernel<SPLIT><<<grid, CORR_THREADS, G::SMEM, s>>>(k);
+    return check_launch("corr_tc_kernel");
+}
+
+static int check_corr_view(const ft_act& a, const char* name, bool split) {
+    FT_REQUIRE(a.hi && (!split || a.lo), "%s: null plane", name);
+    FT_REQUIRE(a.c % 8 == 0 && a.ld % 8 == 0 && a.coff % 8 == 0 && a.coff + a.c <= a.ld, "%s: c/ld/coff must be multiples of 8 (c=%d ld=%d coff=%d)", name, a.c, a.ld, a.coff);
+    FT_REQUIRE(((uintptr_t)a.hi & 15) == 0 && ((uintptr_t)a.lo & 15) == 0, "%s: planes must be 16-byte aligned", name);
+    return 0;
+}
+
+}  // namespace ft
+
+using namespace ft;
+
+extern "C" int ft_correlation_tc_supported(int C, int H, int W, int pad, int ksize, int max_disp, int stride1, int stride2) {
+    return pad == 20 && ksize == 1 && max_disp == 20 && stride1 == 1 && stride2 == 2 && C % 64 == 0 && C >= 64 && C <= 256 && H >= 1 && W >= 1 &&
+           (W + 1) / 2 <= CORR_COLS;
+}
+
+extern "C" int ft_correlation_act(const ft_act* in1, const ft_act* in2, float* out, int fuse_leaky, int precision, void* stream) {
+    FT_REQUIRE(in1 && in2 && out, "correlation_act: null argument");
+    FT_REQUIRE(precision == FT_PREC_SPLIT || precision == FT_PREC_FAST, "correlation_act: bad precision %d", precision);
+    const bool split = precision == FT_PREC_SPLIT;
+    if (int e = check_corr_view(*in1, "correlation_act.in1", split)) return e;
+    if (int e = check_corr_view(*in2, "correlation_act.in2", split)) return e;
+    FT_REQUIRE(in1->n == in2->n && in1->h == in2->h && in1->w == in2->w && in1->c == in2->c && in1->n > 0, "correlation_act: the two inputs differ in shape");
+    FT_REQUIRE(ft_correlation_tc_supported(in1->c, in1->h, in1->w, 20, 1, 20, 1, 2),
+               "correlation_act: the tensor-core path needs C in {64,128,192,256} and W <= 64 (got C=%d H=%d W=%d)", in1->c, in1->h, in1->w);
+    CorrK k = {};
+    k.out = out, k.B = in1->n, k.H = in1->h, k.W = in1->w, k.C = in1->c, k.kb = in1->c / CORR_BK;
+    k.inv = 1.f / (float)k.C, k.leaky = fuse_leaky != 0;
+    const int H2 = (k.H + 1) / 2;
+    k.a_tiles = ceil_div(H2, CORR_ROWS);
+    k.num_tiles = k.B * 4 * k.a_tiles;
+    const int box[4] = {CORR_BK, CORR_COLS, CORR_ROWS, 1};
+    for (int cls = 0; cls < 4; ++cls) {
+        const int py = cls >> 1, px = cls & 1;
+        if (py >= k.H || px >= k.W) {      // degenerate 1-pixel-wide/high image: the class is empty; map it onto class 0 (nothing valid is stored)
+            for (int pl = 0; pl < 2; ++pl) k.a_map[cls][pl] = k.a_map[0][pl], k.b_map[cls][pl] = k.b_map[0][pl];
+            continue;
+        }
+        for (int op = 0; op < 2; ++op) {
+            const ft_act& a = op ? *in2 : *in1;
+            const long long dim[4] = {a.c, (k.W - px + 1) / 2, (k.H - py + 1) / 2, k.B};
+            const long long str[3] = {2ll * a.ld, 2ll * k.W * a.ld, (long long)k.H * k.W * a.ld};
+            const size_t off = (size_t)(py * k.W + px) * a.ld + a.coff;
+            CUtensorMap* m = op ? k.b_map[cls] : k.a_map[cls];
+            if (int e = make_map(&m[0], (const __half*)a.hi + off, dim, str, box, 128, op ? "corr.in2.hi" : "corr.in1.hi")) return e;
+            if (split)
+                if (int e = make_map(&m[1], (const __half*)a.lo + off, dim, str, box, 128, op ? "corr.in2.lo" : "corr.in1.lo")) return e;
+        }
+    }
+    return split ? launch_corr<true>(k, (cudaStream_t)stream) : launch_corr<false>(k, (cudaStream_t)stream);
+}
+
+extern "C" size_t ft_correlation_workspace_bytes(int B, int C, int H, int W) {
+    // two split-fp16 NHWC copies of the inputs (hi and lo planes each), 256-byte aligned
+    const size_t plane = (((size_t)B * H * W * C * 2) + 255) & ~(size_t)255;
+    return 4 * plane;
+}
+
+extern "C" int ft_correlation_forward_ws(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int pad, int ksize, int max_disp,
+                                         int stride1, int stride2, int fuse_leaky, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+    FT_REQUIRE(in1 && in2 && out && B > 0 && C > 0 && H > 0 && W > 0, "correlation_ws: bad arguments");
+    if (!ft_correlation_tc_supported(C, H, W, pad, ksize, max_disp, stride1, stride2))
+        return ft_correlation_forward(in1, in2, out, B, C, H, W, pad, ksize, max_disp, stride1, stride2, fuse_leaky, stream);
+    FT_REQUIRE(workspace && ((uintptr_t)workspace & 255) == 0, "correlation_ws: the workspace must be 256-byte aligned");
+    FT_REQUIRE(workspace_bytes >= ft_correlation_workspace_bytes(B, C, H, W), "correlation_ws: workspace too small (%zu < %zu bytes)", workspace_bytes,
+               ft_correlation_workspace_bytes(B, C, H, W));
+    const size_t plane = ft_correlation_workspace_bytes(B, C, H, W) / 4;
+    ft_act a[2];
+    for (int i = 0; i < 2; ++i) {
+        a[i] = ft_act{(uint8_t*)workspace + (2 * i) * plane, (uint8_t*)workspace + (2 * i + 1) * plane, B, H, W, C, C, 0};
+        const float* src = i ? in2 : in1;
+        if (int e = ft_pack_image(src, (long long)C * H * W, (long long)H * W, W, 1, C, 1.f, &a[i], 0, 0, stream)) return e;
+    }
+    return ft_correlation_act(&a[0], &a[1], out, fuse_leaky, precision, stream);
+}

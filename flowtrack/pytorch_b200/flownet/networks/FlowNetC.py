@@ -34,12 +34,18 @@ def build(p, L, frames, B, tag=""):
     c2a = p.conv(L["conv2"], t1.view(0, 64, 0, B), cat[2].view(0, 128))             # top stream feeds concat2 (FlowNetC.py:123)
     c2b = p.conv(L["conv2"], t1.view(0, 64, B, B), p.act(B, H // 4, W // 4, 128))
     h8, w8 = H // 8, W // 8
-    a3f, b3f = p.f32(B, 256, h8, w8), p.f32(B, 256, h8, w8)
-    c3a = p.conv(L["conv3"], c2a, p.act(B, h8, w8, 256), out_f32=a3f)
-    p.conv(L["conv3"], c2b, None, out_f32=b3f)
     merged = p.act(B, h8, w8, 32 + 441, zero=True)                                  # [conv_redir(32) | corr(441 -> 448)]
     corr = p.f32(B, 441, h8, w8)
-    p.call("correlation", lib.ft_correlation_forward, a3f.data_ptr(), b3f.data_ptr(), corr.data_ptr(), B, 256, h8, w8, 20, 1, 20, 1, 2, 1)
+    if lib.ft_correlation_tc_supported(256, h8, w8, 20, 1, 20, 1, 2):
+        # tcgen05 banded GEMM straight on the split-fp16 activations of the two conv3 streams (ft_corr.cu), LeakyReLU fused
+        c3a = p.conv(L["conv3"], c2a, p.act(B, h8, w8, 256))
+        c3b = p.conv(L["conv3"], c2b, p.act(B, h8, w8, 256))
+        p.call("correlation", lib.ft_correlation_act, c3a.struct(), c3b.struct(), corr.data_ptr(), 1, p.precision)
+    else:                                                                          # frames wider than 512 px: CUDA-core kernel on fp32 copies
+        a3f, b3f = p.f32(B, 256, h8, w8), p.f32(B, 256, h8, w8)
+        c3a = p.conv(L["conv3"], c2a, p.act(B, h8, w8, 256), out_f32=a3f)
+        p.conv(L["conv3"], c2b, None, out_f32=b3f)
+        p.call("correlation", lib.ft_correlation_forward, a3f.data_ptr(), b3f.data_ptr(), corr.data_ptr(), B, 256, h8, w8, 20, 1, 20, 1, 2, 1)
     st = corr.stride()
     p.call("pack_image", lib.ft_pack_image, corr.data_ptr(), st[0], st[1], st[2], st[3], 441, 1.0, merged.view(32, 441).struct(), 0, 0)
     p.conv(L["conv_redir"], c3a, merged.view(0, 32))

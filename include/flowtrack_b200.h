@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 4
+#define FT_ABI_VERSION 5
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -124,6 +124,24 @@ int ft_correlation_shape(int H, int W, int pad, int ksize, int max_disp, int str
 int ft_correlation_forward(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
                            int pad, int ksize, int max_disp, int stride1, int stride2, int fuse_leaky,
                            void* stream);
+/* Tensor-core cost volume (ft_corr.cu) for the FlowNetC geometry (pad 20, kernel 1, max displacement 20, stride1 1,
+ * stride2 2; FlowNetC.py:33): the four stride-2 parity classes are independent stride-1 correlations, computed as
+ * banded GEMMs by tcgen05 MMAs.  ft_correlation_tc_supported() != 0 when the geometry, C (64..256, multiple of 64)
+ * and W (<= 64) fit that kernel.
+ *   ft_correlation_act        in1/in2: split-fp16 NHWC activations (the conv stack's layout) -> out: fp32 NCHW
+ *                             [B,441,H,W]; precision = FT_PREC_SPLIT (fp32-grade) | FT_PREC_FAST (fp16 operands).
+ *   ft_correlation_forward_ws the reference's signature (fp32 NCHW in, like ft_correlation_forward) plus a
+ *                             caller-owned scratch buffer -- the counterpart of the rInput1/rInput2 scratch tensors
+ *                             of Correlation_forward_cuda (correlation_cuda.c:36-42): the inputs are re-laid out
+ *                             into it (NHWC split-fp16) and ft_correlation_act runs on the copies.  Geometries the
+ *                             tensor-core kernel does not cover fall through to ft_correlation_forward.
+ *                             workspace: 256-byte aligned, >= ft_correlation_workspace_bytes(B,C,H,W).          */
+int    ft_correlation_tc_supported(int C, int H, int W, int pad, int ksize, int max_disp, int stride1, int stride2);
+int    ft_correlation_act(const ft_act* in1, const ft_act* in2, float* out, int fuse_leaky, int precision, void* stream);
+size_t ft_correlation_workspace_bytes(int B, int C, int H, int W);
+int    ft_correlation_forward_ws(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
+                                 int pad, int ksize, int max_disp, int stride1, int stride2, int fuse_leaky,
+                                 int precision, void* workspace, size_t workspace_bytes, void* stream);
 /* img: [B,C,H,W], flow: [B,2,H,W] (u,v) -> out: [B,C,H,W] */
 int ft_resample2d_forward(const float* img, const float* flow, float* out, int B, int C, int H, int W, void* stream);
 /* x: [B,C,H,W] -> out: [B,1,H,W] */

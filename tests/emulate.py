@@ -87,3 +87,69 @@ def emulate_pose(model, x):
     for dl in L["deconv"]:
         t = emulate_layer(dl, t)
     return emulate_layer(L["head"], t).permute(0, 3, 1, 2).contiguous()
+
+
+def emulate_corr_banded(in1, in2):
+    """Mirror of corr_tc_kernel's decomposition (csrc/ft_corr.cu): four parity classes, tiles of 4 rows x 32 columns of
+    in1', chunks of 4 rows x 32 columns of in2', all-pairs GEMM per (tile, chunk), 21-wide band extraction, explicit
+    zeros for displacement rows outside the image.  in1, in2: [B,C,H,W] -> [B,441,H,W] (float64 arithmetic)."""
+    B, C, H, W = in1.shape
+    assert (W + 1) // 2 <= 32
+    out = torch.full((B, 441, H, W), float("nan"), dtype=torch.float64)
+    D, ROWS, COLS = 10, 4, 32
+    H2 = (H + 1) // 2
+    for n in range(B):
+        for cls in range(4):
+            py, px = cls >> 1, cls & 1
+            a_img = in1[n, :, py::2, px::2].double()        # [C, H2c, W2c]
+            b_img = in2[n, :, py::2, px::2].double()
+            H2c, W2c = (H - py + 1) // 2, (W - px + 1) // 2
+
+            def box(img, r0):                               # TMA box {C, 32 cols from 0, 4 rows from r0}: zero fill outside
+                t = torch.zeros(C, ROWS, COLS, dtype=torch.float64)
+                for r in range(ROWS):
+                    if 0 <= r0 + r < H2c and W2c > 0:
+                        t[:, r, :W2c] = img[:, r0 + r]
+                return t.reshape(C, ROWS * COLS)            # column index = r*32 + b
+
+            for at in range((H2 + ROWS - 1) // ROWS):
+                a0 = at * ROWS
+                r_lo, r_end = max(0, a0 - D), min(H2c, a0 + ROWS + D)
+                chunks = (r_end - r_lo + ROWS - 1) // ROWS if r_end > r_lo else 0
+                A = box(a_img, a0)
+                written = set()
+                for q in range(ROWS):                       # the zero loop of the epilogue warps
+                    a = a0 + q
+                    for tj in range(-D, D + 1):
+                        row = a + tj
+                        if 0 <= row < H2c:
+                            continue
+                        written.add((q, tj))
+                        y = 2 * a + py
+                        for lane in range(COLS):
+                            x = 2 * lane + px
+                            if y < H and x < W:
+                                out[n, (tj + D) * 21:(tj + D) * 21 + 21, y, x] = 0.0
+                for j in range(chunks):
+                    r0 = r_lo + j * ROWS
+                    Dm = A.t() @ box(b_img, r0)             # [128 in1' pixels, 128 in2' pixels]
+                    for q in range(ROWS):
+                        a = a0 + q
+                        y = 2 * a + py
+                        for rr in range(ROWS):
+                            row = r0 + rr
+                            tj = row - a
+                            if not (-D <= tj <= D and row < H2c):
+                                continue
+                            assert (q, tj) not in written
+                            written.add((q, tj))
+                            for lane in range(COLS):
+                                x = 2 * lane + px
+                                if not (y < H and x < W):
+                                    continue
+                                for ti in range(-D, D + 1):
+                                    b2 = lane + ti
+                                    v = Dm[q * COLS + lane, rr * COLS + b2] if 0 <= b2 < COLS else 0.0
+                                    out[n, (tj + D) * 21 + ti + D, y, x] = v / C
+                assert len(written) == ROWS * 21
+    return out

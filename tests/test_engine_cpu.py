@@ -134,7 +134,7 @@ def test_library_exports_every_declared_symbol():
     declared -= {"ft_act", "ft_conv_desc"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     l = _lib.lib()                                         # loads the .so and resolves every symbol
-    assert l.ft_abi_version() == 4
+    assert l.ft_abi_version() == _lib.ABI_VERSION == 5
     assert l.ft_sizeof(0) == ctypes.sizeof(_lib.FtAct) == 40 and l.ft_sizeof(1) == ctypes.sizeof(_lib.FtConvDesc)
 
 
@@ -165,3 +165,16 @@ def test_fusion_plan_builds_on_cpu():
     p = engine.Plan("cpu")
     out = FlowNetFusion.build(p, submodules.pack_all(net, "cpu"), p.act(1, 64, 128, 11), 1, p.f32(1, 2, 64, 128))
     assert len(p.calls) == 17 and tuple(out.shape) == (1, 2, 64, 128)
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 13, 31), (2, 4, 16, 24), (1, 4, 2, 2), (1, 4, 50, 20)])
+def test_correlation_banded_gemm_decomposition(shape):
+    """The tile / chunk / band bookkeeping of the tcgen05 correlation kernel (csrc/ft_corr.cu), emulated on the CPU,
+    reproduces the reference cost volume (every output written exactly once, zeros outside the image)."""
+    from oracle import ops_oracle
+    g = torch.Generator().manual_seed(5)
+    a, b = torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)
+    ref = ops_oracle.correlation_torch(a, b, 20, 1, 20, 1, 2).double()
+    out = emulate.emulate_corr_banded(a, b)
+    assert not torch.isnan(out).any()
+    assert (out - ref).abs().max() < 1e-6

@@ -43,6 +43,60 @@ def test_correlation_vs_oracle(shape, params):
         assert (out - ops_oracle.correlation_c(a, b, *params)).abs().max() < 1e-5
 
 
+def _corr_ws(a, b, leaky=0, precision=_lib.PREC_SPLIT):
+    """ft_correlation_forward_ws: the tcgen05 banded-GEMM kernel behind the reference's fp32 NCHW signature."""
+    B, C, H, W = a.shape
+    out = torch.full((B, 441, H, W), float("nan"), device="cuda")
+    n = L().ft_correlation_workspace_bytes(B, C, H, W)
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    assert ws.data_ptr() % 256 == 0
+    _lib.check(L().ft_correlation_forward_ws(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, C, H, W, 20, 1, 20, 1, 2, leaky, precision,
+                                             ws.data_ptr(), n, gpu_util.sp()), "corr_ws")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 48, 64),      # FlowNetC at 384x512
+                                   (3, 256, 16, 24),      # FlowNetC at 128x192 (tiles with out-of-image rows and columns)
+                                   (1, 64, 13, 31),       # odd H and W: the parity classes differ in size
+                                   (2, 128, 50, 64),      # H/2 not a multiple of the 4-row tile
+                                   (1, 192, 2, 2)])       # one pixel per parity class
+def test_correlation_tensor_core_vs_oracle(shape):
+    assert L().ft_correlation_tc_supported(shape[1], shape[2], shape[3], 20, 1, 20, 1, 2) == 1
+    g = torch.Generator().manual_seed(7 + sum(shape))
+    a, b = torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)
+    ref = ops_oracle.correlation_torch(a, b, 20, 1, 20, 1, 2)
+    out = _corr_ws(a.cuda(), b.cuda()).cpu()
+    assert torch.isfinite(out).all()
+    err = (out - ref).abs().max().item()
+    print("tcgen05 correlation %s: max-abs %.3g (ref abs-max %.3g)" % (shape, err, ref.abs().max().item()))
+    assert err < 1e-5 * max(1.0, ref.abs().max().item())
+    simt = _corr(a.cuda(), b.cuda(), 20, 1, 20, 1, 2).cpu()                       # the CUDA-core kernel on the same inputs
+    assert (out - simt).abs().max() < 1e-5
+    fast = _corr_ws(a.cuda(), b.cuda(), precision=_lib.PREC_FAST).cpu()           # fp16 operands: ~2^-11 relative per product
+    assert (fast - ref).abs().max() < 4e-3 * max(1.0, ref.abs().max().item())
+    ol = _corr_ws(a.cuda(), b.cuda(), leaky=1).cpu()
+    assert torch.equal(ol, torch.where(out > 0, out, 0.1 * out))
+
+
+def test_correlation_tensor_core_full_size_properties():
+    """BASELINE config 3 size [32,256,48,64]: checked through size-independent properties (the oracle is too slow)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a, b = torch.randn(32, 256, 48, 64, device="cuda", generator=g), torch.randn(32, 256, 48, 64, device="cuda", generator=g)
+    o = _corr_ws(a, b)
+    assert torch.isfinite(o).all()
+    assert (o[:, 220] - (a * b).mean(1)).abs().max() < 1e-5                        # zero displacement = mean_c a*b
+    # displacement (tj, ti) = (+3, -4) -> in2 shifted by (+6, -8) pixels, zero outside the image
+    sh = torch.zeros_like(b)
+    sh[:, :, :42, 8:] = b[:, :, 6:, :56]
+    assert (o[:, (3 + 10) * 21 + (-4 + 10)] - (a * sh).mean(1)).abs().max() < 1e-5
+    assert (_corr_ws(2 * a, b) - 2 * o).abs().max() < 1e-5                         # linear in input1
+    # swapping the inputs mirrors the displacement: corr(b,a)[-d](p) = corr(a,b)[d](p - 2d); check the centre row of channels
+    o2 = _corr_ws(b, a)
+    assert (o2[:, 220] - o[:, 220]).abs().max() < 1e-5
+    assert (o2[:, (10 - 2) * 21 + 10, 4:, :] - o[:, (10 + 2) * 21 + 10, :44, :]).abs().max() < 1e-5
+
+
 def test_correlation_leaky_and_linearity():
     g = torch.Generator().manual_seed(1)
     a, b = torch.randn(2, 256, 48, 64, generator=g).cuda(), torch.randn(2, 256, 48, 64, generator=g).cuda()
