@@ -24,6 +24,7 @@
 //                   tcgen05.ld 32 columns (one in2' row) -> per-warp smem slab S[b][b2] -> lane b reads the band
 //                   S[b][b+ti], scales by 1/C, LeakyReLU, and stores out[n, ch, 2a+py, 2b+px] (fp32 NCHW).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "ft_tc.cuh"
 
@@ -56,6 +57,7 @@ struct alignas(64) CorrK {
     int a_tiles, num_tiles;
     float inv;
     int leaky;
+    int dbg_skip;   // profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no B loads, 4 = no MMAs, 8 = no global stores (results are garbage)
 };
 
 struct CorrTile {
@@ -121,11 +123,16 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_c
                         const int s = it % G::STAGES;
                         mbar_wait(empty_bar(s), ((it / G::STAGES) & 1) ^ 1);
                         const uint32_t stage = smem_base + s * G::STAGE;
-                        mbar_arrive_expect_tx(full_bar(s), (uint32_t)G::STAGE);
-                        tma_load_4d(stage, &p.a_map[t.cls][0], full_bar(s), kb * CORR_BK, 0, t.a0, t.n);
-                        if (SPLIT) tma_load_4d(stage + CORR_TILE, &p.a_map[t.cls][1], full_bar(s), kb * CORR_BK, 0, t.a0, t.n);
-                        tma_load_4d(stage + G::PLANES * CORR_TILE, &p.b_map[t.cls][0], full_bar(s), kb * CORR_BK, 0, r0, t.n);
-                        if (SPLIT) tma_load_4d(stage + G::PLANES * CORR_TILE + CORR_TILE, &p.b_map[t.cls][1], full_bar(s), kb * CORR_BK, 0, r0, t.n);
+                        const bool ldA = !(p.dbg_skip & 1), ldB = !(p.dbg_skip & 2);
+                        mbar_arrive_expect_tx(full_bar(s), (uint32_t)((ldA ? G::STAGE / 2 : 0) + (ldB ? G::STAGE / 2 : 0)));
+                        if (ldA) {
+                            tma_load_4d(stage, &p.a_map[t.cls][0], full_bar(s), kb * CORR_BK, 0, t.a0, t.n);
+                            if (SPLIT) tma_load_4d(stage + CORR_TILE, &p.a_map[t.cls][1], full_bar(s), kb * CORR_BK, 0, t.a0, t.n);
+                        }
+                        if (ldB) {
+                            tma_load_4d(stage + G::PLANES * CORR_TILE, &p.b_map[t.cls][0], full_bar(s), kb * CORR_BK, 0, r0, t.n);
+                            if (SPLIT) tma_load_4d(stage + G::PLANES * CORR_TILE + CORR_TILE, &p.b_map[t.cls][1], full_bar(s), kb * CORR_BK, 0, r0, t.n);
+                        }
                     }
                 }
             }
@@ -150,6 +157,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_c
                         const uint32_t b_hi = a_hi + G::PLANES * CORR_TILE;
 #pragma unroll
                         for (int k = 0; k < CORR_BK / 16; ++k) {
+                            if (p.dbg_skip & 4) break;
                             const uint64_t da = sw128_desc(a_hi + k * 32), db = sw128_desc(b_hi + k * 32);
                             tc_mma_f16(d_tmem, da, db, idesc, (kb > 0) || (k != 0));
                             if (SPLIT) {
@@ -173,7 +181,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_c
             const CorrTile t = corr_tile(p, tile);
             const int a = t.a0 + q;
             const int y = 2 * a + t.py, x = 2 * lane + t.px;
-            const bool valid = y < p.H && x < p.W;
+            const bool valid = y < p.H && x < p.W && !(p.dbg_skip & 8);
             float* o = p.out + (size_t)t.n * (CDS * CDS) * plane + (size_t)y * p.W + x;
             // displacement rows that fall outside the image: the correlation is zero there (never visited by a chunk)
             for (int tj = -CD + h; tj <= CD; tj += 2) {
@@ -277,6 +285,7 @@ extern "C" int ft_correlation_act(const ft_act* in1, const ft_act* in2, float* o
     CorrK k = {};
     k.out = out, k.B = in1->n, k.H = in1->h, k.W = in1->w, k.C = in1->c, k.kb = in1->c / CORR_BK;
     k.inv = 1.f / (float)k.C, k.leaky = fuse_leaky != 0;
+    if (const char* e = getenv("FT_DEV_SKIP")) k.dbg_skip = atoi(e);
     const int H2 = (k.H + 1) / 2;
     k.a_tiles = ceil_div(H2, CORR_ROWS);
     k.num_tiles = k.B * 4 * k.a_tiles;

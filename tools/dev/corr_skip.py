@@ -1,0 +1,34 @@
+"""Time corr_tc_kernel at [32,256,48,64] (dev tool; honours FT_DEV_SKIP).  Usage: corr_skip.py [split|fast]"""
+import os
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from flowtrack.pytorch_b200 import _lib, engine  # noqa: E402
+
+prec = _lib.PREC_FAST if (len(sys.argv) > 1 and sys.argv[1] == "fast") else _lib.PREC_SPLIT
+B, C, H, W = 32, 256, 48, 64
+L = _lib.lib()
+g = torch.Generator(device="cuda").manual_seed(0)
+acts = []
+for i in range(2):
+    t = torch.randn(B, C, H, W, device="cuda", generator=g)
+    act = engine.Act(B, H, W, C, "cuda")
+    st = t.stride()
+    _lib.check(L.ft_pack_image(t.data_ptr(), st[0], st[1], st[2], st[3], C, 1.0, act.struct(), 0, 0, 0), "pack")
+    acts.append(act)
+o = torch.empty(B, 441, H, W, device="cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+ts = []
+for i in range(8):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(L.ft_correlation_act(acts[0].struct(), acts[1].struct(), o.data_ptr(), 1, prec, 0), "corr")
+    e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+print("skip=%s %s: %.1f us (median of %d, min %.1f)" % (os.environ.get("FT_DEV_SKIP", "0"), sys.argv[1] if len(sys.argv) > 1 else "split",
+                                                       statistics.median(ts[2:]) * 1e3, len(ts) - 2, min(ts) * 1e3))
