@@ -16,11 +16,14 @@
 // per parity class (pixel strides doubled), so no thread ever computes an operand address; products are
 // A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (fp32-grade, FT_PREC_SPLIT) or A_hi*B_hi (FT_PREC_FAST), accumulated in TMEM.
 //
-// CTA = 10 warps, persistent over tiles:
-//   warp 9  TMA   : per (chunk, 64-channel k-block) one stage = A box + B box (hi and lo planes), 3 stages of 64 KiB
-//   warp 8  MMA   : one thread, tcgen05.mma.cta_group::1.kind::f16 M=128 N=128 K=16; one TMEM accumulator stage
-//                   (128 columns) per chunk, 4 stages in flight
-//   warps 0-7 epilogue: warp (q, h) owns TMEM lanes 32q.. (= in1' row a0+q, lane = column b) and chunk rows 2h, 2h+1.
+// CTA = 6 warps, persistent over work units (a tile, or a part of a tile's chunk list):
+//   warp 5  TMA   : the unit's A operand (C/64 k-blocks x hi/lo = up to 128 KiB) is loaded once and stays resident;
+//                   the B chunks stream through a ring of 16 KiB stages (one plane of one k-block each, 5 stages in
+//                   split mode, 9 in fast mode), so the L2 -> shared-memory traffic is about half of "A and B per chunk"
+//   warp 4  MMA   : one thread, tcgen05.mma.cta_group::1.kind::f16 M=128 N=128 K=16; one TMEM accumulator stage
+//                   (128 columns) per chunk, 4 stages in flight; frees A k-block kb right after its last use so the
+//                   next unit's A loads overlap the tail of this one
+//   warps 0-3 epilogue: warp q owns TMEM lanes 32q.. (= in1' row a0+q, lane = column b).  Per chunk row:
 //                   tcgen05.ld 32 columns (one in2' row) -> per-warp smem slab S[b][b2] -> lane b reads the band
 //                   S[b][b+ti], scales by 1/C, LeakyReLU, and stores out[n, ch, 2a+py, 2b+px] (fp32 NCHW).
 #include <cuda.h>
@@ -35,18 +38,20 @@ constexpr int CDS = 2 * CD + 1;        // 21
 constexpr int CORR_BM = 128, CORR_BN = 128, CORR_BK = 64;
 constexpr int CORR_TILE = CORR_BM * CORR_BK * 2;      // 16 KiB: one operand plane of one k-block
 constexpr int CORR_ROWS = 4, CORR_COLS = 32;          // pixel box of a tile / chunk
-constexpr int CORR_EPI_WARPS = 8;
+constexpr int CORR_KB_MAX = 4;                        // C <= 256
+constexpr int CORR_EPI_WARPS = 4;
 constexpr int CORR_THREADS = (CORR_EPI_WARPS + 2) * 32;
 constexpr int CORR_ACC_STAGES = 4;                    // x 128 TMEM columns = all 512
-constexpr int CORR_SLAB = 32 * 33 * 4;                // per epilogue warp: S[32][33] floats
+constexpr int CORR_SLAB = 32 * 34 * 4;                // per epilogue warp: S[c][b] at c*34 + b: conflict-free writes (fixed c) and band reads (c = b + ti)
 
 template <bool SPLIT>
 struct CorrGeo {
     static constexpr int PLANES = SPLIT ? 2 : 1;
-    static constexpr int STAGE = 2 * PLANES * CORR_TILE;           // A + B
-    static constexpr int STAGES = SPLIT ? 3 : 6;
-    static constexpr int SMEM = 1024 + STAGES * STAGE + CORR_EPI_WARPS * CORR_SLAB + 512;
-    static_assert(SMEM <= 232448, "shared memory budget");
+    static constexpr int A_BYTES = CORR_KB_MAX * PLANES * CORR_TILE;     // the A operand of a work unit stays resident
+    static constexpr int SLABS = CORR_EPI_WARPS * CORR_SLAB;
+    static constexpr int STAGES = (232448 - 1024 - 512 - A_BYTES - SLABS) / CORR_TILE;   // B ring: one plane of one k-block per stage
+    static constexpr int SMEM = 1024 + A_BYTES + STAGES * CORR_TILE + SLABS + 512;
+    static_assert(STAGES >= 4 && SMEM <= 232448, "shared memory budget");
 };
 
 struct alignas(64) CorrK {
@@ -54,17 +59,20 @@ struct alignas(64) CorrK {
     CUtensorMap b_map[4][2];     // of in2
     float* out;
     int B, H, W, C, kb;
-    int a_tiles, num_tiles;
+    int a_tiles, num_tiles, parts, num_units;
     float inv;
     int leaky;
-    int dbg_skip;   // profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no B loads, 4 = no MMAs, 8 = no global stores (results are garbage)
+    int dbg_skip;   // profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no B loads, 4 = no MMAs, 8 = no global stores, 16 = no TMEM reads / staging (results are garbage)
 };
 
-struct CorrTile {
-    int n, cls, py, px, a0, H2c, r_lo, chunks;
+// A work unit = part `part` of the chunk list of tile (n, cls, a0): chunks [c_lo, c_lo + nch) of in2' rows r_lo + 4*chunk.
+struct CorrUnit {
+    int n, cls, py, px, a0, H2c, r_lo, c_lo, nch, part;
 };
-__device__ __forceinline__ CorrTile corr_tile(const CorrK& p, int tile) {
-    CorrTile t;
+__device__ __forceinline__ CorrUnit corr_unit(const CorrK& p, int unit) {
+    CorrUnit t;
+    const int tile = unit / p.parts;
+    t.part = unit - tile * p.parts;
     const int at = tile % p.a_tiles, r = tile / p.a_tiles;     // consecutive CTAs share the in2' sub-image through L2
     t.cls = r & 3, t.n = r >> 2;
     t.py = t.cls >> 1, t.px = t.cls & 1;
@@ -72,7 +80,10 @@ __device__ __forceinline__ CorrTile corr_tile(const CorrK& p, int tile) {
     t.H2c = (p.H - t.py + 1) >> 1;
     t.r_lo = max(0, t.a0 - CD);
     const int r_end = min(t.H2c, t.a0 + CORR_ROWS + CD);
-    t.chunks = r_end > t.r_lo ? (r_end - t.r_lo + CORR_ROWS - 1) / CORR_ROWS : 0;
+    const int chunks = r_end > t.r_lo ? (r_end - t.r_lo + CORR_ROWS - 1) / CORR_ROWS : 0;
+    const int per = (chunks + p.parts - 1) / p.parts;
+    t.c_lo = min(chunks, t.part * per);
+    t.nch = min(chunks, t.c_lo + per) - t.c_lo;
     return t;
 }
 
@@ -80,20 +91,28 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_constant__ CorrK p) {
     using G = CorrGeo<SPLIT>;
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t slabs = smem_base + G::STAGES * G::STAGE;
-    const uint32_t bar_base = slabs + CORR_EPI_WARPS * CORR_SLAB;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (G::STAGES + s); };
-    auto accf_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + a); };
-    auto acce_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + CORR_ACC_STAGES + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * G::STAGES + 2 * CORR_ACC_STAGES);
+    const uint32_t a_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ring = a_base + G::A_BYTES;
+    const uint32_t slabs = ring + G::STAGES * CORR_TILE;
+    const uint32_t bar_base = slabs + G::SLABS;
+    auto bfull_bar = [&](int s) { return bar_base + 8u * s; };
+    auto bempty_bar = [&](int s) { return bar_base + 8u * (G::STAGES + s); };
+    auto afull_bar = [&](int k) { return bar_base + 8u * (2 * G::STAGES + k); };
+    auto aempty_bar = [&](int k) { return bar_base + 8u * (2 * G::STAGES + CORR_KB_MAX + k); };
+    auto accf_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + 2 * CORR_KB_MAX + a); };
+    auto acce_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + 2 * CORR_KB_MAX + CORR_ACC_STAGES + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * G::STAGES + 2 * CORR_KB_MAX + 2 * CORR_ACC_STAGES);
+    static_assert(8 * (2 * G::STAGES + 2 * CORR_KB_MAX + 2 * CORR_ACC_STAGES + 1) <= 512, "barrier block");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < G::STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(bfull_bar(s), 1);
+            mbar_init(bempty_bar(s), 1);
+        }
+        for (int k = 0; k < CORR_KB_MAX; ++k) {
+            mbar_init(afull_bar(k), 1);
+            mbar_init(aempty_bar(k), 1);
         }
         for (int a = 0; a < CORR_ACC_STAGES; ++a) {
             mbar_init(accf_bar(a), 1);
@@ -114,118 +133,151 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_c
     if (warp == CORR_EPI_WARPS + 1) {
         // =========================== TMA producer ===========================
         if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const CorrTile t = corr_tile(p, tile);
-                for (int j = 0; j < t.chunks; ++j) {
-                    const int r0 = t.r_lo + j * CORR_ROWS;
-                    for (int kb = 0; kb < p.kb; ++kb, ++it) {
-                        const int s = it % G::STAGES;
-                        mbar_wait(empty_bar(s), ((it / G::STAGES) & 1) ^ 1);
-                        const uint32_t stage = smem_base + s * G::STAGE;
-                        const bool ldA = !(p.dbg_skip & 1), ldB = !(p.dbg_skip & 2);
-                        mbar_arrive_expect_tx(full_bar(s), (uint32_t)((ldA ? G::STAGE / 2 : 0) + (ldB ? G::STAGE / 2 : 0)));
-                        if (ldA) {
-                            tma_load_4d(stage, &p.a_map[t.cls][0], full_bar(s), kb * CORR_BK, 0, t.a0, t.n);
-                            if (SPLIT) tma_load_4d(stage + CORR_TILE, &p.a_map[t.cls][1], full_bar(s), kb * CORR_BK, 0, t.a0, t.n);
+            const bool ldA = !(p.dbg_skip & 1), ldB = !(p.dbg_skip & 2);
+            int bit = 0, ut = 0;     // B ring stages issued / work units with chunks (phase of the A barriers)
+            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+                const CorrUnit t = corr_unit(p, unit);
+                if (t.nch == 0) continue;
+                for (int j = 0; j < t.nch; ++j) {
+                    const int r0 = t.r_lo + (t.c_lo + j) * CORR_ROWS;
+                    for (int kb = 0; kb < p.kb; ++kb) {
+                        if (j == 0) {
+                            // A k-block kb of this unit: its slot is freed by the MMA warp right after the previous unit's last use,
+                            // and the B stages of the unit's first chunk follow it immediately, so the unit switch costs no bubble
+                            mbar_wait(aempty_bar(kb), (ut & 1) ^ 1);
+                            const uint32_t dst = a_base + kb * G::PLANES * CORR_TILE;
+                            mbar_arrive_expect_tx(afull_bar(kb), ldA ? (uint32_t)(G::PLANES * CORR_TILE) : 0u);
+                            if (ldA) {
+                                tma_load_4d(dst, &p.a_map[t.cls][0], afull_bar(kb), kb * CORR_BK, 0, t.a0, t.n);
+                                if (SPLIT) tma_load_4d(dst + CORR_TILE, &p.a_map[t.cls][1], afull_bar(kb), kb * CORR_BK, 0, t.a0, t.n);
+                            }
                         }
-                        if (ldB) {
-                            tma_load_4d(stage + G::PLANES * CORR_TILE, &p.b_map[t.cls][0], full_bar(s), kb * CORR_BK, 0, r0, t.n);
-                            if (SPLIT) tma_load_4d(stage + G::PLANES * CORR_TILE + CORR_TILE, &p.b_map[t.cls][1], full_bar(s), kb * CORR_BK, 0, r0, t.n);
+#pragma unroll
+                        for (int pl = 0; pl < G::PLANES; ++pl, ++bit) {
+                            const int s = bit % G::STAGES;
+                            mbar_wait(bempty_bar(s), ((bit / G::STAGES) & 1) ^ 1);
+                            mbar_arrive_expect_tx(bfull_bar(s), ldB ? (uint32_t)CORR_TILE : 0u);
+                            if (ldB) tma_load_4d(ring + s * CORR_TILE, &p.b_map[t.cls][pl], bfull_bar(s), kb * CORR_BK, 0, r0, t.n);
                         }
                     }
                 }
+                ++ut;
             }
         }
     } else if (warp == CORR_EPI_WARPS) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             constexpr uint32_t idesc = f16_idesc(CORR_BM, CORR_BN);
-            int it = 0, acc_it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const CorrTile t = corr_tile(p, tile);
-                for (int j = 0; j < t.chunks; ++j, ++acc_it) {
+            const bool do_mma = !(p.dbg_skip & 4);
+            int bit = 0, ut = 0, acc_it = 0;
+            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+                const CorrUnit t = corr_unit(p, unit);
+                if (t.nch == 0) continue;
+                for (int j = 0; j < t.nch; ++j, ++acc_it) {
                     const int a = acc_it % CORR_ACC_STAGES;
                     mbar_wait(acce_bar(a), ((acc_it / CORR_ACC_STAGES) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(a * CORR_BN);
-                    for (int kb = 0; kb < p.kb; ++kb, ++it) {
-                        const int s = it % G::STAGES;
-                        mbar_wait(full_bar(s), (it / G::STAGES) & 1);
-                        tc_fence_after();
-                        const uint32_t a_hi = smem_base + s * G::STAGE;
-                        const uint32_t b_hi = a_hi + G::PLANES * CORR_TILE;
+                    for (int kb = 0; kb < p.kb; ++kb) {
+                        if (j == 0) mbar_wait(afull_bar(kb), ut & 1);
+                        const uint32_t a_hi = a_base + kb * G::PLANES * CORR_TILE;
+                        {   // B_hi: A_hi*B_hi (+ A_lo*B_hi)
+                            const int s = bit % G::STAGES;
+                            mbar_wait(bfull_bar(s), (bit / G::STAGES) & 1);
+                            tc_fence_after();
+                            const uint32_t b = ring + s * CORR_TILE;
 #pragma unroll
-                        for (int k = 0; k < CORR_BK / 16; ++k) {
-                            if (p.dbg_skip & 4) break;
-                            const uint64_t da = sw128_desc(a_hi + k * 32), db = sw128_desc(b_hi + k * 32);
-                            tc_mma_f16(d_tmem, da, db, idesc, (kb > 0) || (k != 0));
-                            if (SPLIT) {
-                                tc_mma_f16(d_tmem, sw128_desc(a_hi + CORR_TILE + k * 32), db, idesc, 1);
-                                tc_mma_f16(d_tmem, da, sw128_desc(b_hi + CORR_TILE + k * 32), idesc, 1);
+                            for (int k = 0; k < CORR_BK / 16; ++k) {
+                                if (!do_mma) break;
+                                const uint64_t db = sw128_desc(b + k * 32);
+                                tc_mma_f16(d_tmem, sw128_desc(a_hi + k * 32), db, idesc, (kb > 0) || (k != 0));
+                                if (SPLIT) tc_mma_f16(d_tmem, sw128_desc(a_hi + CORR_TILE + k * 32), db, idesc, 1);
                             }
+                            tc_commit(bempty_bar(s));
+                            ++bit;
                         }
-                        tc_commit(empty_bar(s));
+                        if (SPLIT) {   // B_lo: A_hi*B_lo
+                            const int s = bit % G::STAGES;
+                            mbar_wait(bfull_bar(s), (bit / G::STAGES) & 1);
+                            tc_fence_after();
+                            const uint32_t b = ring + s * CORR_TILE;
+#pragma unroll
+                            for (int k = 0; k < CORR_BK / 16; ++k) {
+                                if (!do_mma) break;
+                                tc_mma_f16(d_tmem, sw128_desc(a_hi + k * 32), sw128_desc(b + k * 32), idesc, 1);
+                            }
+                            tc_commit(bempty_bar(s));
+                            ++bit;
+                        }
+                        if (j == t.nch - 1) tc_commit(aempty_bar(kb));     // the unit's last use of this A k-block
                     }
                     tc_commit(accf_bar(a));
                 }
+                ++ut;
             }
         }
     } else {
-        // =========================== epilogue (warps 0-7) ===========================
-        const int q = warp & 3, h = warp >> 2;
-        float* S = reinterpret_cast<float*>(smem_raw + (slabs - smem_u32(smem_raw))) + warp * (32 * 33);
+        // =========================== epilogue (warps 0-3) ===========================
+        const int q = warp;                                       // TMEM lane quarter = in1' row a0 + q; lane = column b
+        float* S = reinterpret_cast<float*>(smem_raw + (slabs - smem_u32(smem_raw))) + warp * (32 * 34);
         const size_t plane = (size_t)p.H * p.W;
         int acc_it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const CorrTile t = corr_tile(p, tile);
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+            const CorrUnit t = corr_unit(p, unit);
             const int a = t.a0 + q;
             const int y = 2 * a + t.py, x = 2 * lane + t.px;
             const bool valid = y < p.H && x < p.W && !(p.dbg_skip & 8);
             float* o = p.out + (size_t)t.n * (CDS * CDS) * plane + (size_t)y * p.W + x;
-            // displacement rows that fall outside the image: the correlation is zero there (never visited by a chunk)
-            for (int tj = -CD + h; tj <= CD; tj += 2) {
-                const int row = a + tj;
-                if (row >= 0 && row < t.H2c) continue;
-                if (valid) {
+            if (t.part == 0) {
+                // displacement rows that fall outside the image: the correlation is zero there (never visited by a chunk)
+                for (int tj = -CD; tj <= CD; ++tj) {
+                    const int row = a + tj;
+                    if (row >= 0 && row < t.H2c) continue;
+                    if (valid) {
 #pragma unroll
-                    for (int ti = 0; ti < CDS; ++ti) o[(size_t)((tj + CD) * CDS + ti) * plane] = 0.f;
+                        for (int ti = 0; ti < CDS; ++ti) o[(size_t)((tj + CD) * CDS + ti) * plane] = 0.f;
+                    }
                 }
             }
-            for (int j = 0; j < t.chunks; ++j, ++acc_it) {
+            for (int j = 0; j < t.nch; ++j, ++acc_it) {
                 const int as = acc_it % CORR_ACC_STAGES;
-                const int r0 = t.r_lo + j * CORR_ROWS;
+                const int r0 = t.r_lo + (t.c_lo + j) * CORR_ROWS;
                 mbar_wait(accf_bar(as), (acc_it / CORR_ACC_STAGES) & 1);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * CORR_BN);
-                uint32_t v0[32], v1[32];
-                const int row0 = r0 + 2 * h, row1 = row0 + 1;
-                const int tj0 = row0 - a, tj1 = row1 - a;
-                const bool use0 = tj0 >= -CD && tj0 <= CD && row0 < t.H2c;     // warp-uniform
-                const bool use1 = tj1 >= -CD && tj1 <= CD && row1 < t.H2c;
-                if (use0) TMEM_LD_32(t_row + (2 * h) * 32, v0);
-                if (use1) TMEM_LD_32(t_row + (2 * h + 1) * 32, v1);
-                if (use0 || use1) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                mbar_arrive(acce_bar(as));                  // this thread is done with the TMEM stage
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const bool use = rr ? use1 : use0;
-                    if (!use) continue;
-                    const int tj = rr ? tj1 : tj0;
-                    __syncwarp();
+                for (int h = 0; h < 2; ++h) {                      // chunk rows 2h, 2h+1
+                    uint32_t v0[32], v1[32];
+                    const int row0 = r0 + 2 * h, row1 = row0 + 1;
+                    const int tj0 = row0 - a, tj1 = row1 - a;
+                    const bool use0 = tj0 >= -CD && tj0 <= CD && row0 < t.H2c && !(p.dbg_skip & 16);     // warp-uniform
+                    const bool use1 = tj1 >= -CD && tj1 <= CD && row1 < t.H2c && !(p.dbg_skip & 16);
+                    if (use0) TMEM_LD_32(t_row + (2 * h) * 32, v0);
+                    if (use1) TMEM_LD_32(t_row + (2 * h + 1) * 32, v1);
+                    if (use0 || use1) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (h == 1) {
+                        tc_fence_before();
+                        mbar_arrive(acce_bar(as));              // this thread is done with the TMEM stage
+                    }
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) S[lane * 33 + c] = __uint_as_float(rr ? v1[c] : v0[c]);
-                    __syncwarp();
-                    if (valid) {
-                        float* oc = o + (size_t)((tj + CD) * CDS) * plane;
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const bool use = rr ? use1 : use0;
+                        if (!use) continue;
+                        const int tj = rr ? tj1 : tj0;
+                        __syncwarp();
 #pragma unroll
-                        for (int ti = 0; ti < CDS; ++ti) {
-                            const int b2 = lane + ti - CD;
-                            float val = (b2 >= 0 && b2 < 32) ? S[lane * 33 + b2] : 0.f;   // columns >= W/2 were zero-filled by TMA
-                            val *= p.inv;
-                            if (p.leaky) val = val > 0.f ? val : 0.1f * val;
-                            oc[(size_t)ti * plane] = val;
+                        for (int c = 0; c < 32; ++c) S[c * 34 + lane] = __uint_as_float(rr ? v1[c] : v0[c]);
+                        __syncwarp();
+                        if (valid) {
+                            float* oc = o + (size_t)((tj + CD) * CDS) * plane;
+#pragma unroll
+                            for (int ti = 0; ti < CDS; ++ti) {
+                                const int b2 = lane + ti - CD;
+                                float val = (b2 >= 0 && b2 < 32) ? S[b2 * 34 + lane] : 0.f;   // columns >= W/2 were zero-filled by TMA
+                                val *= p.inv;
+                                if (p.leaky) val = val > 0.f ? val : 0.1f * val;
+                                oc[(size_t)ti * plane] = val;
+                            }
                         }
                     }
                 }
@@ -237,6 +289,39 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_c
     if (warp == CORR_EPI_WARPS) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// Re-layout for the reference-signature entry point: contiguous fp32 NCHW -> split-fp16 NHWC planes (hi, lo).  A block
+// transposes a tile of 64 channels x 32 pixels through shared memory: 128-byte coalesced reads along x, 16-byte stores
+// that complete full 128-byte lines of a pixel's channel vector.
+__global__ void __launch_bounds__(256) corr_relayout_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, int C, long long npix) {
+    __shared__ float tile[64][33];
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 64, n = blockIdx.z;
+    const float* s = src + (size_t)n * C * npix;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + w * 8 + i;
+        const long long px = p0 + lane;
+        tile[w * 8 + i][lane] = (c < C && px < npix) ? __ldg(s + (size_t)c * npix + px) : 0.f;
+    }
+    __syncthreads();
+    const int pl = threadIdx.x >> 3, g = threadIdx.x & 7;       // pixel of the tile, 8-channel group
+    const long long px = p0 + pl;
+    if (px < npix && c0 + g * 8 < C) {
+        Half8 h8, l8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __half h0, l0, h1, l1;
+            split_f32(tile[g * 8 + 2 * k][pl], h0, l0);
+            split_f32(tile[g * 8 + 2 * k + 1][pl], h1, l1);
+            h8.v[k] = __halves2half2(h0, h1), l8.v[k] = __halves2half2(l0, l1);
+        }
+        const size_t off = ((size_t)n * npix + px) * C + c0 + g * 8;
+        *reinterpret_cast<Half8*>(hi + off) = h8;
+        *reinterpret_cast<Half8*>(lo + off) = l8;
     }
 }
 
@@ -252,7 +337,7 @@ static int launch_corr(const CorrK& k, cudaStream_t s) {
         }
         attr_set = true;
     }
-    const int grid = k.num_tiles < 148 ? k.num_tiles : 148;
+    const int grid = k.num_units < 148 ? k.num_units : 148;
     corr_tc_kernel<SPLIT><<<grid, CORR_THREADS, G::SMEM, s>>>(k);
     return check_launch("corr_tc_kernel");
 }
@@ -289,6 +374,13 @@ extern "C" int ft_correlation_act(const ft_act* in1, const ft_act* in2, float* o
     const int H2 = (k.H + 1) / 2;
     k.a_tiles = ceil_div(H2, CORR_ROWS);
     k.num_tiles = k.B * 4 * k.a_tiles;
+    // work units: a tile's chunk list is cut into 3 parts of <= 2 chunks (each part re-loads the tile's A operand through
+    // L2): whole tiles (4-6 chunks) leave the last round of the 148 persistent CTAs mostly idle.  Measured on B200 at
+    // [B,256,48,64], parts = 1/2/3/4/5/6: B=32 142/143/132/178/133/148 us, B=16 68/74/66/86/64/72, B=8 51/43/41/51/43/43
+    // (parts sharing a factor with 148 pin the large parts to the same CTAs under the static round-robin order).
+    k.parts = 3;
+    if (const char* e = getenv("FT_DEV_CORR_PARTS")) k.parts = atoi(e) >= 1 && atoi(e) <= 6 ? atoi(e) : 3;
+    k.num_units = k.num_tiles * k.parts;
     const int box[4] = {CORR_BK, CORR_COLS, CORR_ROWS, 1};
     for (int cls = 0; cls < 4; ++cls) {
         const int py = cls >> 1, px = cls & 1;
@@ -328,8 +420,9 @@ extern "C" int ft_correlation_forward_ws(const float* in1, const float* in2, flo
     ft_act a[2];
     for (int i = 0; i < 2; ++i) {
         a[i] = ft_act{(uint8_t*)workspace + (2 * i) * plane, (uint8_t*)workspace + (2 * i + 1) * plane, B, H, W, C, C, 0};
-        const float* src = i ? in2 : in1;
-        if (int e = ft_pack_image(src, (long long)C * H * W, (long long)H * W, W, 1, C, 1.f, &a[i], 0, 0, stream)) return e;
+        const long long npix = (long long)H * W;
+        corr_relayout_kernel<<<dim3((unsigned)ceil_div((int)npix, 32), C / 64, B), 256, 0, (cudaStream_t)stream>>>(i ? in2 : in1, (__half*)a[i].hi, (__half*)a[i].lo, C, npix);
+        if (check_launch("corr_relayout_kernel")) return 1;
     }
     return ft_correlation_act(&a[0], &a[1], out, fuse_leaky, precision, stream);
 }

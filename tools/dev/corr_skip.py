@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 from flowtrack.pytorch_b200 import _lib, engine  # noqa: E402
 
 prec = _lib.PREC_FAST if (len(sys.argv) > 1 and sys.argv[1] == "fast") else _lib.PREC_SPLIT
-B, C, H, W = 32, 256, 48, 64
+B, C, H, W = int(os.environ.get("CORR_B", "32")), 256, 48, 64
 L = _lib.lib()
 g = torch.Generator(device="cuda").manual_seed(0)
 acts = []
@@ -21,14 +21,18 @@ for i in range(2):
     acts.append(act)
 o = torch.empty(B, 441, H, W, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+flush2 = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
+clean = os.environ.get("FLUSH_CLEAN", "0") == "1"
 ts = []
 for i in range(8):
     flush.zero_()
+    if clean:
+        flush2.sum()      # read 256 MB: L2 ends up holding clean lines instead of the memset's dirty ones
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     _lib.check(L.ft_correlation_act(acts[0].struct(), acts[1].struct(), o.data_ptr(), 1, prec, 0), "corr")
     e1.record()
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
-print("skip=%s %s: %.1f us (median of %d, min %.1f)" % (os.environ.get("FT_DEV_SKIP", "0"), sys.argv[1] if len(sys.argv) > 1 else "split",
+print("B=%d parts=%s clean=%d skip=%s %s: %.1f us (median of %d, min %.1f)" % (B, os.environ.get("FT_DEV_CORR_PARTS", "auto"), clean, os.environ.get("FT_DEV_SKIP", "0"), sys.argv[1] if len(sys.argv) > 1 else "split",
                                                        statistics.median(ts[2:]) * 1e3, len(ts) - 2, min(ts) * 1e3))
