@@ -257,8 +257,18 @@ def run_ours(args):
                     other[what] = other.get(what, 0.0) + per[i]
         n_conv = sum(1 for plan in (pipe.pose_plan, pipe.flow_plan) for c in plan.calls if c[0] == "conv2d")
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
+        traffic, ncu_note = None, None
+        try:     # DRAM bytes per conv launch from the committed ncu --set full capture of the same plans (not measured in this run)
+            with open(os.path.join(ROOT, "profiles", "r01g_conv_traffic.json")) as f:
+                tr = json.load(f)
+            traffic = tr["dram_bytes_per_launch"]
+            ncu_note = {"tensor_pipe_active_pct_time_weighted": tr["tensor_pipe_active_pct_time_weighted"], "source": tr["source"]}
+        except Exception:
+            pass
         roof = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv/deconv, %d launches per step)" % n_conv, "bound": "tensor",
-                "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
+                "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": traffic,
+                "traffic_unit": "DRAM bytes (read+write) per launch, averaged over the conv launches of a step", "ncu": ncu_note,
+                "algorithmic_flop_per_launch": conv_flops / n_conv, "ms_per_launch": conv_ms / n_conv,
                 "algorithmic_gflop_per_step": conv_flops / 1e9, "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / ms,
                 "executed_over_algorithmic": 3.0 if args.precision == "split" else 1.0,
                 "peak_source": peaks["source"] + ", sustained dense bf16 GEMM"}

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libflowtrack_b200.so")
-SOURCES = ["ft_ops.cu", "ft_conv.cu", "ft_corr.cu"]
+SOURCES = ["ft_ops.cu", "ft_conv.cu", "ft_corr.cu", "ft_track.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas=-v"]

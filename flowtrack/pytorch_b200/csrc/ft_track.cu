@@ -1,0 +1,187 @@
+// ft_track.cu -- the tracking glue either side of the two networks, sm_100a only:
+//   ft_crop_affine  person crops for pose_est (lib/tracking/net_utils.py:48-57 -> lib/pose/utils/transforms.py:231-240
+//                   transform_image -> cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0)), all boxes of a batch in one launch
+//   ft_nms          greedy person-box NMS (lib/tracking/net_utils.py:29-32 -> lib/detection/nms/pth_nms.py:5-46,
+//                   src/nms.c:36-62 / src/cuda/nms_kernel.cu:13-70), one CTA per frame, nothing leaves the GPU
+#include "ft_common.cuh"
+
+namespace ft {
+
+// ------------------------------------------------------------------------------------------------
+// Affine crops.  cv2.warpAffine is the reference's third-party arithmetic (OpenCV, un-vendored); its bilinear path
+// works on a fixed-point grid, restated here (modules/imgproc/src/imgwarp.cpp, WarpAffineInvoker):
+//   M = 2x3 forward map, inverted in double precision (dst -> src);
+//   X = (round(M0*x*1024) + round((M1*y + M2)*1024) + 16) >> 5     (1/32-pixel source coordinate), Y likewise;
+//   sx = X >> 5, fx = X & 31;  the four taps outside the image count as 0;
+//   8-bit images: out = (sum_i w_i * p_i + 512) >> 10 with w = (32-fx)(32-fy), fx(32-fy), (32-fx)fy, fx*fy  (exact
+//   integer form of OpenCV's 15-bit weight table); float images: the same weights / 1024 in floating point.
+// The forward map is get_transform(center, scale, res) (transforms.py:173-184, factor 1, rot 0):
+//   M0 = M4 = res_h / scale,  M2 = -res_h*cx/scale + res_w/2,  M5 = -res_h*cy/scale + res_h/2.
+// ------------------------------------------------------------------------------------------------
+struct CropSrc {
+    const void* base;
+    long long sn, sc, sh, sw;   // element strides: frame, channel, row, column
+    int H, W, C, is_u8;
+};
+
+__global__ void __launch_bounds__(256) crop_affine_kernel(CropSrc src, const float* __restrict__ centers, const float* __restrict__ scales,
+                                                          const int32_t* __restrict__ frame_of, int N, int oh, int ow, int reverse_c,
+                                                          float* __restrict__ out) {
+    const int n = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= ow || y >= oh) return;
+    const double cx = centers[2 * n], cy = centers[2 * n + 1], scale = scales[n];
+    double M0 = (double)oh / scale, M1 = 0.0, M3 = 0.0, M4 = (double)oh / scale;
+    double M2 = -(double)oh * cx / scale + 0.5 * ow, M5 = -(double)oh * cy / scale + 0.5 * oh;
+    {   // cv::warpAffine: invert the forward map
+        double D = M0 * M4 - M1 * M3;
+        D = D != 0 ? 1. / D : 0;
+        const double A11 = M4 * D, A22 = M0 * D;
+        M0 = A11, M1 *= -D, M3 *= -D, M4 = A22;
+        const double b1 = -M0 * M2 - M1 * M5, b2 = -M3 * M2 - M4 * M5;
+        M2 = b1, M5 = b2;
+    }
+    const int X = (__double2int_rn(M0 * x * 1024.0) + __double2int_rn((M1 * y + M2) * 1024.0) + 16) >> 5;
+    const int Y = (__double2int_rn(M3 * x * 1024.0) + __double2int_rn((M4 * y + M5) * 1024.0) + 16) >> 5;
+    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+    const int fx = X & 31, fy = Y & 31;
+    const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy), w10 = (32 - fx) * fy, w11 = fx * fy;
+    const bool x0 = sx >= 0 && sx < src.W, x1 = sx + 1 >= 0 && sx + 1 < src.W;
+    const bool y0 = sy >= 0 && sy < src.H, y1 = sy + 1 >= 0 && sy + 1 < src.H;
+    const long long f = frame_of ? frame_of[n] : 0;
+    for (int c = 0; c < src.C; ++c) {
+        const long long b = f * src.sn + (long long)c * src.sc;
+        const long long o00 = b + sy * src.sh + sx * src.sw, o01 = o00 + src.sw, o10 = o00 + src.sh, o11 = o10 + src.sw;
+        float v;
+        if (src.is_u8) {
+            const uint8_t* p = (const uint8_t*)src.base;
+            const int s = w00 * (y0 && x0 ? (int)p[o00] : 0) + w01 * (y0 && x1 ? (int)p[o01] : 0) + w10 * (y1 && x0 ? (int)p[o10] : 0) +
+                          w11 * (y1 && x1 ? (int)p[o11] : 0);
+            v = (float)((s + 512) >> 10);
+        } else {
+            const float* p = (const float*)src.base;
+            const float k = 1.f / 1024.f;
+            v = (y0 && x0 ? __ldg(p + o00) : 0.f) * (w00 * k) + (y0 && x1 ? __ldg(p + o01) : 0.f) * (w01 * k) + (y1 && x0 ? __ldg(p + o10) : 0.f) * (w10 * k) +
+                (y1 && x1 ? __ldg(p + o11) : 0.f) * (w11 * k);
+        }
+        const int co = reverse_c ? src.C - 1 - c : c;
+        out[(((size_t)n * src.C + co) * oh + y) * ow + x] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NMS.  One CTA per frame: bitonic sort of (score, index) in shared memory, the upper-triangular suppression matrix as
+// bit rows in shared memory (row i: which lower-scored boxes box i suppresses), then one warp walks the sorted list
+// (lane w owns word w of the 1024-bit "removed" set).  IoU uses the reference's +1 pixel convention.
+// ------------------------------------------------------------------------------------------------
+constexpr int NMS_MAX = 1024;
+constexpr int NMS_WORDS = NMS_MAX / 32;
+
+__global__ void __launch_bounds__(1024) nms_kernel(const float* __restrict__ dets, const int32_t* __restrict__ counts, int N, float thresh, int inclusive,
+                                                   int32_t* __restrict__ keep, int32_t* __restrict__ num_keep) {
+    extern __shared__ uint32_t nms_smem[];
+    float* key = reinterpret_cast<float*>(nms_smem);                  // [1024] scores (sorted descending)
+    int* idx = reinterpret_cast<int*>(nms_smem + NMS_MAX);            // [1024] original indices
+    float* box = reinterpret_cast<float*>(nms_smem + 2 * NMS_MAX);    // [1024][4] sorted boxes
+    uint32_t* mask = nms_smem + 6 * NMS_MAX;                          // [n][words]
+    const int f = blockIdx.x, t = threadIdx.x;
+    const int n = counts ? min(max(counts[f], 0), N) : N;
+    const float* d = dets + (size_t)f * N * 5;
+    int32_t* kp = keep + (size_t)f * N;
+    int np2 = 32;
+    while (np2 < n) np2 <<= 1;
+    // sort by score, descending; ties by ascending index; padding sorts last
+    key[t] = t < n ? d[t * 5 + 4] : -INFINITY;
+    idx[t] = t < n ? t : 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int p = t ^ j;
+            if (t < np2 && p > t) {
+                const bool desc = (t & k) == 0;
+                const float a = key[t], b = key[p];
+                const int ia = idx[t], ib = idx[p];
+                const bool a_first = a > b || (a == b && ia < ib);      // a belongs before b in the final order
+                if (desc ? !a_first : a_first) key[t] = b, key[p] = a, idx[t] = ib, idx[p] = ia;
+            }
+            __syncthreads();
+        }
+    if (t < n) {
+        const float* s = d + (size_t)idx[t] * 5;
+        box[4 * t] = s[0], box[4 * t + 1] = s[1], box[4 * t + 2] = s[2], box[4 * t + 3] = s[3];
+    }
+    __syncthreads();
+    const int words = (n + 31) >> 5;
+    // suppression bits: thread t handles row t, all words (n*words IoU bit-words in total)
+    if (t < n) {
+        const float ax1 = box[4 * t], ay1 = box[4 * t + 1], ax2 = box[4 * t + 2], ay2 = box[4 * t + 3];
+        const float sa = (ax2 - ax1 + 1) * (ay2 - ay1 + 1);
+        for (int w = 0; w < words; ++w) {
+            uint32_t bits = 0;
+            if (w >= (t >> 5)) {
+                for (int b = 0; b < 32; ++b) {
+                    const int j = w * 32 + b;
+                    if (j <= t || j >= n) continue;
+                    const float bx1 = box[4 * j], by1 = box[4 * j + 1], bx2 = box[4 * j + 2], by2 = box[4 * j + 3];
+                    const float iw = fmaxf(fminf(ax2, bx2) - fmaxf(ax1, bx1) + 1, 0.f), ih = fmaxf(fminf(ay2, by2) - fmaxf(ay1, by1) + 1, 0.f);
+                    const float inter = iw * ih;
+                    const float sb = (bx2 - bx1 + 1) * (by2 - by1 + 1);
+                    const float ovr = inter / (sa + sb - inter);
+                    if (inclusive ? ovr >= thresh : ovr > thresh) bits |= 1u << b;
+                }
+            }
+            mask[t * words + w] = bits;
+        }
+    }
+    __syncthreads();
+    if (t < 32) {
+        uint32_t removed = 0;          // lane w: word w of the removed set
+        int kept = 0;
+        for (int i = 0; i < n; ++i) {
+            const uint32_t wv = __shfl_sync(0xffffffffu, removed, i >> 5);
+            if (!((wv >> (i & 31)) & 1u)) {
+                if (t == 0) kp[kept] = idx[i];
+                ++kept;
+                if (t < words) removed |= mask[i * words + t];
+            }
+        }
+        if (t == 0) num_keep[f] = kept;
+        for (int i = kept + t; i < N; i += 32) kp[i] = -1;
+    }
+}
+
+}  // namespace ft
+
+using namespace ft;
+
+extern "C" int ft_crop_affine(const void* frames, int is_u8, long long sn, long long sc, long long sh, long long sw, int H, int W, int C,
+                              const float* centers, const float* scales, const int32_t* frame_of, int N, int out_h, int out_w, int reverse_channels,
+                              float* out, void* stream) {
+    FT_REQUIRE(H > 0 && W > 0 && C > 0 && C <= 4 && out_h > 0 && out_w > 0 && N >= 0, "crop_affine: bad shape");
+    if (N == 0) return 0;                    // no boxes in this batch: nothing to launch (the pointers may be null)
+    FT_REQUIRE(frames && centers && scales && out, "crop_affine: null pointer");
+    FT_REQUIRE(N <= 65535, "crop_affine: at most 65535 crops per call");
+    CropSrc s = {frames, sn, sc, sh, sw, H, W, C, is_u8 != 0};
+    crop_affine_kernel<<<dim3(ceil_div(out_w, 32), ceil_div(out_h, 8), N), 256, 0, (cudaStream_t)stream>>>(s, centers, scales, frame_of, N, out_h, out_w,
+                                                                                                            reverse_channels != 0, out);
+    return check_launch("crop_affine_kernel");
+}
+
+extern "C" int ft_nms(const float* dets, const int32_t* counts, int frames, int N, float thresh, int inclusive, int32_t* keep, int32_t* num_keep,
+                      void* stream) {
+    FT_REQUIRE(dets && keep && num_keep && frames > 0, "nms: null pointer / no frames");
+    FT_REQUIRE(N >= 0 && N <= NMS_MAX, "nms: at most %d boxes per frame (got %d)", NMS_MAX, N);
+    const int words = (N + 31) / 32;
+    const int smem = (6 * NMS_MAX + (N > 0 ? N * words : 1)) * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (6 * NMS_MAX + NMS_MAX * NMS_WORDS) * 4);
+        if (e != cudaSuccess) {
+            set_error("nms_kernel: cannot opt in to shared memory: %s", cudaGetErrorString(e));
+            return 1;
+        }
+        attr_set = true;
+    }
+    nms_kernel<<<frames, 1024, smem, (cudaStream_t)stream>>>(dets, counts, N, thresh, inclusive != 0, keep, num_keep);
+    return check_launch("nms_kernel");
+}

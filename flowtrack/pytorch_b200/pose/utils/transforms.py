@@ -1,23 +1,35 @@
-"""Host-side affine helpers with the reference names (lib/pose/utils/transforms.py:173-240): get_transform,
-transform_point, transform_preds, transform_image.  Pure numpy/cv2 host glue (A11); the decode hot path applies the
-same inverse affine inside ft_decode_keypoints."""
+"""Host-side affine helpers with the reference names and signatures (lib/pose/utils/transforms.py:173-240, the
+factor = 1 / rot = 0 / delta = 0 branch the tracking path uses): get_transform, do_transfrom, transform_point,
+transform_preds, transform_image.  Pure numpy/cv2 host glue (A11); the hot path applies the same maps on the GPU
+(ft_decode_keypoints for the inverse map of the key-points, ft_crop_affine for the crops)."""
 import numpy as np
 
 from ...tracking.net_utils import get_transform, transform_image  # noqa: F401
 
 
+def do_transfrom(pt, t):
+    """transforms.py:197-205 (spelling as in the reference): pt [(M,) N, 2] -> t . [pt, 1]."""
+    pt = np.asarray(pt)
+    shape = pt.shape
+    if len(shape) >= 3:
+        pt = pt.reshape((-1, 2))
+    pt_ = np.concatenate((pt, np.ones((pt.shape[0], 1))), axis=1)
+    new_pt = np.dot(t, pt_.T)[:2].T
+    if len(shape) >= 3:
+        new_pt = new_pt.reshape(shape)
+    return new_pt
+
+
 def transform_point(pt, center, scale, res, invert=0):
-    """transforms.py:204-212 (rot = 0): pixel <-> crop coordinates of one point."""
+    """transforms.py:208-213: pixel <-> crop coordinates of the points pt [(M,) N, 2]."""
     t = get_transform(center, scale, res)
     if invert:
         t = np.linalg.inv(t)
-    new_pt = np.array([pt[0], pt[1], 1.0])
-    return np.dot(t, new_pt)[:2]
+    return do_transfrom(pt, t)
 
 
 def transform_preds(coords, center, scale, res):
-    """transforms.py:214-228: heat-map coordinates [K,2] of one person -> image coordinates."""
-    coords = np.asarray(coords, dtype=np.float64).copy()
-    for p in range(coords.shape[0]):
-        coords[p, 0:2] = transform_point(coords[p, 0:2], center, scale, res, 1)
+    """transforms.py:216-221: coords [B, J, 2] in heat-map pixels, center [B,2], scale [B] -> image coordinates (in place)."""
+    for i in range(coords.shape[0]):
+        coords[i] = transform_point(coords[i], center[i], scale[i], res, invert=1)
     return coords

@@ -54,9 +54,59 @@ def final_preds_cuda(heatmaps, centers, scales, adjust_coords=True, out=None):
     return out
 
 
+def crop_boxes_cuda(frames, centers, scales, frame_of=None, inp_res=(256, 192), reverse_channels=False, out=None):
+    """All person crops of a batch in one launch (ft_crop_affine; transform_image / cv2.warpAffine semantics).
+    frames: CUDA uint8 [F,H,W,C] (cv2 layout) or float32 [F,C,H,W] / [F,H,W,C]-strided view; centers [N,2], scales [N]
+    CUDA fp32; frame_of [N] int32 or None (all crops from frame 0) -> CUDA fp32 [N,C,res_h,res_w]."""
+    if not frames.is_cuda:
+        raise RuntimeError("crop_boxes_cuda needs CUDA tensors (no CPU path)")
+    is_u8 = frames.dtype == torch.uint8
+    assert is_u8 or frames.dtype == torch.float32
+    if is_u8:                                    # [F,H,W,C]
+        F_, H, W, C = frames.shape
+        sn, sh, sw, sc = frames.stride()
+    else:                                        # [F,C,H,W]
+        F_, C, H, W = frames.shape
+        sn, sc, sh, sw = frames.stride()
+    N = centers.shape[0]
+    if out is None:
+        out = torch.empty(N, C, inp_res[0], inp_res[1], device=frames.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ft_crop_affine(frames.data_ptr(), int(is_u8), sn, sc, sh, sw, H, W, C, centers.data_ptr(), scales.data_ptr(),
+                                         frame_of.data_ptr() if frame_of is not None else None, N, inp_res[0], inp_res[1],
+                                         int(bool(reverse_channels)), out.data_ptr(), engine.stream_ptr()), "crop_affine")
+    return out
+
+
+def nms_cuda(dets, thresh, counts=None, inclusive=True):
+    """Greedy NMS of every frame in one launch (ft_nms).  dets: CUDA fp32 [F,N,5]; counts: CUDA int32 [F] or None
+    -> (keep int32 [F,N] original indices in descending score order, -1 padded; num_keep int32 [F])."""
+    if not dets.is_cuda:
+        raise RuntimeError("nms_cuda needs CUDA tensors (no CPU path)")
+    assert dets.dtype == torch.float32 and dets.is_contiguous() and dets.dim() == 3 and dets.shape[2] == 5
+    F_, N, _ = dets.shape
+    keep = torch.empty(F_, N, dtype=torch.int32, device=dets.device)
+    num = torch.empty(F_, dtype=torch.int32, device=dets.device)
+    _lib.check(_lib.lib().ft_nms(dets.data_ptr(), counts.data_ptr() if counts is not None else None, F_, N, float(thresh), int(bool(inclusive)),
+                                 keep.data_ptr(), num.data_ptr(), engine.stream_ptr()), "nms")
+    return keep, num
+
+
+def nms(dets, thresh):
+    """detection.model.nms_wrapper.nms / pth_nms signature (lib/detection/nms/pth_nms.py:5-46): dets tensor [N,5] ->
+    LongTensor of kept indices, highest score first.  A CPU tensor takes the reference's cpu_nms rule (IoU >= thresh,
+    src/nms.c:57), a CUDA tensor its gpu rule (IoU > thresh, nms_kernel.cu:62); both run on the GPU here."""
+    inclusive = not dets.is_cuda
+    d = dets.detach().float().contiguous().cuda().unsqueeze(0)
+    if d.shape[1] == 0:
+        return torch.zeros(0, dtype=torch.long, device=dets.device)
+    keep, num = nms_cuda(d, thresh, inclusive=inclusive)
+    return keep[0, :int(num[0].item())].long().to(dets.device)
+
+
 @torch.no_grad()
 def pose_est(net, im, boxes, inp_res=(256, 192), max_batch=32, flip_test=False):
-    """im: HxWx3 ndarray (BGR, as loaded by cv2); boxes: ndarray [N,4] -> keypoints ndarray [N, num_kpts, 3]."""
+    """im: HxWx3 ndarray (BGR, as loaded by cv2); boxes: ndarray [N,4] -> keypoints ndarray [N, num_kpts, 3].
+    The frame is uploaded once; crops, network and decode run on the GPU."""
     if flip_test:
         raise NotImplementedError("flip_test is not on the hot path (the reference accepts the flag and ignores it, net_utils.py:36)")
     boxes = np.asarray(boxes)
@@ -64,15 +114,19 @@ def pose_est(net, im, boxes, inp_res=(256, 192), max_batch=32, flip_test=False):
     if n == 0:
         return np.zeros((0, getattr(net, "num_classes", 17), 3), np.float32)
     centers, scales = boxes_to_center_scale(boxes, inp_res)
-    crops = torch.stack([transform_image(im, centers[i], scales[i], inp_res) for i in range(n)]).float()
     dev = next(net.parameters()).device
+    frame = torch.from_numpy(np.ascontiguousarray(im)).to(dev)
+    if frame.dtype != torch.uint8:
+        frame = frame.float().permute(2, 0, 1).contiguous()          # [C,H,W] fp32
+    frame = frame.unsqueeze(0)
+    c_all = torch.from_numpy(centers.astype(np.float32)).to(dev)
+    s_all = torch.from_numpy(scales.astype(np.float32)).to(dev)
     outs = []
     for s in range(0, n, max_batch):
         e = min(n, s + max_batch)
-        hm = net(crops[s:e].to(dev, non_blocking=True))
-        c = torch.from_numpy(centers[s:e].astype(np.float32)).to(dev)
-        sc = torch.from_numpy(scales[s:e].astype(np.float32)).to(dev)
-        outs.append(final_preds_cuda(hm, c, sc, True))
+        crops = crop_boxes_cuda(frame, c_all[s:e].contiguous(), s_all[s:e].contiguous(), None, inp_res)
+        hm = net(crops)
+        outs.append(final_preds_cuda(hm, c_all[s:e].contiguous(), s_all[s:e].contiguous(), True))
     return torch.cat(outs).cpu().numpy()
 
 

@@ -28,6 +28,8 @@
  *   ft_upsample4x            nn.Upsample(scale_factor=4, bilinear|nearest)          lib/flownet/networks/FlowNetS.py:58, models.py:32,59-60
  *   ft_decode_keypoints      max_preds + final_preds + transform_preds              lib/pose/utils/evaluation.py:11-35, transforms.py:173-228
  *   ft_box_propagation       box_propagation                                       lib/tracking/flow_utils.py:7-35
+ *   ft_crop_affine           transform_image (cv2.warpAffine) per person box         lib/tracking/net_utils.py:48-57, lib/pose/utils/transforms.py:231-240
+ *   ft_nms                   pth_nms / cpu_nms / nms_kernel                          lib/detection/nms/pth_nms.py:5-46, src/nms.c:36-62, src/cuda/nms_kernel.cu:13-70
  */
 #ifndef FLOWTRACK_B200_H_
 #define FLOWTRACK_B200_H_
@@ -39,7 +41,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 5
+#define FT_ABI_VERSION 6
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -195,6 +197,24 @@ int ft_decode_keypoints(const float* hm, int N, int C, int h, int w, const float
  * before the look-up (the reference indexes unclamped, lib/tracking/flow_utils.py:23-24).             */
 int ft_box_propagation(const float* kps, const int32_t* frame_of, int N, int K, const float* flow,
                        int B, int H, int W, float* boxes, void* stream);
+
+/* ---- tracking glue either side of the networks ------------------------------ */
+/* Person crops of pose_est (lib/tracking/net_utils.py:48-57 -> transforms.py:231-240 transform_image ->
+ * cv2.warpAffine, bilinear, zero border), every box of a batch in one launch.  frames: N_f images addressed by
+ * element strides (sn frame, sc channel, sh row, sw column), uint8 (is_u8 != 0: the reference's cv2 frames,
+ * bit-exact with cv2.warpAffine's fixed-point bilinear path) or float32; centers [N,2] / scales [N] as in pose_est
+ * (box centre, max(box_h, box_w/out_w*out_h)); frame_of [N] int32 (NULL: frame 0) -> out [N,C,out_h,out_w] fp32.
+ * reverse_channels != 0 writes channel c to C-1-c (RGB frames of the flow input -> the BGR crops pose_est feeds). */
+int ft_crop_affine(const void* frames, int is_u8, long long sn, long long sc, long long sh, long long sw,
+                   int H, int W, int C, const float* centers, const float* scales, const int32_t* frame_of,
+                   int N, int out_h, int out_w, int reverse_channels, float* out, void* stream);
+/* Greedy box NMS per frame (net_utils.py:29-32 -> detection/nms/pth_nms.py:5-46).  dets [frames,N,5] =
+ * (x1,y1,x2,y2,score), counts [frames] valid boxes per frame (NULL: N), N <= 1024.  inclusive != 0 suppresses at
+ * IoU >= thresh (cpu_nms, src/nms.c:57 -- the variant the tracking path reaches with its CPU tensor), 0 at
+ * IoU > thresh (nms_kernel.cu:62).  keep [frames,N] int32: indices of the kept boxes in descending score order
+ * (-1 beyond num_keep[frame]).                                                                        */
+int ft_nms(const float* dets, const int32_t* counts, int frames, int N, float thresh, int inclusive,
+           int32_t* keep, int32_t* num_keep, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,118 @@
+"""TEST INFRASTRUCTURE ONLY (oracle): CPU restatements of the tracking glue either side of the two networks --
+person crops and greedy box NMS (row 2).  Only tests/, __graft_entry__.smoke() and bench.py's
+CPU legs may import this.
+
+  get_transform / crop_boxes   lib/pose/utils/transforms.py:173-184,231-240 + lib/tracking/net_utils.py:48-57
+                               (transform_image -> cv2.warpAffine(img, t[:2], (res[1], res[0])), bilinear, zero border)
+  warp_affine_fixed            restatement of OpenCV's bilinear warpAffine (third-party, un-vendored; this image ships
+                               opencv-python 4.13.0; the reference pins no version): modules/imgproc/src/imgwarp.cpp,
+                               WarpAffineInvoker + remapBilinear fixed-point path.  Pinned against cv2.warpAffine itself
+                               (tests/test_oracle_golden.py: bit-exact on uint8 images) and against crops produced by the
+                               reference's own transform_image (tests/golden/reference_outputs.npz, keys crop_*).
+  nms_cpu                      lib/detection/nms/src/nms.c:36-62 (cpu_nms: suppress at IoU >= thresh) with the ordering
+                               of pth_nms.py:13-22; inclusive=False gives the GPU variant (nms_kernel.cu:62, IoU > thresh).
+                               The reference extension needs TH/cffi (gone): parity of this restatement is pinned by
+                               hand-checked cases and set properties only ("parity unpinned" against reference output).
+"""
+import numpy as np
+
+
+def get_transform(center, scale, res):
+    t = np.eye(3)
+    t[0, 0] = t[1, 1] = res[0] / scale
+    t[0, 2] = -res[0] * center[0] / scale + 0.5 * res[1]
+    t[1, 2] = -res[0] * center[1] / scale + 0.5 * res[0]
+    return t
+
+
+def boxes_to_center_scale(boxes, inp_res=(256, 192)):
+    boxes = np.asarray(boxes, dtype=np.float64)
+    centers = np.stack((boxes[:, [0, 2]].mean(1), boxes[:, [1, 3]].mean(1)), axis=1)
+    scales = np.maximum(boxes[:, 3] - boxes[:, 1], (boxes[:, 2] - boxes[:, 0]) / inp_res[1] * inp_res[0])
+    return centers, scales
+
+
+def warp_affine_fixed(img, M, res):
+    """img: [H,W,C] uint8 or float; M: 2x3 forward map; res = (h, w) -> [h,w,C] (uint8 in -> uint8 out, else float32)."""
+    M = np.asarray(M, dtype=np.float64)[:2].copy().ravel()
+    D = M[0] * M[4] - M[1] * M[3]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22 = M[4] * D, M[0] * D
+    M[0], M[1], M[3], M[4] = A11, M[1] * -D, M[3] * -D, A22
+    b1 = -M[0] * M[2] - M[1] * M[5]
+    b2 = -M[3] * M[2] - M[4] * M[5]
+    M[2], M[5] = b1, b2
+    h, w = res
+    H, W = img.shape[:2]
+    xs, ys = np.arange(w), np.arange(h)
+    ad = np.rint(M[0] * xs * 1024).astype(np.int64)
+    bd = np.rint(M[3] * xs * 1024).astype(np.int64)
+    X0 = np.rint((M[1] * ys + M[2]) * 1024).astype(np.int64) + 16
+    Y0 = np.rint((M[4] * ys + M[5]) * 1024).astype(np.int64) + 16
+    X = (X0[:, None] + ad[None, :]) >> 5
+    Y = (Y0[:, None] + bd[None, :]) >> 5
+    sx, sy = np.clip(X >> 5, -32768, 32767), np.clip(Y >> 5, -32768, 32767)
+    fx, fy = X & 31, Y & 31
+    is_u8 = img.dtype == np.uint8
+    src = img.astype(np.int64) if is_u8 else img.astype(np.float32)
+    if src.ndim == 2:
+        src = src[:, :, None]
+
+    def px(yy, xx):
+        ok = (yy >= 0) & (yy < H) & (xx >= 0) & (xx < W)
+        return src[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)] * ok[..., None]
+
+    w00, w01, w10, w11 = (32 - fx) * (32 - fy), fx * (32 - fy), (32 - fx) * fy, fx * fy
+    if is_u8:
+        s = px(sy, sx) * w00[..., None] + px(sy, sx + 1) * w01[..., None] + px(sy + 1, sx) * w10[..., None] + px(sy + 1, sx + 1) * w11[..., None]
+        return ((s + 512) >> 10).astype(np.uint8)
+    k = np.float32(1.0 / 1024.0)
+    f = lambda wt: (wt.astype(np.float32) * k)[..., None]
+    return (px(sy, sx) * f(w00) + px(sy, sx + 1) * f(w01) + px(sy + 1, sx) * f(w10) + px(sy + 1, sx + 1) * f(w11)).astype(np.float32)
+
+
+def crop_boxes(img, boxes, inp_res=(256, 192), use_cv2=False):
+    """pose_est's crop loop: img [H,W,C] -> crops [N,C,res_h,res_w] float32 (values as warpAffine returns them)."""
+    centers, scales = boxes_to_center_scale(boxes, inp_res)
+    out = []
+    for c, s in zip(centers, scales):
+        M = get_transform(c, s, inp_res)[:2]
+        if use_cv2:
+            import cv2
+            o = cv2.warpAffine(img, M, (inp_res[1], inp_res[0]))
+            if o.ndim == 2:
+                o = o[:, :, None]
+        else:
+            o = warp_affine_fixed(img, M, inp_res)
+        out.append(o.transpose(2, 0, 1).astype(np.float32))
+    return np.stack(out) if out else np.zeros((0, img.shape[2], inp_res[0], inp_res[1]), np.float32)
+
+
+def nms_cpu(dets, thresh, inclusive=True):
+    """dets: [N,5] float32 (x1,y1,x2,y2,score) -> indices of the kept boxes, highest score first."""
+    dets = np.asarray(dets, dtype=np.float32)
+    n = dets.shape[0]
+    if n == 0:
+        return np.zeros((0,), np.int64)
+    x1, y1, x2, y2, sc = (dets[:, i] for i in range(5))
+    areas = (x2 - x1 + np.float32(1)) * (y2 - y1 + np.float32(1))
+    order = np.lexsort((np.arange(n), -sc.astype(np.float64)))          # descending score, ties by index
+    suppressed = np.zeros(n, bool)
+    keep = []
+    one, zero = np.float32(1), np.float32(0)
+    for _i in range(n):
+        i = order[_i]
+        if suppressed[i]:
+            continue
+        keep.append(i)
+        for _j in range(_i + 1, n):
+            j = order[_j]
+            if suppressed[j]:
+                continue
+            w = max(zero, min(x2[i], x2[j]) - max(x1[i], x1[j]) + one)
+            h = max(zero, min(y2[i], y2[j]) - max(y1[i], y1[j]) + one)
+            inter = np.float32(w * h)
+            ovr = inter / (areas[i] + areas[j] - inter)
+            if (ovr >= thresh) if inclusive else (ovr > thresh):
+                suppressed[j] = True
+    return np.asarray(keep, np.int64)

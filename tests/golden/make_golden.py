@@ -135,9 +135,28 @@ def make_decode(ref_eval, ref_tf, out):
     print("decode ok", coords.shape, scores.shape)
 
 
+def make_track(ref_tf):
+    """Person crops through the reference's own transform_image (transforms.py:231-240) with pose_est's centre/scale
+    rule (net_utils.py:49-50); stored in a separate small file (reference_track.npz)."""
+    img = recipes.track_frame()
+    boxes = recipes.TRACK_BOXES
+    res = recipes.TRACK_RES
+    centers = np.stack((boxes[:, [0, 2]].mean(1), boxes[:, [1, 3]].mean(1)), axis=1)
+    scales = np.maximum(boxes[:, 3] - boxes[:, 1], (boxes[:, 2] - boxes[:, 0]) / res[1] * res[0])
+    crops = np.stack([ref_tf.transform_image(img, centers[i], scales[i], res).numpy() for i in range(len(boxes))])
+    crops_f = np.stack([ref_tf.transform_image(img.astype(np.float32), centers[i], scales[i], res).numpy() for i in range(len(boxes))])
+    path = os.path.join(HERE, "reference_track.npz")
+    np.savez_compressed(path, crops_u8=crops, crops_f32=crops_f, centers=centers, scales=scales)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB", crops.shape, crops.dtype)
+
+
 def main():
     out = {}
     ref_pose, ref_eval, ref_tf = import_reference_pose()
+    if "--track-only" in sys.argv:
+        make_track(ref_tf)
+        return
+    make_track(ref_tf)
     make_pose(ref_pose, out)
     make_decode(ref_eval, ref_tf, out)
     ref_flow = import_reference_flow()

@@ -1,4 +1,5 @@
 """Seeded weight/input recipes shared by make_golden.py (reference side) and the tests (oracle side)."""
+import numpy as np
 import torch
 
 from oracle import flow_oracle, pose_oracle
@@ -34,3 +35,16 @@ def decode_heatmaps():
     hm[0, 3] = -hm[0, 3].abs()      # all-negative map: score <= 0 -> coords zeroed
     hm[1, 5, 0, 7] = 9.0            # maximum on the border: no quarter-pixel shift
     return hm
+
+
+# ---- tracking glue (person crops) ----
+TRACK_RES = (64, 48)
+TRACK_BOXES = np.array([[10.0, 5.0, 60.0, 90.0], [50.5, 20.25, 120.0, 80.0], [-20.0, -10.0, 40.0, 50.5], [100.0, 60.0, 127.0, 95.0]])
+
+
+def track_frame():
+    """A deterministic 96x128 BGR uint8 frame (smooth gradients + noise, so interpolation errors are visible)."""
+    rng = np.random.default_rng(7)
+    yy, xx = np.mgrid[0:96, 0:128]
+    base = np.stack([(xx * 2) % 256, (yy * 3) % 256, (xx + yy) % 256], axis=2)
+    return ((base + rng.integers(0, 64, base.shape)) % 256).astype(np.uint8)

@@ -2,6 +2,7 @@
 (tests/golden/make_golden.py).  This is what pins the oracle (the reference has no
 golden vectors of its own, only parameter-count doc-strings, which are checked here too)."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -109,3 +110,51 @@ def test_ops_c_restatement_vs_vectorised():
 
 def test_correlation_shape_flownetc():
     assert ops_oracle.correlation_shape(48, 64, 20, 1, 20, 1, 2) == (441, 48, 64)
+
+
+# ---- tracking glue: person crops and NMS (row 2) ----
+def test_crop_oracle_matches_reference_transform_image():
+    """oracle.track_oracle.warp_affine_fixed (restated OpenCV bilinear warpAffine) == crops produced by the reference's
+    own transform_image (tests/golden/reference_track.npz), bit for bit on the uint8 frame."""
+    from oracle import track_oracle
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_track.npz"))
+    img = recipes.track_frame()
+    c, s = track_oracle.boxes_to_center_scale(recipes.TRACK_BOXES, recipes.TRACK_RES)
+    np.testing.assert_array_equal(c, g["centers"])
+    np.testing.assert_array_equal(s, g["scales"])
+    crops = track_oracle.crop_boxes(img, recipes.TRACK_BOXES, recipes.TRACK_RES)
+    np.testing.assert_array_equal(crops.astype(np.uint8), g["crops_u8"])
+    crops_f = track_oracle.crop_boxes(img.astype(np.float32), recipes.TRACK_BOXES, recipes.TRACK_RES)
+    np.testing.assert_allclose(crops_f, g["crops_f32"], rtol=0, atol=1e-4)
+
+
+def test_crop_oracle_matches_cv2_on_random_boxes():
+    cv2 = pytest.importorskip("cv2")
+    from oracle import track_oracle
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    for i in range(12):
+        c = (rng.uniform(-20, 180), rng.uniform(-20, 140))
+        s = rng.uniform(15, 300)
+        res = (64, 48) if i % 2 else (128, 96)
+        M = track_oracle.get_transform(c, s, res)[:2]
+        np.testing.assert_array_equal(track_oracle.warp_affine_fixed(img, M, res), cv2.warpAffine(img, M, (res[1], res[0])))
+
+
+def test_nms_oracle_hand_cases_and_properties():
+    from oracle import track_oracle
+    d = np.array([[0, 0, 10, 10, .9], [1, 1, 11, 11, .8], [20, 20, 30, 30, .7], [0, 0, 10, 10, .95], [21, 21, 31, 31, .1]], np.float32)
+    # IoU(box0, box1) = 100/142 = 0.704, IoU(box2, box4) = 0.704, box3 == box0
+    assert track_oracle.nms_cpu(d, 0.5).tolist() == [3, 2]
+    assert track_oracle.nms_cpu(d, 0.75).tolist() == [3, 1, 2, 4]
+    assert track_oracle.nms_cpu(d, 1.0, inclusive=True).tolist() == [3, 1, 2, 4]      # identical boxes: IoU == 1 >= 1 suppresses
+    assert track_oracle.nms_cpu(d, 1.0, inclusive=False).tolist() == [3, 0, 1, 2, 4]  # the GPU rule (>) keeps them
+    rng = np.random.default_rng(0)
+    xy = rng.uniform(0, 200, (200, 2)).astype(np.float32)
+    wh = rng.uniform(5, 80, (200, 2)).astype(np.float32)
+    dets = np.concatenate([xy, xy + wh, rng.permutation(200).astype(np.float32)[:, None] / 200], axis=1)
+    keep = track_oracle.nms_cpu(dets, 0.3)
+    assert len(set(keep.tolist())) == len(keep) and np.all(np.diff(dets[keep, 4]) < 0)   # unique, descending score
+    assert keep[0] == dets[:, 4].argmax()
+    again = track_oracle.nms_cpu(dets[keep], 0.3)                                         # idempotent on its own output
+    assert again.tolist() == list(range(len(keep)))

@@ -76,3 +76,29 @@ def test_synthetic_batch_is_seeded_and_consistent():
     np.testing.assert_allclose(s, np.maximum(bx[:, 3] - bx[:, 1], (bx[:, 2] - bx[:, 0]) / 48 * 64), rtol=1e-6)   # net_utils.py:49-50
     kp = a["prev_keypoints"].numpy()
     assert (kp[:, :, 0] >= bx[:, None, 0]).all() and (kp[:, :, 0] <= bx[:, None, 2]).all()
+
+
+def test_flo_writer_bytes_and_roundtrip(tmp_path):
+    """Middlebury .flo layout (reference lib/flownet/utils/flow_utils.py:5-55): magic float 202021.25, int32 w, int32 h,
+    interleaved (u, v) float32 rows -- checked against hand-packed bytes, then read back."""
+    import struct
+
+    import numpy as np
+    import torch
+
+    from flowtrack.pytorch_b200.flownet.utils import flow_utils
+    u = np.array([[1.5, -2.0, 3.25], [0.0, 7.0, -8.5]], np.float32)
+    v = np.array([[10.0, 20.0, 30.0], [-1.0, -2.0, -3.0]], np.float32)
+    want = struct.pack("<f", 202021.25) + struct.pack("<ii", 3, 2) + b"".join(struct.pack("<ff", u[r, c], v[r, c]) for r in range(2) for c in range(3))
+    assert want[:4] == b"PIEH"
+    p = tmp_path / "a.flo"
+    flow_utils.writeFlow(str(p), np.stack((u, v), axis=2))
+    assert p.read_bytes() == want
+    flow_utils.writeFlow(str(p), u, v)
+    assert p.read_bytes() == want
+    flow_utils.writeFlow(str(p), torch.from_numpy(np.stack((u, v))))          # the network's [2,H,W] output
+    assert p.read_bytes() == want
+    back = flow_utils.readFlow(str(p))
+    assert back.shape == (2, 3, 2) and np.array_equal(back[:, :, 0], u) and np.array_equal(back[:, :, 1], v)
+    (tmp_path / "bad.flo").write_bytes(b"\x00" * 16)
+    assert flow_utils.readFlow(str(tmp_path / "bad.flo")) is None
