@@ -26,6 +26,8 @@ import sys
 import tempfile
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -101,7 +103,7 @@ def cpu_reference_runner(pairs_per_step):
     own PyTorch CPU kernels through the oracle's restated modules (oracle/{pose,flow,decode}_oracle.py)."""
     import torch
     from flowtrack.pytorch_b200.tracking import synthetic
-    from oracle import decode_oracle, flow_oracle, pose_oracle
+    from oracle import decode_oracle, flow_oracle, pose_oracle, track_oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
@@ -109,12 +111,22 @@ def cpu_reference_runner(pairs_per_step):
     synthetic.condition_pose_weights(pose, 0)
     flow = flow_oracle.FlowNet2S(None).eval()
     d = synthetic.frame_pair_batch(pairs_per_step, PEOPLE, FRAME_HW, CROP_HW, seed=1)
+    boxes_np = d["boxes"].numpy()
+    try:
+        import cv2  # noqa: F401
+        have_cv2 = True
+    except Exception:
+        have_cv2 = False
 
     def step():
         with torch.no_grad():
             fl = flow(d["pair"]).numpy()
             boxes = [decode_oracle.box_propagation(d["prev_keypoints"][i * PEOPLE:(i + 1) * PEOPLE].numpy(), fl[i]) for i in range(pairs_per_step)]
-            hm = pose(d["crops"]).numpy()
+            # pose_est's crop loop (net_utils.py:52-57): one warpAffine per person box out of the pair's current frame (BGR)
+            frames = d["pair"][:, :, 1].permute(0, 2, 3, 1).numpy()[:, :, :, ::-1]
+            crops = np.concatenate([track_oracle.crop_boxes(np.ascontiguousarray(frames[i]), boxes_np[i * PEOPLE:(i + 1) * PEOPLE], CROP_HW, use_cv2=have_cv2)
+                                    for i in range(pairs_per_step)])
+            hm = pose(torch.from_numpy(crops)).numpy()
             kps, sc = decode_oracle.final_preds(hm, d["centers"].numpy(), d["scales"].numpy(), True)
         return kps, sc, boxes
 
@@ -150,11 +162,11 @@ def run_reference(args):
 
 def workload_config(world, pairs_per_gpu):
     return {"workload": "config4 joint pipeline: per GPU and step %d frame pairs = FlowNet2S [%d,3,2,%d,%d] + PoseResNet-50 on %d crops [%d,3,%d,%d] "
-                        "(P=%d people/frame) + heat-map decode + flow box propagation" % (pairs_per_gpu, pairs_per_gpu, FRAME_HW[0], FRAME_HW[1],
+                        "(P=%d people/frame, crops cut from the current frame by the warpAffine rule of pose_est) + heat-map decode + flow box propagation" % (pairs_per_gpu, pairs_per_gpu, FRAME_HW[0], FRAME_HW[1],
                                                                                            pairs_per_gpu * PEOPLE, pairs_per_gpu * PEOPLE, CROP_HW[0], CROP_HW[1], PEOPLE),
             "pairs_per_gpu": pairs_per_gpu, "people_per_frame": PEOPLE, "global_pairs": pairs_per_gpu * world,
             "parallelism": "frame pairs sharded over %d GPU(s), one all-gather of key-point records per step" % world,
-            "l2": "no explicit flush: a step streams ~113 MB of inputs and several GB of activations, far beyond the 126 MB L2",
+            "l2": "no explicit flush: a step streams ~75 MB of inputs and several GB of activations, far beyond the 126 MB L2",
             "weights": "random-init (reference init + conditioned BatchNorm/head, seed 0)"}
 
 
@@ -186,7 +198,7 @@ def run_ours(args):
     pose = synthetic.condition_pose_weights(pose_models.deconv("resnet50", 17, False), 0).cuda()
     flow = flow_models.FlowNet2S(None).cuda()
     pose.precision = flow.precision = args.precision
-    pipe = pl.FramePairPipeline(pose, flow, args.pairs, PEOPLE, FRAME_HW, CROP_HW, dev)
+    pipe = pl.FramePairPipeline(pose, flow, args.pairs, PEOPLE, FRAME_HW, CROP_HW, dev, crops_from_frames=not args.host_crops)
     data = synthetic.frame_pair_batch(args.pairs, PEOPLE, FRAME_HW, CROP_HW, seed=100 + rank)
     pipe.process(data["pair"], data["crops"], data["centers"], data["scales"], data["prev_keypoints"])   # fills static + pinned buffers, captures
 
@@ -365,6 +377,7 @@ def main():
     ap.add_argument("--precision", default="split", choices=["split", "fast"])
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-crops", action="store_true", help="take ready-made person crops from the host instead of cutting them on the GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

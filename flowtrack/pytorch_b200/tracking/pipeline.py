@@ -43,8 +43,13 @@ def gather_keypoints(local, group=None):
 
 class FramePairPipeline:
     def __init__(self, pose_net, flow_net, pairs, people, frame_hw=(384, 512), crop_hw=(256, 192), device="cuda", use_cuda_graph=True,
-                 concurrent=True):
+                 concurrent=True, crops_from_frames=False):
+        """crops_from_frames: cut the person crops on the GPU (ft_crop_affine, the cv2.warpAffine rule of pose_est,
+        net_utils.py:48-57) out of the current frame of every pair -- the frame is already on the device for the flow net --
+        instead of taking ready-made crops from the host.  The crops are the BGR view of the RGB flow input, raw 0..255
+        values, as the reference feeds them."""
         self.pose_net, self.flow_net = pose_net, flow_net
+        self.crops_from_frames = crops_from_frames
         self.pairs, self.people, self.n = pairs, people, pairs * people
         self.device = torch.device(device)
         self.frame_hw, self.crop_hw = frame_hw, crop_hw
@@ -66,11 +71,12 @@ class FramePairPipeline:
         pin = dict(dtype=torch.float32, pin_memory=True)
         n_meta, n_out = self.n * (2 + 1 + self.num_joints * 3), self.n * (self.num_joints * 3 + 4)
         self._slots = []
+        crop_shape = (0,) if crops_from_frames else tuple(self.crops.shape)       # no crop staging when they are cut on the device
         for _ in range(2):
             self._slots.append(dict(
-                h_pair=torch.empty(self.pair.shape, **pin), h_crops=torch.empty(self.crops.shape, **pin), h_meta=torch.empty(n_meta, **pin),
+                h_pair=torch.empty(self.pair.shape, **pin), h_crops=torch.empty(crop_shape, **pin), h_meta=torch.empty(n_meta, **pin),
                 h_out=torch.empty(n_out, **pin),
-                d_pair=torch.empty(self.pair.shape, **f32), d_crops=torch.empty(self.crops.shape, **f32), d_meta=torch.empty(n_meta, **f32),
+                d_pair=torch.empty(self.pair.shape, **f32), d_crops=torch.empty(crop_shape, **f32), d_meta=torch.empty(n_meta, **f32),
                 d_out=torch.empty(n_out, **f32),
                 copied=torch.cuda.Event(), done=torch.cuda.Event(), consumed=torch.cuda.Event(), busy=False))
         self._copy = torch.cuda.Stream(device=dev)
@@ -85,6 +91,8 @@ class FramePairPipeline:
                 self.flow_plan.enqueue()
         else:
             self.flow_plan.enqueue()
+        if self.crops_from_frames:
+            net_utils.crop_boxes_cuda(self.pair[:, :, 1], self.centers, self.scales, self.frame_of, self.crop_hw, reverse_channels=True, out=self.crops)
         self.pose_plan.enqueue()
         net_utils.final_preds_cuda(self.heatmaps, self.centers, self.scales, True, out=self.keypoints)
         if self.concurrent:
@@ -131,13 +139,15 @@ class FramePairPipeline:
 
     def stage(self, pairs, crops, centers, scales, prev_keypoints, slot=None):
         """Fill the pinned host staging buffers of a slot (the next one by default) with one batch; returns the slot index.
-        pairs [pairs,3,2,H,W] (RGB 0..255), crops [n,3,h,w], centers [n,2], scales [n], prev_keypoints [n,K,3] (fp32)."""
+        pairs [pairs,3,2,H,W] (RGB 0..255), crops [n,3,h,w] (ignored / None with crops_from_frames), centers [n,2],
+        scales [n], prev_keypoints [n,K,3] (fp32)."""
         k = self._next if slot is None else slot
         sl, n = self._slots[k], self.n
         if sl["busy"]:
             raise RuntimeError("slot %d still holds an uncollected batch" % k)
         sl["h_pair"].copy_(pairs)
-        sl["h_crops"].copy_(crops)
+        if not self.crops_from_frames:
+            sl["h_crops"].copy_(crops)
         m = sl["h_meta"]
         m[:2 * n].copy_(torch.as_tensor(centers, dtype=torch.float32).reshape(-1))
         m[2 * n:3 * n].copy_(torch.as_tensor(scales, dtype=torch.float32).reshape(-1))
@@ -157,12 +167,14 @@ class FramePairPipeline:
         with torch.cuda.stream(self._copy):
             self._copy.wait_event(sl["consumed"])            # the previous batch of this slot has left the device staging
             sl["d_pair"].copy_(sl["h_pair"], non_blocking=True)
-            sl["d_crops"].copy_(sl["h_crops"], non_blocking=True)
+            if not self.crops_from_frames:
+                sl["d_crops"].copy_(sl["h_crops"], non_blocking=True)
             sl["d_meta"].copy_(sl["h_meta"], non_blocking=True)
             sl["copied"].record(self._copy)
         main.wait_event(sl["copied"])
         self.pair.copy_(sl["d_pair"])
-        self.crops.copy_(sl["d_crops"])
+        if not self.crops_from_frames:
+            self.crops.copy_(sl["d_crops"])
         self.centers.copy_(sl["d_meta"][:2 * n].view(n, 2))
         self.scales.copy_(sl["d_meta"][2 * n:3 * n])
         self.prev_kps.copy_(sl["d_meta"][3 * n:].view(n, K, 3))

@@ -47,6 +47,32 @@ def test_frame_pair_pipeline_matches_oracle(graph):
     assert pipe.launches_per_step > 0 and pipe.h2d_bytes > 0 and pipe.d2h_bytes == 4 * pairs * people * (17 * 3 + 4)
 
 
+def test_frame_pair_pipeline_crops_cut_on_the_device():
+    """crops_from_frames: the crops are warpAffine'd out of the current frame on the GPU (raw 0..255 BGR values, as the
+    reference's pose_est feeds them) -- compared with the oracle crop + oracle nets on the same frames."""
+    from oracle import track_oracle
+    o_pose, o_flow, pose, flow = _nets()
+    pairs, people, frame_hw, crop_hw = 2, 2, (128, 192), (128, 96)
+    pipe = pl.FramePairPipeline(pose, flow, pairs, people, frame_hw, crop_hw, "cuda:0", crops_from_frames=True)
+    d = synthetic.frame_pair_batch(pairs, people, frame_hw, crop_hw, seed=4)
+    d["pair"] = d["pair"].round()                                           # integer pixel values: the float crop arithmetic is exact
+    for _ in range(2):
+        kps, boxes = pipe.process(d["pair"], None, d["centers"], d["scales"], d["prev_keypoints"])
+    kps = kps.clone().numpy()
+    n = pairs * people
+    crops = np.stack([track_oracle.warp_affine_fixed(d["pair"][i // people, :, 1].permute(1, 2, 0).numpy()[:, :, ::-1].copy(),
+                                                     track_oracle.get_transform(d["centers"][i].double().numpy(), float(d["scales"][i]), crop_hw)[:2], crop_hw)
+                      .transpose(2, 0, 1) for i in range(n)])
+    assert np.array_equal(pipe.crops.cpu().numpy(), crops)                  # bit-exact crops
+    with torch.no_grad():
+        r_hm = o_pose(torch.from_numpy(crops))
+    amax = r_hm.abs().max().item()
+    assert (pipe.heatmaps.cpu() - r_hm).abs().max() < 1e-3 * max(1.0, amax / 4.0)      # 1e-3 at the calibrated heat-map scale (abs-max ~4)
+    r_xy, r_sc = decode_oracle.final_preds(r_hm.numpy(), d["centers"].numpy(), d["scales"].numpy(), True)
+    assert np.abs(kps[:, :, :2] - r_xy).max() <= 1.0
+    assert pipe.h2d_bytes == 4 * (d["pair"].numel() + n * (3 + 17 * 3))     # no crops cross PCIe
+
+
 def test_pose_est_and_flow_est_reference_signatures():
     o_pose, o_flow, pose, flow = _nets()
     rng = np.random.RandomState(0)
