@@ -64,6 +64,7 @@ struct alignas(64) ConvK {
     int res_ld, res_coff;
     int in_stride, out_mul;
     int n_phase, taps, cb, kb_main, kb_total, k_pad, chunk;
+    int rev;        // tile_order: walk the tile list from the end (see ft_conv_desc.tile_order)
     int dbg_skip;   // bring-up/profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no weight loads, 4 = no MMAs (results are garbage)
     int M, m_tiles, n_tiles, num_tiles;
     int bw, bh, bn, lg_bw, lg_bh, tiles_w, tiles_h;
@@ -115,6 +116,7 @@ struct TileCoord {
 template <bool GATHER, bool PAIR = false>
 __device__ __forceinline__ TileCoord tile_coord(const ConvK& p, int tile, int cta_rank = 0) {
     TileCoord t;
+    if (p.rev) tile = p.num_tiles - 1 - tile;
     t.nt = tile % p.n_tiles;               // consecutive CTAs share the A tile (L2 reuse), differ in weights
     const int r = tile / p.n_tiles;
     if (PAIR) {                            // a pair tile = two consecutive m-tiles (one per CTA) x one n-tile
@@ -808,6 +810,7 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
                 if (int e = make_map(&k.res_map[1], k.res_lo + k.res_coff, dim, str, abox, 128, "res.lo")) return e;
         }
     }
+    k.rev = d->tile_order != 0;
     const bool pair = d->cta_pair != 0;
     FT_REQUIRE(!pair || (!gather && BN >= 64), "conv2d: cta_pair needs the TMA variant and block_n >= 64");
     k.num_tiles = k.n_phase * (pair ? (k.m_tiles + 1) / 2 : k.m_tiles) * k.n_tiles;

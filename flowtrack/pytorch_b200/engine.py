@@ -7,6 +7,7 @@ k4 s2 p1 transposed convolution split into its four output-parity 2x2 sub-convol
 7.3 item 5), and every forward step is a kernel launch in libflowtrack_b200.so.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -359,6 +360,8 @@ class Plan:
         self.graph = None
         self.taps = {}       # name -> Act / tensor, for layer-by-layer tests
         self.flops = {}      # call index -> algorithmic FLOPs (convolutions only)
+        self.alternate_tile_order = os.environ.get("FT_TILE_ORDER", "alternate") == "alternate"
+        self._rev = 0        # tile order of the next convolution (alternates: a consumer starts where its producer ended, in L2)
 
     def act(self, n, h, w, c, zero=False, xpad=(0, 0)):
         a = Act(n, h, w, c, self.device, split=True, zero=zero, xpad=xpad)
@@ -372,6 +375,9 @@ class Plan:
 
     def conv(self, layer, x, out=None, out_f32=None, res=None, name=None):
         d = layer.desc(x, out, out_f32, res, self.precision, self.impl)
+        if self.alternate_tile_order:
+            d.tile_order = self._rev
+            self._rev ^= 1
         self.calls.append(("conv2d", _lib.lib().ft_conv2d_fprop, (ctypes.byref(d),), d))
         self.flops[len(self.calls) - 1] = layer.flops(x.n, x.h, x.w)
         if name:

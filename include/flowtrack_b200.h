@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 6
+#define FT_ABI_VERSION 7
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -109,6 +109,9 @@ typedef struct {
                                Block j holds diag(f) for channels [64j, 64j+64) of the tile, where
                                f[c] = 1/scale[c] must be a power of two (the host folds BatchNorm's
                                scale into the weights of such layers), so acc += res * f exactly.   */
+    int32_t tile_order;     /* 0: the persistent CTAs walk the output tiles first image -> last image, 1: last -> first.
+                               A layer that runs in the opposite order of its producer starts on the part of its
+                               input that is still in the 126 MB L2 (engine.py alternates the order along a plan). */
 } ft_conv_desc;
 
 int         ft_abi_version(void);

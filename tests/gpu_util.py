@@ -19,12 +19,13 @@ def pack_nchw(x, cpad=None, xpad=(0, 0)):
     return a
 
 
-def run_layer(layer, x_act, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05, want_f32=False, out=None, tiling=None):
+def run_layer(layer, x_act, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05, want_f32=False, out=None, tiling=None, tile_order=0):
     ho, wo = layer.out_hw(x_act.h, x_act.w)
     if out is None:
         out = engine.Act(x_act.n, ho, wo, layer.cout, x_act.hi.device, zero=True)
     f32 = torch.zeros(x_act.n, layer.cout, ho, wo, device=x_act.hi.device) if want_f32 else None
     d = layer.desc(x_act, out, f32, res, precision, impl, tiling=tiling)
+    d.tile_order = tile_order
     _lib.check(_lib.lib().ft_conv2d_fprop(ctypes.byref(d), sp()), "conv2d")
     torch.cuda.synchronize()
     return (out, f32) if want_f32 else out

@@ -201,3 +201,17 @@ def test_conv_cta_pair_tiles(name, ctor, shape, act, residual, bn, prec, tol):
     assert (f32.cpu() - ref).abs().max() <= tol * scale
     single = gpu_util.run_layer(layer, xa, res=ra, precision=prec, tiling=(layer.block_n, 0)).to_nchw(layer.cout).cpu()
     assert (got - single).abs().max() <= (2e-6 if prec == _lib.PREC_SPLIT else 1e-5) * scale     # same arithmetic, different tiling
+
+
+@pytest.mark.parametrize("name,ctor,shape,act", [c for c in CASES if c[0] in ("3x3_s2_128", "stem7x7", "deconv_batch", "l4_3x3_batch", "stem3x3_cin16", "wide_2048")],
+                         ids=["3x3_s2_128", "stem7x7", "wide_2048", "l4_3x3_batch", "deconv_batch", "stem3x3_cin16"])
+def test_reverse_tile_order_is_bit_identical(name, ctor, shape, act):
+    """ft_conv_desc.tile_order only changes the order in which the persistent CTAs visit the tiles (L2 reuse)."""
+    torch.manual_seed(1)
+    mod = ctor()
+    x = torch.randn(*shape)
+    layer = engine.conv_from_modules(mod, None, act, device="cuda")
+    xa = gpu_util.pack_nchw(x.cuda(), layer.cin_p, xpad=layer.in_xpad)
+    a, fa = gpu_util.run_layer(layer, xa, want_f32=True, tile_order=0)
+    b, fb = gpu_util.run_layer(layer, xa, want_f32=True, tile_order=1)
+    assert torch.equal(fa, fb) and torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)
