@@ -196,7 +196,9 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
 
     if (warp == TMA_WARP) {
         // =========================== TMA producer ===========================
-        if (!GATHER && lane == 0) {
+        // the whole warp runs the loop with warp-uniform values and one elected lane issues the copies: in single-lane code the
+        // compiler wraps every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST sequence (~100 cycles each)
+        if (!GATHER) {
             int it = 0;
             for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
                 const TileCoord tc = tile_coord<false, PAIR>(p, tile, cta_rank);
@@ -208,8 +210,9 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                     mbar_wait(empty_bar(s), ((it / G::STAGES) & 1) ^ 1);
                     const uint32_t stage = smem_base + s * G::STAGE;
                     const bool ldA = !(p.dbg_skip & 1), ldB = !(p.dbg_skip & 2);
-                    mbar_arrive_expect_tx(full_bar(s), (uint32_t)((ldA ? G::PLANES * A_TILE : 0) + (ldB ? G::PLANES * G::B_LOCAL : 0)));
-                    if (!ldA) {
+                    const bool leader = elect_one();
+                    if (leader) mbar_arrive_expect_tx(full_bar(s), (uint32_t)((ldA ? G::PLANES * A_TILE : 0) + (ldB ? G::PLANES * G::B_LOCAL : 0)));
+                    if (!ldA || !leader) {
                     } else if (kb < p.kb_main) {
                         // FT_K_ROW: k-block `tap` is kernel row tap (all kw taps of it, contiguous in the x-padded input)
                         const int dy = p.row_mode ? tap - p.pad : p.tap_dy[tc.phase][tap], dx = p.row_mode ? 0 : p.tap_dx[tc.phase][tap];
@@ -222,19 +225,20 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                         }
                         tma_load_4d(stage, &p.in_map[view][0], full_bar(s), cblk * BK, cx, cy, tc.n0);
                         if (SPLIT) tma_load_4d(stage + A_TILE, &p.in_map[view][1], full_bar(s), cblk * BK, cx, cy, tc.n0);
-                        if (++cblk == p.cb) cblk = 0, ++tap;
                     } else {                          // residual k-block: 64 channels of the residual tensor at the output pixels
                         const int c0 = tc.nt * BN + (kb - p.kb_main) * BK;
                         tma_load_4d(stage, &p.res_map[0], full_bar(s), c0, tc.qx0, tc.qy0, tc.n0);
                         if (SPLIT) tma_load_4d(stage + A_TILE, &p.res_map[1], full_bar(s), c0, tc.qx0, tc.qy0, tc.n0);
                     }
-                    if (!ldB) {
+                    if (kb < p.kb_main && ++cblk == p.cb) cblk = 0, ++tap;      // (tap, channel block) of the next k-block: every lane tracks it
+                    if (!ldB || !leader) {
                     } else if (PAIR) {
                         bulk_g2s(stage + G::PLANES * A_TILE, wsrc + (size_t)kb * (2 * G::B_TILE), G::B_LOCAL, full_bar(s));
                         if (SPLIT) bulk_g2s(stage + G::PLANES * A_TILE + G::B_LOCAL, wsrc + (size_t)kb * (2 * G::B_TILE) + G::B_TILE, G::B_LOCAL, full_bar(s));
                     } else {
                         bulk_g2s(stage + G::PLANES * A_TILE, wsrc + (size_t)kb * (2 * G::B_TILE), G::PLANES * G::B_TILE, full_bar(s));
                     }
+                    __syncwarp();
                 }
             }
         }
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         }
     } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===========================
-        if (lane == 0 && cta_rank == 0) {
+        if (cta_rank == 0) {          // whole warp, warp-uniform values; one elected lane issues (see the TMA producer)
             constexpr uint32_t idesc = f16_idesc(PAIR ? 2 * BM : BM, BN);
             int it = 0, acc_it = 0;                     // k-block and accumulator-stage counters (across tiles)
             for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
@@ -329,6 +333,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                         const uint32_t a_hi = smem_base + s * G::STAGE;
                         const uint32_t b_hi = a_hi + G::PLANES * A_TILE;
                         const bool main_block = kb < p.kb_main;     // residual blocks multiply by (identity * f): the W_lo term is zero
+                        if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             if (p.dbg_skip & 4) break;
@@ -349,9 +354,13 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                         }
                         if (PAIR) tc_commit_pair(empty_bar(s));   // smem slot reusable in BOTH CTAs once these MMAs retire
                         else tc_commit(empty_bar(s));
+                        if (kb == kb1 - 1) {
+                            if (PAIR) tc_commit_pair(accf_bar(a));        // chunk complete -> both CTAs' epilogues
+                            else tc_commit(accf_bar(a));
+                        }
+                        }
+                        __syncwarp();
                     }
-                    if (PAIR) tc_commit_pair(accf_bar(a));        // chunk complete -> both CTAs' epilogues
-                    else tc_commit(accf_bar(a));
                 }
             }
         } else if (PAIR && lane == 0) {

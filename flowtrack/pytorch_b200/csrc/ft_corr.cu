@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_c
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == CORR_EPI_WARPS + 1) {
-        // =========================== TMA producer ===========================
-        if (lane == 0) {
+        // =========================== TMA producer (whole warp, one elected lane issues) ===========================
+        {
             const bool ldA = !(p.dbg_skip & 1), ldB = !(p.dbg_skip & 2);
             int bit = 0, ut = 0;     // B ring stages issued / work units with chunks (phase of the A barriers)
             for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
@@ -146,18 +146,24 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_c
                             // and the B stages of the unit's first chunk follow it immediately, so the unit switch costs no bubble
                             mbar_wait(aempty_bar(kb), (ut & 1) ^ 1);
                             const uint32_t dst = a_base + kb * G::PLANES * CORR_TILE;
-                            mbar_arrive_expect_tx(afull_bar(kb), ldA ? (uint32_t)(G::PLANES * CORR_TILE) : 0u);
-                            if (ldA) {
-                                tma_load_4d(dst, &p.a_map[t.cls][0], afull_bar(kb), kb * CORR_BK, 0, t.a0, t.n);
-                                if (SPLIT) tma_load_4d(dst + CORR_TILE, &p.a_map[t.cls][1], afull_bar(kb), kb * CORR_BK, 0, t.a0, t.n);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(afull_bar(kb), ldA ? (uint32_t)(G::PLANES * CORR_TILE) : 0u);
+                                if (ldA) {
+                                    tma_load_4d(dst, &p.a_map[t.cls][0], afull_bar(kb), kb * CORR_BK, 0, t.a0, t.n);
+                                    if (SPLIT) tma_load_4d(dst + CORR_TILE, &p.a_map[t.cls][1], afull_bar(kb), kb * CORR_BK, 0, t.a0, t.n);
+                                }
                             }
+                            __syncwarp();
                         }
 #pragma unroll
                         for (int pl = 0; pl < G::PLANES; ++pl, ++bit) {
                             const int s = bit % G::STAGES;
                             mbar_wait(bempty_bar(s), ((bit / G::STAGES) & 1) ^ 1);
-                            mbar_arrive_expect_tx(bfull_bar(s), ldB ? (uint32_t)CORR_TILE : 0u);
-                            if (ldB) tma_load_4d(ring + s * CORR_TILE, &p.b_map[t.cls][pl], bfull_bar(s), kb * CORR_BK, 0, r0, t.n);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(bfull_bar(s), ldB ? (uint32_t)CORR_TILE : 0u);
+                                if (ldB) tma_load_4d(ring + s * CORR_TILE, &p.b_map[t.cls][pl], bfull_bar(s), kb * CORR_BK, 0, r0, t.n);
+                            }
+                            __syncwarp();
                         }
                     }
                 }
@@ -166,7 +172,9 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_c
         }
     } else if (warp == CORR_EPI_WARPS) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // The whole warp runs the loop with warp-uniform values; one elected lane issues the tcgen05 instructions (in single-lane
+        // code the compiler wraps every UTCHMMA in an ELECT + R2UR.BROADCAST sequence of ~100 cycles, slower than the MMA itself).
+        {
             constexpr uint32_t idesc = f16_idesc(CORR_BM, CORR_BN);
             const bool do_mma = !(p.dbg_skip & 4);
             int bit = 0, ut = 0, acc_it = 0;
@@ -186,14 +194,21 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_c
                             mbar_wait(bfull_bar(s), (bit / G::STAGES) & 1);
                             tc_fence_after();
                             const uint32_t b = ring + s * CORR_TILE;
+                            if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < CORR_BK / 16; ++k) {
-                                if (!do_mma) break;
-                                const uint64_t db = sw128_desc(b + k * 32);
-                                tc_mma_f16(d_tmem, sw128_desc(a_hi + k * 32), db, idesc, (kb > 0) || (k != 0));
-                                if (SPLIT) tc_mma_f16(d_tmem, sw128_desc(a_hi + CORR_TILE + k * 32), db, idesc, 1);
+                                for (int k = 0; k < CORR_BK / 16; ++k) {
+                                    if (!do_mma) break;
+                                    const uint64_t db = sw128_desc(b + k * 32);
+                                    tc_mma_f16(d_tmem, sw128_desc(a_hi + k * 32), db, idesc, (kb > 0) || (k != 0));
+                                    if (SPLIT) tc_mma_f16(d_tmem, sw128_desc(a_hi + CORR_TILE + k * 32), db, idesc, 1);
+                                }
+                                tc_commit(bempty_bar(s));
+                                if (!SPLIT) {
+                                    if (j == t.nch - 1) tc_commit(aempty_bar(kb));
+                                    if (kb == p.kb - 1) tc_commit(accf_bar(a));
+                                }
                             }
-                            tc_commit(bempty_bar(s));
+                            __syncwarp();
                             ++bit;
                         }
                         if (SPLIT) {   // B_lo: A_hi*B_lo
@@ -201,17 +216,20 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_c
                             mbar_wait(bfull_bar(s), (bit / G::STAGES) & 1);
                             tc_fence_after();
                             const uint32_t b = ring + s * CORR_TILE;
+                            if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < CORR_BK / 16; ++k) {
-                                if (!do_mma) break;
-                                tc_mma_f16(d_tmem, sw128_desc(a_hi + k * 32), sw128_desc(b + k * 32), idesc, 1);
+                                for (int k = 0; k < CORR_BK / 16; ++k) {
+                                    if (!do_mma) break;
+                                    tc_mma_f16(d_tmem, sw128_desc(a_hi + k * 32), sw128_desc(b + k * 32), idesc, 1);
+                                }
+                                tc_commit(bempty_bar(s));
+                                if (j == t.nch - 1) tc_commit(aempty_bar(kb));     // the unit's last use of this A k-block
+                                if (kb == p.kb - 1) tc_commit(accf_bar(a));
                             }
-                            tc_commit(bempty_bar(s));
+                            __syncwarp();
                             ++bit;
                         }
-                        if (j == t.nch - 1) tc_commit(aempty_bar(kb));     // the unit's last use of this A k-block
                     }
-                    tc_commit(accf_bar(a));
                 }
                 ++ut;
             }
@@ -325,6 +343,264 @@ __global__ void __launch_bounds__(256) corr_relayout_kernel(const float* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Variant 3: the A operand lives in TENSOR MEMORY.  A unit's in1' tile (C/64 k-blocks x hi/lo) is staged through the same
+// shared-memory ring as the in2' chunks and copied into TMEM columns [256, 512) by tcgen05.cp (issued by the MMA thread;
+// tcgen05.cp and tcgen05.mma execute in issue order, so no barrier is needed between the copy and the MMAs that read it,
+// nor between a unit's last MMA and the next unit's copy).  Shared memory then holds nothing but the ring: 5 stages of
+// 32 KiB (one k-block, hi and lo plane) = 160 KiB of operand bytes in flight instead of 80 KiB -- the main loop of variant 2 is bound by the latency of a
+// ring stage times the number of stages that fit beside the resident A tile.  Accumulators: 2 TMEM stages x 128 columns
+// (columns [0, 256)); 8 epilogue warps (two per lane quarter, two chunk rows each) release a stage right after their
+// tcgen05.ld.
+// ------------------------------------------------------------------------------------------------
+// dev instrumentation (FT_DEV_SKIP bit 64): cycles each role spends waiting, per CTA: [role][slot]
+__device__ long long g_corr_prof[148][16];
+#define MBAR_WAIT1(bar, par) do { if (p.dbg_skip & 32) mbar_wait(bar, par); else mbar_wait_spin(bar, par); } while (0)
+#define TIMED(slot, stmt) do { if (prof) { const long long t_ = clock64(); stmt; pw[slot] += clock64() - t_; } else { stmt; } } while (0)
+constexpr int C3_EPI_WARPS = 8;
+constexpr int C3_THREADS = (C3_EPI_WARPS + 2) * 32;
+constexpr int C3_ACC_STAGES = 2;
+constexpr int C3_A_COL = 256;                         // first TMEM column of the A operand: [hi: kb*32 + k*8 | lo: 128 + ...]
+
+template <bool SPLIT>
+struct Corr3Geo {
+    static constexpr int PLANES = SPLIT ? 2 : 1;
+    static constexpr int SLABS = C3_EPI_WARPS * CORR_SLAB;
+    static constexpr int STAGE = PLANES * CORR_TILE;                 // one 64-channel k-block of one operand, hi (and lo) plane
+    static constexpr int STAGES = (232448 - 1024 - 512 - SLABS) / STAGE;
+    static constexpr int SMEM = 1024 + STAGES * STAGE + SLABS + 512;
+    static_assert(STAGES >= 4 && STAGES <= 16 && SMEM <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ void tc_cp_128x256b(uint32_t d_tmem, uint64_t s_desc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(d_tmem), "l"(s_desc) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(C3_THREADS, 1) corr_tc3_kernel(const __grid_constant__ CorrK p) {
+    using G = Corr3Geo<SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t slabs = ring + G::STAGES * G::STAGE;
+    const uint32_t bar_base = slabs + G::SLABS;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (G::STAGES + s); };
+    auto accf_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + a); };
+    auto acce_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + C3_ACC_STAGES + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * G::STAGES + 2 * C3_ACC_STAGES);
+    static_assert(8 * (2 * G::STAGES + 2 * C3_ACC_STAGES + 1) <= 512, "barrier block");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool prof = (p.dbg_skip & 64) != 0;
+    long long pw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_start = clock64();
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < C3_ACC_STAGES; ++a) {
+            mbar_init(accf_bar(a), 1);
+            mbar_init(acce_bar(a), C3_EPI_WARPS * 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == C3_EPI_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == C3_EPI_WARPS + 1) {
+        // =========================== TMA producer: per unit the A stages, then the B stages of every chunk ===========================
+        if (lane == 0) {
+            const bool ldA = !(p.dbg_skip & 1), ldB = !(p.dbg_skip & 2);
+            int it = 0;
+            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+                const CorrUnit t = corr_unit(p, unit);
+                if (t.nch == 0) continue;
+                for (int j = -1; j < t.nch; ++j) {                 // j = -1: the unit's A operand
+                    const int r0 = j < 0 ? t.a0 : t.r_lo + (t.c_lo + j) * CORR_ROWS;
+                    const CUtensorMap* maps = j < 0 ? p.a_map[t.cls] : p.b_map[t.cls];
+                    const bool ld = j < 0 ? ldA : ldB;
+                    for (int kb = 0; kb < p.kb; ++kb, ++it) {
+                        const int s = it % G::STAGES;
+                        TIMED(0, MBAR_WAIT1(empty_bar(s), ((it / G::STAGES) & 1) ^ 1));
+                        mbar_arrive_expect_tx(full_bar(s), ld ? (uint32_t)G::STAGE : 0u);
+#pragma unroll
+                        for (int pl = 0; pl < G::PLANES; ++pl)
+                            if (ld) tma_load_4d(ring + s * G::STAGE + pl * CORR_TILE, &maps[pl], full_bar(s), kb * CORR_BK, 0, r0, t.n);
+                    }
+                }
+            }
+        }
+    } else if (warp == C3_EPI_WARPS) {
+        // =========================== MMA issuer (also issues the smem -> TMEM copies of A) ===========================
+        // The whole warp runs the loop with warp-uniform values; one elected lane issues the tcgen05 instructions.
+        {
+            constexpr uint32_t idesc = f16_idesc(CORR_BM, CORR_BN);
+            const bool do_mma = !(p.dbg_skip & 4);
+            const uint32_t a_tmem = tmem_base + C3_A_COL;
+            int it = 0, acc_it = 0;
+            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+                const CorrUnit t = corr_unit(p, unit);
+                if (t.nch == 0) continue;
+                for (int kb = 0; kb < p.kb; ++kb, ++it) {
+                    const int s = it % G::STAGES;
+                    TIMED(0, MBAR_WAIT1(full_bar(s), (it / G::STAGES) & 1));
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int pl = 0; pl < G::PLANES; ++pl)
+#pragma unroll
+                            for (int k = 0; k < CORR_BK / 16; ++k)
+                                tc_cp_128x256b(a_tmem + pl * 128 + kb * 32 + k * 8, sw128_desc(ring + s * G::STAGE + pl * CORR_TILE + k * 32));
+                        tc_commit(empty_bar(s));
+                    }
+                    __syncwarp();
+                }
+                for (int j = 0; j < t.nch; ++j, ++acc_it) {
+                    const int a = acc_it % C3_ACC_STAGES;
+                    TIMED(1, MBAR_WAIT1(acce_bar(a), ((acc_it / C3_ACC_STAGES) & 1) ^ 1));
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(a * CORR_BN);
+                    for (int kb = 0; kb < p.kb; ++kb, ++it) {
+                        const int s = it % G::STAGES;
+                        TIMED(2, MBAR_WAIT1(full_bar(s), (it / G::STAGES) & 1));
+                        TIMED(4, tc_fence_after());
+                        const uint32_t b = ring + s * G::STAGE;
+                        const long long t_issue = prof ? clock64() : 0;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < CORR_BK / 16; ++k) {
+                                if (!do_mma) break;
+                                const uint64_t db = sw128_desc(b + k * 32);
+                                const uint32_t ah = a_tmem + kb * 32 + k * 8;
+                                tc_mma_f16_ts(d_tmem, ah, db, idesc, (kb > 0) || (k != 0));                // A_hi * B_hi
+                                if (SPLIT) {
+                                    tc_mma_f16_ts(d_tmem, ah + 128, db, idesc, 1);                         // A_lo * B_hi
+                                    tc_mma_f16_ts(d_tmem, ah, sw128_desc(b + CORR_TILE + k * 32), idesc, 1);   // A_hi * B_lo
+                                }
+                            }
+                            const long long t_c = prof ? clock64() : 0;
+                            tc_commit(empty_bar(s));
+                            if (kb == p.kb - 1) tc_commit(accf_bar(a));
+                            if (prof) pw[6] += clock64() - t_c;
+                        }
+                        __syncwarp();
+                        if (prof) pw[5] += clock64() - t_issue;
+                    }
+                }
+            }
+        }
+    } else {
+        // =========================== epilogue (warps 0-7): warp (q, h) = TMEM lane quarter q, chunk rows 2h, 2h+1 ===========================
+        const int q = warp & 3, h = warp >> 2;
+        float* S = reinterpret_cast<float*>(smem_raw + (slabs - smem_u32(smem_raw))) + warp * (32 * 34);
+        const size_t plane = (size_t)p.H * p.W;
+        int acc_it = 0;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+            const CorrUnit t = corr_unit(p, unit);
+            const int a = t.a0 + q;
+            const int y = 2 * a + t.py, x = 2 * lane + t.px;
+            const bool valid = y < p.H && x < p.W && !(p.dbg_skip & 8);
+            float* o = p.out + (size_t)t.n * (CDS * CDS) * plane + (size_t)y * p.W + x;
+            if (t.part == 0) {
+                for (int tj = -CD + h; tj <= CD; tj += 2) {       // displacement rows outside the image: zeros
+                    const int row = a + tj;
+                    if (row >= 0 && row < t.H2c) continue;
+                    if (valid) {
+#pragma unroll
+                        for (int ti = 0; ti < CDS; ++ti) o[(size_t)((tj + CD) * CDS + ti) * plane] = 0.f;
+                    }
+                }
+            }
+            for (int j = 0; j < t.nch; ++j, ++acc_it) {
+                const int as = acc_it % C3_ACC_STAGES;
+                const int r0 = t.r_lo + (t.c_lo + j) * CORR_ROWS;
+                TIMED(0, mbar_wait(accf_bar(as), (acc_it / C3_ACC_STAGES) & 1));
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * CORR_BN);
+                uint32_t v0[32], v1[32];
+                const int row0 = r0 + 2 * h, row1 = row0 + 1;
+                const int tj0 = row0 - a, tj1 = row1 - a;
+                const bool use0 = tj0 >= -CD && tj0 <= CD && row0 < t.H2c && !(p.dbg_skip & 16);     // warp-uniform
+                const bool use1 = tj1 >= -CD && tj1 <= CD && row1 < t.H2c && !(p.dbg_skip & 16);
+                if (use0) TMEM_LD_32(t_row + (2 * h) * 32, v0);
+                if (use1) TMEM_LD_32(t_row + (2 * h + 1) * 32, v1);
+                if (use0 || use1) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(acce_bar(as));                  // this thread is done with the TMEM stage
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const bool use = rr ? use1 : use0;
+                    if (!use) continue;
+                    const int tj = rr ? tj1 : tj0;
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) S[c * 34 + lane] = __uint_as_float(rr ? v1[c] : v0[c]);
+                    __syncwarp();
+                    if (valid) {
+                        float* oc = o + (size_t)((tj + CD) * CDS) * plane;
+#pragma unroll
+                        for (int ti = 0; ti < CDS; ++ti) {
+                            const int b2 = lane + ti - CD;
+                            float val = (b2 >= 0 && b2 < 32) ? S[b2 * 34 + lane] : 0.f;
+                            val *= p.inv;
+                            if (p.leaky) val = val > 0.f ? val : 0.1f * val;
+                            oc[(size_t)ti * plane] = val;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (prof && lane == 0 && (warp == 0 || warp >= C3_EPI_WARPS)) {
+        const int role = warp == 0 ? 2 : warp - C3_EPI_WARPS;          // 0 = MMA, 1 = producer, 2 = epilogue warp 0
+        long long* o = g_corr_prof[blockIdx.x] + role * 4;
+        o[0] = pw[0], o[1] = pw[1], o[2] = pw[2], o[3] = clock64() - t_start;
+        if (role == 0) g_corr_prof[blockIdx.x][12] = pw[4], g_corr_prof[blockIdx.x][13] = pw[5], g_corr_prof[blockIdx.x][14] = pw[6];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == C3_EPI_WARPS) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+template <bool SPLIT>
+static int launch_corr3(const CorrK& k, cudaStream_t s) {
+    using G = Corr3Geo<SPLIT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(corr_tc3_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e != cudaSuccess) {
+            set_error("corr_tc3_kernel<%d>: cannot opt in to %d B of shared memory: %s", (int)SPLIT, G::SMEM, cudaGetErrorString(e));
+            return 1;
+        }
+        attr_set = true;
+    }
+    const int grid = k.num_units < 148 ? k.num_units : 148;
+    corr_tc3_kernel<SPLIT><<<grid, C3_THREADS, G::SMEM, s>>>(k);
+    return check_launch("corr_tc3_kernel");
+}
+
 template <bool SPLIT>
 static int launch_corr(const CorrK& k, cudaStream_t s) {
     using G = CorrGeo<SPLIT>;
@@ -399,6 +675,9 @@ extern "C" int ft_correlation_act(const ft_act* in1, const ft_act* in2, float* o
                 if (int e = make_map(&m[1], (const __half*)a.lo + off, dim, str, box, 128, op ? "corr.in2.lo" : "corr.in1.lo")) return e;
         }
     }
+    int variant = 2;
+    if (const char* e = getenv("FT_DEV_CORR_VARIANT")) variant = atoi(e);
+    if (variant == 3) return split ? launch_corr3<true>(k, (cudaStream_t)stream) : launch_corr3<false>(k, (cudaStream_t)stream);
     return split ? launch_corr<true>(k, (cudaStream_t)stream) : launch_corr<false>(k, (cudaStream_t)stream);
 }
 
@@ -425,4 +704,9 @@ extern "C" int ft_correlation_forward_ws(const float* in1, const float* in2, flo
         if (check_launch("corr_relayout_kernel")) return 1;
     }
     return ft_correlation_act(&a[0], &a[1], out, fuse_leaky, precision, stream);
+}
+
+// dev tool: copy the per-CTA wait-cycle counters of the last instrumented corr_tc3_kernel launch (FT_DEV_SKIP bit 64) to the host
+extern "C" int ft_dev_corr_profile(long long* host_out /* [148][16] */) {
+    return cudaMemcpyFromSymbol(host_out, g_corr_prof, sizeof(long long) * 148 * 16) == cudaSuccess ? 0 : 1;
 }

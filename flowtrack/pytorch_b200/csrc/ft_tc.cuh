@@ -42,6 +42,42 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s at 2 GHz
     }
 }
+// Spinning wait (mbarrier.test_wait never suspends the thread): for the single producer / MMA-issuer threads, whose
+// wake-up latency is on the critical path of every pipeline stage.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    if (mbar_test_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_test_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+// One lane of a converged warp (elect.sync): lets a whole warp run a role's loop with warp-uniform values -- the compiler then
+// keeps descriptors / barrier addresses in uniform registers and issues UTCHMMA / UTMALDG / UTCBAR directly, instead of
+// the ELECT + 5x R2UR.BROADCAST + branch sequence it emits around every such instruction in single-lane (divergent) code.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }

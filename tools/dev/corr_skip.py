@@ -36,3 +36,15 @@ for i in range(8):
     ts.append(e0.elapsed_time(e1))
 print("B=%d parts=%s clean=%d skip=%s %s: %.1f us (median of %d, min %.1f)" % (B, os.environ.get("FT_DEV_CORR_PARTS", "auto"), clean, os.environ.get("FT_DEV_SKIP", "0"), sys.argv[1] if len(sys.argv) > 1 else "split",
                                                        statistics.median(ts[2:]) * 1e3, len(ts) - 2, min(ts) * 1e3))
+if int(os.environ.get("FT_DEV_SKIP", "0")) & 64:
+    import ctypes
+    import numpy as np
+    buf = np.zeros((148, 16), np.int64)
+    L.ft_dev_corr_profile.argtypes = [ctypes.c_void_p]
+    L.ft_dev_corr_profile(buf.ctypes.data)
+    m = buf.astype(np.float64)
+    names = {0: "MMA      [wait A-full, wait acc-empty, wait B-full, total]", 1: "producer [wait empty, -, -, total]", 2: "epilogue0 [wait acc-full, -, -, total]"}
+    for r in range(3):
+        if r == 0:
+            print("  MMA extras [fence, issue block (elect..commit..syncwarp), commits] mean kclk:", np.round(m[:, 12:15].mean(0) / 1e3, 1))
+        print("  %-62s mean kclk: %s   (max total %.0f)" % (names[r], np.round(m[:, r * 4:r * 4 + 4].mean(0) / 1e3, 1), m[:, r * 4 + 3].max() / 1e3))
