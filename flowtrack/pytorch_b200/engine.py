@@ -255,16 +255,18 @@ class ConvLayer:
         return self._tiles[block_n]
 
     def choose_tiling(self, n, h, w, precision=_lib.PREC_SPLIT):
-        """(block_n, cta_pair) for an n x h x w input.  Measured on B200 (profiles/r01c_conv_tilings.txt): single-CTA tiles
-        of the default width win or tie everywhere in split mode -- the main loop is bound by the tensor pipe's own
-        shared-memory reads (128x128x16 MMAs need 128 B/clk of smem bandwidth), and CTA-pair 256-wide tiles only gain
-        ~10 % on the largest layers when accumulation is not chunked -- so pairs stay opt-in (FT_DEV_PAIR=1 picks the
-        widest legal pair tile) until the chunk drain of 256-column accumulators is cheaper."""
+        """(block_n, cta_pair) for an n x h x w input.  Measured on B200 with the warp-uniform MMA issue path
+        (profiles/r01i_conv_tilings.txt): CTA pairs (tcgen05 cta_group::2, 256 pixels x block_n per pair, each CTA staging half
+        of the weight tile) win on every TMA-fed layer -- deconv.6 266 -> 236 us, layer3 3x3 57 -> 46, layer4 3x3 58 -> 45,
+        FlowNet conv3_1 155 -> 133 -- because the single-CTA main loop is bound by the shared-memory fill (64 KiB per k-block
+        against 768 tensor-pipe cycles).  256-wide tiles lose with the chunked accumulation.  FT_DEV_PAIR=0 turns pairs off."""
         import os
-        if os.environ.get("FT_DEV_PAIR") == "1" and self.k_mode != _lib.K_PACKED and self.block_n >= 64:
-            for b in (256, 128, 64):
-                if b <= self.cout_pad and self.cout_pad % b == 0:
-                    return b, 1
+        pair_ok = self.k_mode != _lib.K_PACKED and self.block_n >= 64 and os.environ.get("FT_DEV_PAIR", "1") != "0"
+        if pair_ok:
+            ho, wo = self.out_hw(h, w)
+            qh, qw = (h, w) if self.kind == _lib.KIND_DECONV else (ho, wo)
+            if box_tiles(qw, qh, n) >= 2:
+                return self.block_n, 1
         return self.block_n, 0
 
     def out_hw(self, h, w):
