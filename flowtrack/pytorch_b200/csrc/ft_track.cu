@@ -1,6 +1,8 @@
 // ft_track.cu -- the tracking glue either side of the two networks, sm_100a only:
 //   ft_crop_affine  person crops for pose_est (lib/tracking/net_utils.py:48-57 -> lib/pose/utils/transforms.py:231-240
 //                   transform_image -> cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0)), all boxes of a batch in one launch
+//   ft_flip_w / ft_flip_merge  the flip test of tools/pose/main.py:289-299 (mirror the crops, run them in the same batch, mirror the
+//                   heat-maps back with the left/right joints swapped and average)
 //   ft_nms          greedy person-box NMS (lib/tracking/net_utils.py:29-32 -> lib/detection/nms/pth_nms.py:5-46,
 //                   src/nms.c:36-62 / src/cuda/nms_kernel.cu:13-70), one CTA per frame, nothing leaves the GPU
 #include "ft_common.cuh"
@@ -150,6 +152,33 @@ __global__ void __launch_bounds__(1024) nms_kernel(const float* __restrict__ det
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Flip test (tools/pose/main.py:289-299; swaplr_image / swap, lib/pose/utils/transforms.py:140-170).
+// ------------------------------------------------------------------------------------------------
+__global__ void flip_w_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int W) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows * W; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / W;
+        const int x = (int)(i - r * W);
+        dst[i] = __ldg(src + r * W + (W - 1 - x));
+    }
+}
+
+// out[n,c,y,x] = 0.5 * (hm[n,c,y,x] + hm_flipped[n, perm[c], y, W-1-x])
+__global__ void flip_merge_kernel(const float* __restrict__ hm, const float* __restrict__ hm_flipped, const int32_t* __restrict__ perm, int N, int C, int H, int W,
+                                  float* __restrict__ out) {
+    const long long total = (long long)N * C * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const long long r = i / W;
+        const int y = (int)(r % H);
+        const long long nc = r / H;
+        const int c = (int)(nc % C);
+        const long long n = nc / C;
+        const float f = __ldg(hm_flipped + ((n * C + perm[c]) * H + y) * W + (W - 1 - x));
+        out[i] = (__ldg(hm + i) + f) * 0.5f;
+    }
+}
+
 }  // namespace ft
 
 using namespace ft;
@@ -184,4 +213,24 @@ extern "C" int ft_nms(const float* dets, const int32_t* counts, int frames, int 
     }
     nms_kernel<<<frames, 1024, smem, (cudaStream_t)stream>>>(dets, counts, N, thresh, inclusive != 0, keep, num_keep);
     return check_launch("nms_kernel");
+}
+
+extern "C" int ft_flip_w(const float* src, float* dst, long long rows, int W, void* stream) {
+    FT_REQUIRE(rows >= 0 && W > 0, "flip_w: bad shape");
+    if (rows == 0) return 0;
+    FT_REQUIRE(src && dst && src != dst, "flip_w: null pointer / in-place call");
+    const long long total = rows * W;
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    flip_w_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, rows, W);
+    return check_launch("flip_w_kernel");
+}
+
+extern "C" int ft_flip_merge(const float* hm, const float* hm_flipped, const int32_t* perm, int N, int C, int H, int W, float* out, void* stream) {
+    FT_REQUIRE(N >= 0 && C > 0 && H > 0 && W > 0, "flip_merge: bad shape");
+    if (N == 0) return 0;
+    FT_REQUIRE(hm && hm_flipped && perm && out, "flip_merge: null pointer");
+    const long long total = (long long)N * C * H * W;
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    flip_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(hm, hm_flipped, perm, N, C, H, W, out);
+    return check_launch("flip_merge_kernel");
 }

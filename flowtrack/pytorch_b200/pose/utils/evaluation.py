@@ -33,3 +33,26 @@ def final_preds(heatmaps, center, scale, adjust_coords=True):
     s = scale.to(dev).float().contiguous() if torch.is_tensor(scale) else _as_dev(scale, dev)
     out = final_preds_cuda(heatmaps.contiguous().float(), c.reshape(-1, 2), s.reshape(-1), adjust_coords).cpu().numpy()
     return out[:, :, :2].astype(np.float64), out[:, :, 2:3]
+
+
+@torch.no_grad()
+def flip_test_forward(model, inputs, dataset="coco"):
+    """The flip test of tools/pose/main.py:289-299 on the GPU: output = 0.5 * (model(x) + swaplr_image(model(flip_w(x)))).
+    The mirrored crops run in the SAME batch as the originals (one forward of 2B crops); ft_flip_w / ft_flip_merge do the
+    mirroring, the left/right joint swap and the average.  inputs: CUDA fp32 [B,3,H,W] -> CUDA fp32 heat-maps [B,K,H/4,W/4]."""
+    from ... import _lib, engine
+    from .transforms import swap_permutation
+    if not inputs.is_cuda:
+        raise RuntimeError("flip_test_forward needs CUDA tensors (no CPU path)")
+    x = inputs.contiguous().float()
+    B, C, H, W = x.shape
+    both = torch.empty(2 * B, C, H, W, device=x.device, dtype=torch.float32)
+    both[:B].copy_(x)
+    L = _lib.lib()
+    _lib.check(L.ft_flip_w(x.data_ptr(), both[B:].data_ptr(), B * C * H, W, engine.stream_ptr()), "flip_w")
+    hm = model(both)
+    K, h, w = hm.shape[1:]
+    perm = torch.tensor(swap_permutation(K, dataset), dtype=torch.int32, device=x.device)
+    out = torch.empty(B, K, h, w, device=x.device, dtype=torch.float32)
+    _lib.check(L.ft_flip_merge(hm[:B].data_ptr(), hm[B:].data_ptr(), perm.data_ptr(), B, K, h, w, out.data_ptr(), engine.stream_ptr()), "flip_merge")
+    return out

@@ -33,3 +33,23 @@ def transform_preds(coords, center, scale, res):
     for i in range(coords.shape[0]):
         coords[i] = transform_point(coords[i], center[i], scale[i], res, invert=1)
     return coords
+
+
+def get_pairs(dataset="coco"):
+    """transforms.py:60-96: (joint_right, joint_left) index lists of the matched left/right joints."""
+    if dataset == "mpii":
+        return [0, 1, 2, 10, 11, 12], [5, 4, 3, 15, 14, 13]
+    if dataset == "aic":
+        return [0, 1, 2, 6, 7, 8], [3, 4, 5, 9, 10, 11]
+    if dataset == "coco":
+        return [2, 4, 6, 8, 10, 12, 14, 16], [1, 3, 5, 7, 9, 11, 13, 15]
+    raise ValueError("Not supported dataset: " + dataset)
+
+
+def swap_permutation(num_joints, dataset="coco"):
+    """Channel permutation applied by swaplr_image (transforms.py:140-170): perm[c] = the channel that lands on c."""
+    right, left = get_pairs(dataset)
+    perm = list(range(num_joints))
+    for r, l in zip(right, left):
+        perm[r], perm[l] = l, r
+    return perm

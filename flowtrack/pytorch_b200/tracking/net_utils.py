@@ -1,5 +1,6 @@
-"""pose_est / flow_est with the reference signatures (lib/tracking/net_utils.py:36-92).  `detect` (Faster R-CNN)
-is out of scope: person boxes are an input of the hot path.
+"""detect / pose_est / flow_est with the reference signatures (lib/tracking/net_utils.py:14-92).  The Faster R-CNN
+detector itself is out of scope (person boxes are an input of the hot path): `detect` takes any callable with the
+contract of the reference's `im_detect` and does the part that is on the path -- merging the propagated boxes and the NMS.
 
 Fixes relative to the literal source, each documented in SURVEY.md row A11: the batching loop's
 `end = max(...)` (net_utils.py:61) is `min`; the imports (`pose.transforms`, misspelt `transfrom_image`, :11-12)
@@ -101,6 +102,24 @@ def nms(dets, thresh):
         return torch.zeros(0, dtype=torch.long, device=dets.device)
     keep, num = nms_cuda(d, thresh, inclusive=inclusive)
     return keep[0, :int(num[0].item())].long().to(dets.device)
+
+
+def detect(net, im, person_id, thresh=0.3, prop_dets=None):
+    """lib/tracking/net_utils.py:14-34.  net: callable im -> (scores [R, num_classes], boxes [R, 4*num_classes]) (the contract
+    of detection.model.test.im_detect; the detector is not part of this package) or None (no detector: only the propagated
+    boxes survive).  Returns dets ndarray [N,5] after NMS over detected + propagated person boxes (GPU, ft_nms)."""
+    if net is not None:
+        scores, boxes = net(im)
+        scores, boxes = np.asarray(scores), np.asarray(boxes)
+        dets = np.hstack((boxes[:, 4 * person_id:4 * (person_id + 1)], scores[:, person_id][:, np.newaxis])).astype(np.float32)
+    else:
+        dets = np.zeros((0, 5), np.float32)
+    if prop_dets is not None:                   # the reference writes `prop_dets != None` (elementwise on arrays)
+        dets = np.concatenate((dets, np.asarray(prop_dets, np.float32)), axis=0)
+    if dets.shape[0] == 0:
+        return dets
+    keep = nms(torch.from_numpy(dets), thresh)
+    return dets[keep.numpy(), :]
 
 
 @torch.no_grad()

@@ -29,6 +29,7 @@
  *   ft_decode_keypoints      max_preds + final_preds + transform_preds              lib/pose/utils/evaluation.py:11-35, transforms.py:173-228
  *   ft_box_propagation       box_propagation                                       lib/tracking/flow_utils.py:7-35
  *   ft_crop_affine           transform_image (cv2.warpAffine) per person box         lib/tracking/net_utils.py:48-57, lib/pose/utils/transforms.py:231-240
+ *   ft_flip_w / ft_flip_merge  flip test: np.flip + swaplr_image + average                  tools/pose/main.py:289-299, lib/pose/utils/transforms.py:140-170
  *   ft_nms                   pth_nms / cpu_nms / nms_kernel                          lib/detection/nms/pth_nms.py:5-46, src/nms.c:36-62, src/cuda/nms_kernel.cu:13-70
  */
 #ifndef FLOWTRACK_B200_H_
@@ -41,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 7
+#define FT_ABI_VERSION 8
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -211,6 +212,13 @@ int ft_box_propagation(const float* kps, const int32_t* frame_of, int N, int K, 
 int ft_crop_affine(const void* frames, int is_u8, long long sn, long long sc, long long sh, long long sw,
                    int H, int W, int C, const float* centers, const float* scales, const int32_t* frame_of,
                    int N, int out_h, int out_w, int reverse_channels, float* out, void* stream);
+/* Flip test (tools/pose/main.py:289-299; swaplr_image, lib/pose/utils/transforms.py:140-170).
+ * ft_flip_w mirrors the last axis: src/dst [rows, W] fp32 (a [B,C,H,W] batch is rows = B*C*H).
+ * ft_flip_merge: out[n,c,y,x] = 0.5 * (hm[n,c,y,x] + hm_flipped[n, perm[c], y, W-1-x]); perm [C] int32 is the left/right
+ * joint permutation (get_pairs, transforms.py:60-96); `out` may alias `hm`.                                       */
+int ft_flip_w(const float* src, float* dst, long long rows, int W, void* stream);
+int ft_flip_merge(const float* hm, const float* hm_flipped, const int32_t* perm, int N, int C, int H, int W,
+                  float* out, void* stream);
 /* Greedy box NMS per frame (net_utils.py:29-32 -> detection/nms/pth_nms.py:5-46).  dets [frames,N,5] =
  * (x1,y1,x2,y2,score), counts [frames] valid boxes per frame (NULL: N), N <= 1024.  inclusive != 0 suppresses at
  * IoU >= thresh (cpu_nms, src/nms.c:57 -- the variant the tracking path reaches with its CPU tensor), 0 at

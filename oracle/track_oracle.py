@@ -9,6 +9,9 @@ CPU legs may import this.
                                WarpAffineInvoker + remapBilinear fixed-point path.  Pinned against cv2.warpAffine itself
                                (tests/test_oracle_golden.py: bit-exact on uint8 images) and against crops produced by the
                                reference's own transform_image (tests/golden/reference_outputs.npz, keys crop_*).
+  get_pairs / swaplr_image / flip_test_merge
+                               lib/pose/utils/transforms.py:60-96,140-170 and tools/pose/main.py:289-299 (flip test); pinned
+                               against the reference's own swaplr_image (reference_track.npz, keys swap_*).
   nms_cpu                      lib/detection/nms/src/nms.c:36-62 (cpu_nms: suppress at IoU >= thresh) with the ordering
                                of pth_nms.py:13-22; inclusive=False gives the GPU variant (nms_kernel.cu:62, IoU > thresh).
                                The reference extension needs TH/cffi (gone): parity of this restatement is pinned by
@@ -116,3 +119,28 @@ def nms_cpu(dets, thresh, inclusive=True):
             if (ovr >= thresh) if inclusive else (ovr > thresh):
                 suppressed[j] = True
     return np.asarray(keep, np.int64)
+
+
+def get_pairs(dataset="coco"):
+    if dataset == "mpii":
+        return [0, 1, 2, 10, 11, 12], [5, 4, 3, 15, 14, 13]
+    if dataset == "aic":
+        return [0, 1, 2, 6, 7, 8], [3, 4, 5, 9, 10, 11]
+    if dataset == "coco":
+        return [2, 4, 6, 8, 10, 12, 14, 16], [1, 3, 5, 7, 9, 11, 13, 15]
+    raise ValueError(dataset)
+
+
+def swaplr_image(img, dataset="coco"):
+    """img [B,K,h,w]: mirror the width axis and exchange the left/right joint channels (transforms.py:140-170)."""
+    right, left = get_pairs(dataset)
+    img = np.asarray(img)[:, :, :, ::-1].copy()
+    tmp = img[:, right].copy()
+    img[:, right] = img[:, left]
+    img[:, left] = tmp
+    return img
+
+
+def flip_test_merge(output, output_flipped, dataset="coco"):
+    """tools/pose/main.py:296-299: (output + swaplr_image(output_flipped)) * 0.5"""
+    return (np.asarray(output) + swaplr_image(output_flipped, dataset)) * np.float32(0.5)

@@ -145,8 +145,11 @@ def make_track(ref_tf):
     scales = np.maximum(boxes[:, 3] - boxes[:, 1], (boxes[:, 2] - boxes[:, 0]) / res[1] * res[0])
     crops = np.stack([ref_tf.transform_image(img, centers[i], scales[i], res).numpy() for i in range(len(boxes))])
     crops_f = np.stack([ref_tf.transform_image(img.astype(np.float32), centers[i], scales[i], res).numpy() for i in range(len(boxes))])
+    hm = recipes.flip_heatmaps()
+    swapped = {ds: ref_tf.swaplr_image(hm[:, :k].copy(), ds) for ds, k in (("coco", 17), ("mpii", 16), ("aic", 14))}
     path = os.path.join(HERE, "reference_track.npz")
-    np.savez_compressed(path, crops_u8=crops, crops_f32=crops_f, centers=centers, scales=scales)
+    np.savez_compressed(path, crops_u8=crops, crops_f32=crops_f, centers=centers, scales=scales,
+                        **{"swap_" + ds: v for ds, v in swapped.items()})
     print("wrote", path, os.path.getsize(path) // 1024, "KiB", crops.shape, crops.dtype)
 
 

@@ -48,3 +48,7 @@ def track_frame():
     yy, xx = np.mgrid[0:96, 0:128]
     base = np.stack([(xx * 2) % 256, (yy * 3) % 256, (xx + yy) % 256], axis=2)
     return ((base + rng.integers(0, 64, base.shape)) % 256).astype(np.uint8)
+
+
+def flip_heatmaps():
+    return np.random.default_rng(9).standard_normal((2, 17, 8, 6)).astype(np.float32)

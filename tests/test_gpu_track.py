@@ -111,3 +111,76 @@ def test_pose_est_reference_signature_runs_on_gpu_crops():
     assert kps.shape == (3, 17, 3)
     assert np.abs(kps[:, :, :2] - xy).max() <= 1.0 * s.max() / res[0] + 1e-3      # <= 1 heat-map... image px per heat-map px scale
     assert np.abs(kps[:, :, 2:] - sc).max() < 2e-2
+
+
+def test_flip_test_forward_matches_reference_recipe():
+    """tools/pose/main.py:289-299 on the GPU (mirrored crops in the same batch) vs the oracle net + restated swaplr_image."""
+    from flowtrack.pytorch_b200 import _lib, engine
+    from flowtrack.pytorch_b200.pose import models as pose_models
+    from flowtrack.pytorch_b200.pose.utils import evaluation
+    from flowtrack.pytorch_b200.tracking import synthetic
+    from oracle import pose_oracle
+    torch.manual_seed(0)
+    o_pose = synthetic.condition_pose_weights(pose_oracle.deconv("resnet50", 17, False), 0).eval()
+    pose = pose_models.deconv("resnet50", 17, False)
+    pose.load_state_dict(o_pose.state_dict(), strict=True)
+    pose.cuda()
+    x = torch.randn(3, 3, 128, 96, generator=torch.Generator().manual_seed(2))
+    out = evaluation.flip_test_forward(pose, x.cuda()).cpu().numpy()
+    with torch.no_grad():
+        ref = track_oracle.flip_test_merge(o_pose(x).numpy(), o_pose(torch.flip(x, dims=[3])).numpy())
+    assert out.shape == ref.shape == (3, 17, 32, 24)
+    assert np.abs(out - ref).max() < 1e-3
+    # the two kernels alone, bit-exact
+    a = torch.randn(5, 7, 6, 9, device="cuda")
+    f = torch.empty_like(a)
+    _lib.check(_lib.lib().ft_flip_w(a.data_ptr(), f.data_ptr(), 5 * 7 * 6, 9, engine.stream_ptr()), "flip_w")
+    assert torch.equal(f, torch.flip(a, dims=[3]))
+    hm, hf = torch.randn(2, 17, 8, 6, device="cuda"), torch.randn(2, 17, 8, 6, device="cuda")
+    from flowtrack.pytorch_b200.pose.utils import transforms
+    perm = torch.tensor(transforms.swap_permutation(17), dtype=torch.int32, device="cuda")
+    o = torch.empty_like(hm)
+    _lib.check(_lib.lib().ft_flip_merge(hm.data_ptr(), hf.data_ptr(), perm.data_ptr(), 2, 17, 8, 6, o.data_ptr(), engine.stream_ptr()), "flip_merge")
+    np.testing.assert_array_equal(o.cpu().numpy(), track_oracle.flip_test_merge(hm.cpu().numpy(), hf.cpu().numpy()))
+
+
+def test_process_frame_entry_point(tmp_path):
+    """tools/tracking/demo.py process_frame (reference :35-42) end to end on the GPU with a stand-in detector, and
+    tools/flownet/demo.py writing a readable .flo file from a saved checkpoint."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("ft_tracking_demo", os.path.join(root, "tools", "tracking", "demo.py"))
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    args = demo.parse_args(["--pose_backbone", "50", "--flow_net", "FlowNet2S"])
+    torch.manual_seed(0)
+    pose_net, flow_net = demo.build_nets(args)
+    rng = np.random.default_rng(0)
+    prev_im = rng.integers(0, 256, (128, 192, 3), dtype=np.uint8)
+    cur_im = rng.integers(0, 256, (128, 192, 3), dtype=np.uint8)
+    prev_dets = np.array([[20, 10, 90, 120, 0.9], [100, 30, 180, 110, 0.8]], np.float32)
+    prev_kps = net_utils.pose_est(pose_net, prev_im, prev_dets[:, :4], inp_res=(128, 96))
+
+    def fake_detector(im):          # im_detect contract: scores [R, classes], boxes [R, 4*classes]; person = class 1
+        boxes = np.zeros((2, 8), np.float32)
+        boxes[:, 4:] = [[22, 12, 92, 118], [5, 5, 40, 60]]
+        return np.array([[0.1, 0.95], [0.5, 0.6]], np.float32), boxes
+
+    dets, kps = demo.process_frame(fake_detector, pose_net, flow_net, prev_im, cur_im, prev_dets, prev_kps)
+    assert dets.shape[1] == 5 and kps.shape == (dets.shape[0], 17, 3) and 2 <= dets.shape[0] <= 4
+    assert np.all(np.diff(dets[:, 4]) <= 0) and np.isfinite(kps).all()
+    # flow demo: checkpoint in, .flo out
+    spec = importlib.util.spec_from_file_location("ft_flow_demo", os.path.join(root, "tools", "flownet", "demo.py"))
+    fdemo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fdemo)
+    import cv2
+    from flowtrack.pytorch_b200.flownet.model import models as flow_models
+    from flowtrack.pytorch_b200.flownet.utils import flow_utils
+    ck = tmp_path / "flow.pth.tar"
+    torch.save({"arch": "FlowNet2S", "epoch": 1, "state_dict": flow_models.FlowNet2S(None).state_dict(), "best_EPE": 0.0}, str(ck))
+    cv2.imwrite(str(tmp_path / "a.png"), prev_im)
+    cv2.imwrite(str(tmp_path / "b.png"), cur_im)
+    assert fdemo.main(["--input1", str(tmp_path / "a.png"), "--input2", str(tmp_path / "b.png"), "--resume", str(ck), "--save", str(tmp_path / "out")]) == 0
+    flo = flow_utils.readFlow(str(tmp_path / "out" / "output.flo"))
+    assert flo.shape == (128, 192, 2) and np.isfinite(flo).all()

@@ -158,3 +158,15 @@ def test_nms_oracle_hand_cases_and_properties():
     assert keep[0] == dets[:, 4].argmax()
     again = track_oracle.nms_cpu(dets[keep], 0.3)                                         # idempotent on its own output
     assert again.tolist() == list(range(len(keep)))
+
+
+def test_flip_oracle_matches_reference_swaplr_image():
+    from oracle import track_oracle
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_track.npz"))
+    hm = recipes.flip_heatmaps()
+    for ds, k in (("coco", 17), ("mpii", 16), ("aic", 14)):
+        np.testing.assert_array_equal(track_oracle.swaplr_image(hm[:, :k], ds), g["swap_" + ds])
+    from flowtrack.pytorch_b200.pose.utils import transforms
+    for ds, k in (("coco", 17), ("mpii", 16), ("aic", 14)):
+        perm = transforms.swap_permutation(k, ds)
+        np.testing.assert_array_equal(hm[:, :k][:, perm][:, :, :, ::-1], g["swap_" + ds])     # the permutation form the kernel uses
