@@ -271,7 +271,7 @@ def run_ours(args):
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
         traffic, ncu_note = None, None
         try:     # DRAM bytes per conv launch from the committed ncu --set full capture of the same plans (not measured in this run)
-            with open(os.path.join(ROOT, "profiles", "r01g_conv_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r01j_conv_traffic.json")) as f:
                 tr = json.load(f)
             traffic = tr["dram_bytes_per_launch"]
             ncu_note = {"tensor_pipe_active_pct_time_weighted": tr["tensor_pipe_active_pct_time_weighted"], "source": tr["source"]}
