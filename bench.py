@@ -339,6 +339,7 @@ def bench_correlation(torch, _lib, peaks):
     ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
     fns = {
         "tcgen05": lambda: _lib.check(L.ft_correlation_act(acts[0].struct(), acts[1].struct(), o.data_ptr(), 1, _lib.PREC_SPLIT, sp()), "correlation_act"),
+        "tcgen05_planar": lambda: _lib.check(L.ft_correlation_act_planar(acts[0].struct(), acts[1].struct(), o.data_ptr(), 1, _lib.PREC_SPLIT, sp()), "correlation_act_planar"),
         "tcgen05_fast": lambda: _lib.check(L.ft_correlation_act(acts[0].struct(), acts[1].struct(), o.data_ptr(), 1, _lib.PREC_FAST, sp()), "correlation_act"),
         "tcgen05_nchw_abi": lambda: _lib.check(L.ft_correlation_forward_ws(a.data_ptr(), b.data_ptr(), o.data_ptr(), B, C, H, W, 20, 1, 20, 1, 2, 1,
                                                                            _lib.PREC_SPLIT, ws.data_ptr(), nws, sp()), "correlation_ws"),
@@ -361,9 +362,12 @@ def bench_correlation(torch, _lib, peaks):
     ms = res["tcgen05"]
     byts = (2 * B * C * H * W + B * 441 * H * W) * 4
     ach = byts / (ms * 1e-3) / 1e9
-    return {"kernel": "corr_tc_kernel (tcgen05 banded GEMM, split-fp16 NHWC [32,48,64,256] x2 -> fp32 NCHW [32,441,48,64], LeakyReLU fused), L2 flushed between launches",
+    return {"kernel": "corr_pair_kernel (tcgen05 cta_group::2 banded GEMM, split-fp16 NHWC [32,48,64,256] x2 -> fp32 NCHW [32,441,48,64], LeakyReLU fused), L2 flushed between launches",
             "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "ms": ms, "algorithmic_bytes": byts,
-            "gflop": 2 * B * 441 * C * H * W / 1e9, "ms_fast_precision": res["tcgen05_fast"], "ms_fp32_nchw_abi_with_relayout": res["tcgen05_nchw_abi"],
+            "gflop": 2 * B * 441 * C * H * W / 1e9,
+            "ms_parity_planar_output": res["tcgen05_planar"], "gbs_parity_planar_output": byts / (res["tcgen05_planar"] * 1e-3) / 1e9,
+            "note_parity_planar": "same kernel writing the pipeline-internal layout [B,441,4,H/2,W/2] (dense 128-byte warp stores) that FlowNetC consumes through ft_pack_corr_planar",
+            "ms_fast_precision": res["tcgen05_fast"], "ms_fp32_nchw_abi_with_relayout": res["tcgen05_nchw_abi"],
             "ms_cuda_core_kernel": res["simt"]}
 
 

@@ -29,7 +29,7 @@ KIND_CONV, KIND_DECONV = 0, 1
 PREC_SPLIT, PREC_FAST = 0, 1
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
 K_PACKED, K_TAP64, K_ROW = 0, 1, 2
-ABI_VERSION = 8        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
+ABI_VERSION = 9        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
 
 # name -> (restype, argtypes): every symbol include/flowtrack_b200.h declares
 SIGNATURES = {
@@ -42,6 +42,8 @@ SIGNATURES = {
     "ft_correlation_forward": (c_int, [c_void_p] * 3 + [c_int] * 10 + [c_void_p]),
     "ft_correlation_tc_supported": (c_int, [c_int] * 8),
     "ft_correlation_act": (c_int, [ctypes.POINTER(FtAct)] * 2 + [c_void_p, c_int, c_int, c_void_p]),
+    "ft_correlation_act_planar": (c_int, [ctypes.POINTER(FtAct)] * 2 + [c_void_p, c_int, c_int, c_void_p]),
+    "ft_pack_corr_planar": (c_int, [c_void_p, ctypes.POINTER(FtAct), c_void_p]),
     "ft_correlation_workspace_bytes": (ctypes.c_size_t, [c_int] * 4),
     "ft_correlation_forward_ws": (c_int, [c_void_p] * 3 + [c_int] * 11 + [c_void_p, ctypes.c_size_t, c_void_p]),
     "ft_resample2d_forward": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),

@@ -56,12 +56,14 @@ struct CorrGeo {
 
 struct alignas(64) CorrK {
     CUtensorMap a_map[4][2];     // [parity class][hi, lo] of in1
-    CUtensorMap b_map[4][2];     // of in2
+    CUtensorMap b_map[4][2];     // of in2 (4-row chunk boxes)
+    CUtensorMap b2_map[4][2];    // of in2, 2-row boxes: the half chunk a CTA of a pair stages
     float* out;
     int B, H, W, C, kb;
     int a_tiles, num_tiles, parts, num_units;
     float inv;
     int leaky;
+    int planar;     // output layout: 0 = fp32 NCHW [B,441,H,W] (the reference's), 1 = parity-planar [B,441,4,ceil(H/2),ceil(W/2)] (see ft_correlation_act)
     int dbg_skip;   // profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no B loads, 4 = no MMAs, 8 = no global stores, 16 = no TMEM reads / staging (results are garbage)
 };
 
@@ -344,6 +346,313 @@ __global__ void __launch_bounds__(256) corr_relayout_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a cluster (the two SMs of a TPC) take two adjacent in1' tiles
+// (8 rows = 256 pixels, M = 256) of the same parity class; each keeps ITS tile resident and stages only HALF of every
+// in2' chunk (2 of its 4 rows), the tensor cores of both SMs read both halves.  Per SM a chunk then costs 64 KiB of
+// shared-memory fill instead of 128 KiB against the same 3072 tensor-pipe cycles -- the single-CTA main loop is bound by
+// exactly that fill (ring depth x stage latency).  The union of the two tiles' displacement windows is 28 in2' rows:
+// 16 pair-chunks per 24-row class instead of 2 x 15 tile-chunks (+7 % MMA work).
+// Protocol as in conv_tc_kernel<PAIR>: rank 0 issues every MMA; the peer's MMA warp relays "my stage is full"; commits are
+// multicast to both CTAs; the leader's acc_empty barriers count the epilogue threads of both CTAs.
+// ------------------------------------------------------------------------------------------------
+constexpr int CP_HALF = CORR_TILE / 2;                // 8 KiB: 64 in2' pixels x 64 channels, one plane
+
+template <bool SPLIT>
+struct CorrPairGeo {
+    static constexpr int PLANES = SPLIT ? 2 : 1;
+    static constexpr int A_BYTES = CORR_KB_MAX * PLANES * CORR_TILE;
+    static constexpr int SLABS = CORR_EPI_WARPS * CORR_SLAB;
+    static constexpr int STAGE = PLANES * CP_HALF;                    // one k-block of this CTA's half chunk, hi (and lo)
+    static constexpr int STAGES_FIT = (232448 - 1024 - 512 - A_BYTES - SLABS) / STAGE;
+    static constexpr int STAGES = STAGES_FIT > 10 ? 10 : STAGES_FIT;
+    static constexpr int SMEM = 1024 + A_BYTES + STAGES * STAGE + SLABS + 512;
+    static_assert(STAGES >= 4 && SMEM <= 232448, "shared memory budget");
+};
+
+struct CorrPairUnit {
+    int n, cls, py, px, a0, H2c, r_lo, c_lo, nch, part;
+};
+__device__ __forceinline__ CorrPairUnit corr_pair_unit(const CorrK& p, int unit, int rank) {
+    CorrPairUnit t;
+    const int ap_tiles = (p.a_tiles + 1) >> 1;
+    const int tile = unit / p.parts;
+    t.part = unit - tile * p.parts;
+    const int ap = tile % ap_tiles, r = tile / ap_tiles;
+    t.cls = r & 3, t.n = r >> 2;
+    t.py = t.cls >> 1, t.px = t.cls & 1;
+    const int A0 = ap * 2 * CORR_ROWS;
+    t.a0 = A0 + rank * CORR_ROWS;                                  // this CTA's in1' rows (may lie beyond the image: all padding)
+    t.H2c = (p.H - t.py + 1) >> 1;
+    t.r_lo = max(0, A0 - CD);
+    const int r_end = min(t.H2c, A0 + 2 * CORR_ROWS + CD);
+    const int chunks = r_end > t.r_lo ? (r_end - t.r_lo + CORR_ROWS - 1) / CORR_ROWS : 0;
+    const int per = (chunks + p.parts - 1) / p.parts;
+    t.c_lo = min(chunks, t.part * per);
+    t.nch = min(chunks, t.c_lo + per) - t.c_lo;
+    return t;
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(CORR_THREADS, 1) corr_pair_kernel(const __grid_constant__ CorrK p) {
+    using G = CorrPairGeo<SPLIT>;
+    const int rank = (int)cluster_ctarank();
+    const int first_unit = (int)(blockIdx.x >> 1), unit_step = (int)(gridDim.x >> 1);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t a_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ring = a_base + G::A_BYTES;
+    const uint32_t slabs = ring + G::STAGES * G::STAGE;
+    const uint32_t bar_base = slabs + G::SLABS;
+    // barrier slots: bfull[S] | bempty[S] | afull[4] | aempty[4] | accf[4] | acce[4] | tmem ptr | peer_bfull[S] | peer_afull[4]
+    auto bfull_bar = [&](int s) { return bar_base + 8u * s; };
+    auto bempty_bar = [&](int s) { return bar_base + 8u * (G::STAGES + s); };
+    auto afull_bar = [&](int k) { return bar_base + 8u * (2 * G::STAGES + k); };
+    auto aempty_bar = [&](int k) { return bar_base + 8u * (2 * G::STAGES + CORR_KB_MAX + k); };
+    auto accf_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + 2 * CORR_KB_MAX + a); };
+    auto acce_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + 2 * CORR_KB_MAX + CORR_ACC_STAGES + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * G::STAGES + 2 * CORR_KB_MAX + 2 * CORR_ACC_STAGES);
+    auto peer_bfull_bar = [&](int s) { return bar_base + 8u * (2 * G::STAGES + 2 * CORR_KB_MAX + 2 * CORR_ACC_STAGES + 1 + s); };
+    auto peer_afull_bar = [&](int k) { return bar_base + 8u * (3 * G::STAGES + 2 * CORR_KB_MAX + 2 * CORR_ACC_STAGES + 1 + k); };
+    static_assert(8 * (3 * G::STAGES + 3 * CORR_KB_MAX + 2 * CORR_ACC_STAGES + 1) <= 512, "barrier block");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G::STAGES; ++s) {
+            mbar_init(bfull_bar(s), 1);
+            mbar_init(bempty_bar(s), 1);
+            mbar_init(peer_bfull_bar(s), 1);
+        }
+        for (int k = 0; k < CORR_KB_MAX; ++k) {
+            mbar_init(afull_bar(k), 1);
+            mbar_init(aempty_bar(k), 1);
+            mbar_init(peer_afull_bar(k), 1);
+        }
+        for (int a = 0; a < CORR_ACC_STAGES; ++a) {
+            mbar_init(accf_bar(a), 1);
+            mbar_init(acce_bar(a), 2 * CORR_EPI_WARPS * 32);          // the epilogue threads of both CTAs release the stage
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == CORR_EPI_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == CORR_EPI_WARPS + 1) {
+        // =========================== TMA producer: this CTA's A tile and its half (2 rows) of every chunk ===========================
+        const bool ldA = !(p.dbg_skip & 1), ldB = !(p.dbg_skip & 2);
+        int bit = 0, ut = 0;
+        for (int unit = first_unit; unit < p.num_units; unit += unit_step) {
+            const CorrPairUnit t = corr_pair_unit(p, unit, rank);
+            if (t.nch == 0) continue;
+            for (int j = 0; j < t.nch; ++j) {
+                const int r0 = t.r_lo + (t.c_lo + j) * CORR_ROWS + 2 * rank;
+                for (int kb = 0; kb < p.kb; ++kb, ++bit) {
+                    if (j == 0) {
+                        mbar_wait_cluster(aempty_bar(kb), (ut & 1) ^ 1);
+                        const uint32_t dst = a_base + kb * G::PLANES * CORR_TILE;
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(afull_bar(kb), ldA ? (uint32_t)(G::PLANES * CORR_TILE) : 0u);
+                            if (ldA) {
+                                tma_load_4d(dst, &p.a_map[t.cls][0], afull_bar(kb), kb * CORR_BK, 0, t.a0, t.n);
+                                if (SPLIT) tma_load_4d(dst + CORR_TILE, &p.a_map[t.cls][1], afull_bar(kb), kb * CORR_BK, 0, t.a0, t.n);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    const int s = bit % G::STAGES;
+                    mbar_wait_cluster(bempty_bar(s), ((bit / G::STAGES) & 1) ^ 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(bfull_bar(s), ldB ? (uint32_t)G::STAGE : 0u);
+                        if (ldB) {
+                            tma_load_4d(ring + s * G::STAGE, &p.b2_map[t.cls][0], bfull_bar(s), kb * CORR_BK, 0, r0, t.n);
+                            if (SPLIT) tma_load_4d(ring + s * G::STAGE + CP_HALF, &p.b2_map[t.cls][1], bfull_bar(s), kb * CORR_BK, 0, r0, t.n);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            ++ut;
+        }
+    } else if (warp == CORR_EPI_WARPS) {
+        if (rank == 0) {
+            // =========================== MMA issuer (leader CTA; whole warp, one elected lane issues) ===========================
+            constexpr uint32_t idesc = f16_idesc(2 * CORR_BM, CORR_BN);
+            const bool do_mma = !(p.dbg_skip & 4);
+            int bit = 0, ut = 0, acc_it = 0;
+            for (int unit = first_unit; unit < p.num_units; unit += unit_step) {
+                const CorrPairUnit t = corr_pair_unit(p, unit, 0);
+                if (t.nch == 0) continue;
+                for (int j = 0; j < t.nch; ++j, ++acc_it) {
+                    const int a = acc_it % CORR_ACC_STAGES;
+                    mbar_wait_cluster(acce_bar(a), ((acc_it / CORR_ACC_STAGES) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(a * CORR_BN);
+                    for (int kb = 0; kb < p.kb; ++kb, ++bit) {
+                        if (j == 0) {
+                            mbar_wait(afull_bar(kb), ut & 1);
+                            mbar_wait_cluster(peer_afull_bar(kb), ut & 1);
+                        }
+                        const uint32_t a_hi = a_base + kb * G::PLANES * CORR_TILE;
+                        const int s = bit % G::STAGES;
+                        mbar_wait(bfull_bar(s), (bit / G::STAGES) & 1);
+                        mbar_wait_cluster(peer_bfull_bar(s), (bit / G::STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t b = ring + s * G::STAGE;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < CORR_BK / 16; ++k) {
+                                if (!do_mma) break;
+                                const uint64_t da = sw128_desc(a_hi + k * 32), db = sw128_desc(b + k * 32);
+                                tc_mma_f16_pair(d_tmem, da, db, idesc, (kb > 0) || (k != 0));                                   // A_hi * B_hi
+                                if (SPLIT) {
+                                    tc_mma_f16_pair(d_tmem, sw128_desc(a_hi + CORR_TILE + k * 32), db, idesc, 1);               // A_lo * B_hi
+                                    tc_mma_f16_pair(d_tmem, da, sw128_desc(b + CP_HALF + k * 32), idesc, 1);                    // A_hi * B_lo
+                                }
+                            }
+                            tc_commit_pair(bempty_bar(s));
+                            if (j == t.nch - 1) tc_commit_pair(aempty_bar(kb));
+                            if (kb == p.kb - 1) tc_commit_pair(accf_bar(a));
+                        }
+                        __syncwarp();
+                    }
+                }
+                ++ut;
+            }
+        } else if (lane == 0) {
+            // peer CTA: tell the leader when this CTA's A k-blocks / B half stages have landed (same order as the leader consumes them)
+            int bit = 0, ut = 0;
+            for (int unit = first_unit; unit < p.num_units; unit += unit_step) {
+                const CorrPairUnit t = corr_pair_unit(p, unit, 1);
+                if (t.nch == 0) continue;
+                for (int j = 0; j < t.nch; ++j)
+                    for (int kb = 0; kb < p.kb; ++kb, ++bit) {
+                        if (j == 0) {
+                            mbar_wait(afull_bar(kb), ut & 1);
+                            mbar_arrive_remote(map_to_cta(peer_afull_bar(kb), 0));
+                        }
+                        const int s = bit % G::STAGES;
+                        mbar_wait(bfull_bar(s), (bit / G::STAGES) & 1);
+                        mbar_arrive_remote(map_to_cta(peer_bfull_bar(s), 0));
+                    }
+                ++ut;
+            }
+        }
+    } else {
+        // =========================== epilogue (warps 0-3): this CTA's 128 TMEM lanes = its in1' tile ===========================
+        const int q = warp;
+        float* S = reinterpret_cast<float*>(smem_raw + (slabs - smem_u32(smem_raw))) + warp * (32 * 34);
+        // NCHW: lane b writes column 2b+px of row 2a+py (4-byte stores 8 bytes apart: half-filled sectors).  Parity-planar: every
+        // class owns a dense [H2, W2] plane per channel, lane b writes column b: 128 contiguous bytes per warp store.
+        const int H2 = (p.H + 1) >> 1, W2 = (p.W + 1) >> 1;
+        const size_t plane = p.planar ? (size_t)4 * H2 * W2 : (size_t)p.H * p.W;
+        const uint32_t acce_remote0 = map_to_cta(acce_bar(0), 0);
+        int acc_it = 0;
+        for (int unit = first_unit; unit < p.num_units; unit += unit_step) {
+            const CorrPairUnit t = corr_pair_unit(p, unit, rank);
+            const int a = t.a0 + q;
+            const int y = 2 * a + t.py, x = 2 * lane + t.px;
+            const bool valid = y < p.H && x < p.W && !(p.dbg_skip & 8);
+            float* o = p.out + (size_t)t.n * (CDS * CDS) * plane + (p.planar ? ((size_t)t.cls * H2 + a) * W2 + lane : (size_t)y * p.W + x);
+            if (t.part == 0) {
+                for (int tj = -CD; tj <= CD; ++tj) {              // displacement rows outside the image: zeros
+                    const int row = a + tj;
+                    if (row >= 0 && row < t.H2c) continue;
+                    if (valid) {
+#pragma unroll
+                        for (int ti = 0; ti < CDS; ++ti) o[(size_t)((tj + CD) * CDS + ti) * plane] = 0.f;
+                    }
+                }
+            }
+            for (int j = 0; j < t.nch; ++j, ++acc_it) {
+                const int as = acc_it % CORR_ACC_STAGES;
+                const int r0 = t.r_lo + (t.c_lo + j) * CORR_ROWS;
+                mbar_wait_cluster(accf_bar(as), (acc_it / CORR_ACC_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * CORR_BN);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v0[32], v1[32];
+                    const int row0 = r0 + 2 * h, row1 = row0 + 1;
+                    const int tj0 = row0 - a, tj1 = row1 - a;
+                    const bool use0 = tj0 >= -CD && tj0 <= CD && row0 < t.H2c && !(p.dbg_skip & 16);     // warp-uniform
+                    const bool use1 = tj1 >= -CD && tj1 <= CD && row1 < t.H2c && !(p.dbg_skip & 16);
+                    if (use0) TMEM_LD_32(t_row + (2 * h) * 32, v0);
+                    if (use1) TMEM_LD_32(t_row + (2 * h + 1) * 32, v1);
+                    if (use0 || use1) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (h == 1) {
+                        tc_fence_before();
+                        mbar_arrive_remote(acce_remote0 + 8u * as);      // the leader's barrier counts both CTAs' epilogue threads
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const bool use = rr ? use1 : use0;
+                        if (!use) continue;
+                        const int tj = rr ? tj1 : tj0;
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) S[c * 34 + lane] = __uint_as_float(rr ? v1[c] : v0[c]);
+                        __syncwarp();
+                        if (valid) {
+                            float* oc = o + (size_t)((tj + CD) * CDS) * plane;
+#pragma unroll
+                            for (int ti = 0; ti < CDS; ++ti) {
+                                const int b2 = lane + ti - CD;
+                                float val = (b2 >= 0 && b2 < 32) ? S[b2 * 34 + lane] : 0.f;
+                                val *= p.inv;
+                                if (p.leaky) val = val > 0.f ? val : 0.1f * val;
+                                oc[(size_t)ti * plane] = val;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // neither CTA may leave (or free TMEM) while its peer can still touch its smem / barriers
+    if (warp == CORR_EPI_WARPS) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+template <bool SPLIT>
+static int launch_corr_pair(const CorrK& k0, cudaStream_t s) {
+    using G = CorrPairGeo<SPLIT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(corr_pair_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e != cudaSuccess) {
+            set_error("corr_pair_kernel<%d>: cannot opt in to %d B of shared memory: %s", (int)SPLIT, G::SMEM, cudaGetErrorString(e));
+            return 1;
+        }
+        attr_set = true;
+    }
+    CorrK k = k0;
+    k.num_units = k.B * 4 * ((k.a_tiles + 1) / 2) * k.parts;
+    const int clusters = k.num_units < 74 ? k.num_units : 74;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(CORR_THREADS), cfg.dynamicSmemBytes = G::SMEM, cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, corr_pair_kernel<SPLIT>, k);
+    if (e != cudaSuccess) {
+        set_error("corr_pair_kernel<%d>: cluster launch failed: %s", (int)SPLIT, cudaGetErrorString(e));
+        return 1;
+    }
+    return check_launch("corr_pair_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
 // Variant 3: the A operand lives in TENSOR MEMORY.  A unit's in1' tile (C/64 k-blocks x hi/lo) is staged through the same
 // shared-memory ring as the in2' chunks and copied into TMEM columns [256, 512) by tcgen05.cp (issued by the MMA thread;
 // tcgen05.cp and tcgen05.mma execute in issue order, so no barrier is needed between the copy and the MMAs that read it,
@@ -601,6 +910,42 @@ static int launch_corr3(const CorrK& k, cudaStream_t s) {
     return check_launch("corr_tc3_kernel");
 }
 
+// Parity-planar cost volume [B,441,4,H2,W2] fp32 -> channels [0,441) of a split-fp16 NHWC view (FlowNetC's 473-channel merge
+// buffer); channels [441, dst.c) are zero-filled.  One thread per (pixel, 8-channel group): 128-byte coalesced reads along x
+// within a parity plane, 16-byte stores.
+__global__ void __launch_bounds__(256) corr_planar_pack_kernel(const float* __restrict__ src, ft_act d, int H2, int W2) {
+    const int groups = d.c / 8;
+    const size_t npix = (size_t)d.n * d.h * d.w;
+    const size_t cplane = (size_t)4 * H2 * W2;
+    __half* dh = reinterpret_cast<__half*>(d.hi);
+    __half* dl = reinterpret_cast<__half*>(d.lo);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix * groups; i += (size_t)gridDim.x * blockDim.x) {
+        // consecutive threads walk the columns of ONE parity class first, so the planar reads coalesce
+        const size_t spix = i % npix;
+        const int g = (int)(i / npix);
+        const int per_img = d.h * d.w;
+        const int n = (int)(spix / per_img), r = (int)(spix % per_img);
+        const int cls = r / (H2 * W2), rr = r % (H2 * W2);
+        const int a = rr / W2, bcol = rr % W2;
+        const int y = 2 * a + (cls >> 1), x = 2 * bcol + (cls & 1);
+        if (y >= d.h || x >= d.w) continue;
+        const float* s = src + (size_t)n * (CDS * CDS) * cplane + ((size_t)cls * H2 + a) * W2 + bcol;
+        Half8 h8, l8;
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+            const int c0 = g * 8 + 2 * k2;
+            const float v0 = c0 < CDS * CDS ? __ldg(s + (size_t)c0 * cplane) : 0.f, v1 = c0 + 1 < CDS * CDS ? __ldg(s + (size_t)(c0 + 1) * cplane) : 0.f;
+            __half h0, l0, h1, l1;
+            split_f32(v0, h0, l0);
+            split_f32(v1, h1, l1);
+            h8.v[k2] = __halves2half2(h0, h1), l8.v[k2] = __halves2half2(l0, l1);
+        }
+        const size_t off = (((size_t)n * d.h + y) * d.w + x) * d.ld + d.coff + g * 8;
+        *reinterpret_cast<Half8*>(dh + off) = h8;
+        if (dl) *reinterpret_cast<Half8*>(dl + off) = l8;
+    }
+}
+
 template <bool SPLIT>
 static int launch_corr(const CorrK& k, cudaStream_t s) {
     using G = CorrGeo<SPLIT>;
@@ -634,7 +979,17 @@ extern "C" int ft_correlation_tc_supported(int C, int H, int W, int pad, int ksi
            (W + 1) / 2 <= CORR_COLS;
 }
 
+static int correlation_act_impl(const ft_act* in1, const ft_act* in2, float* out, int fuse_leaky, int precision, int planar, void* stream);
+
 extern "C" int ft_correlation_act(const ft_act* in1, const ft_act* in2, float* out, int fuse_leaky, int precision, void* stream) {
+    return correlation_act_impl(in1, in2, out, fuse_leaky, precision, 0, stream);
+}
+
+extern "C" int ft_correlation_act_planar(const ft_act* in1, const ft_act* in2, float* out, int fuse_leaky, int precision, void* stream) {
+    return correlation_act_impl(in1, in2, out, fuse_leaky, precision, 1, stream);
+}
+
+static int correlation_act_impl(const ft_act* in1, const ft_act* in2, float* out, int fuse_leaky, int precision, int planar, void* stream) {
     FT_REQUIRE(in1 && in2 && out, "correlation_act: null argument");
     FT_REQUIRE(precision == FT_PREC_SPLIT || precision == FT_PREC_FAST, "correlation_act: bad precision %d", precision);
     const bool split = precision == FT_PREC_SPLIT;
@@ -645,7 +1000,7 @@ extern "C" int ft_correlation_act(const ft_act* in1, const ft_act* in2, float* o
                "correlation_act: the tensor-core path needs C in {64,128,192,256} and W <= 64 (got C=%d H=%d W=%d)", in1->c, in1->h, in1->w);
     CorrK k = {};
     k.out = out, k.B = in1->n, k.H = in1->h, k.W = in1->w, k.C = in1->c, k.kb = in1->c / CORR_BK;
-    k.inv = 1.f / (float)k.C, k.leaky = fuse_leaky != 0;
+    k.inv = 1.f / (float)k.C, k.leaky = fuse_leaky != 0, k.planar = planar;
     if (const char* e = getenv("FT_DEV_SKIP")) k.dbg_skip = atoi(e);
     const int H2 = (k.H + 1) / 2;
     k.a_tiles = ceil_div(H2, CORR_ROWS);
@@ -661,7 +1016,7 @@ extern "C" int ft_correlation_act(const ft_act* in1, const ft_act* in2, float* o
     for (int cls = 0; cls < 4; ++cls) {
         const int py = cls >> 1, px = cls & 1;
         if (py >= k.H || px >= k.W) {      // degenerate 1-pixel-wide/high image: the class is empty; map it onto class 0 (nothing valid is stored)
-            for (int pl = 0; pl < 2; ++pl) k.a_map[cls][pl] = k.a_map[0][pl], k.b_map[cls][pl] = k.b_map[0][pl];
+            for (int pl = 0; pl < 2; ++pl) k.a_map[cls][pl] = k.a_map[0][pl], k.b_map[cls][pl] = k.b_map[0][pl], k.b2_map[cls][pl] = k.b2_map[0][pl];
             continue;
         }
         for (int op = 0; op < 2; ++op) {
@@ -673,10 +1028,18 @@ extern "C" int ft_correlation_act(const ft_act* in1, const ft_act* in2, float* o
             if (int e = make_map(&m[0], (const __half*)a.hi + off, dim, str, box, 128, op ? "corr.in2.hi" : "corr.in1.hi")) return e;
             if (split)
                 if (int e = make_map(&m[1], (const __half*)a.lo + off, dim, str, box, 128, op ? "corr.in2.lo" : "corr.in1.lo")) return e;
+            if (op) {
+                const int box2[4] = {CORR_BK, CORR_COLS, CORR_ROWS / 2, 1};
+                if (int e = make_map(&k.b2_map[cls][0], (const __half*)a.hi + off, dim, str, box2, 128, "corr.in2.hi(half)")) return e;
+                if (split)
+                    if (int e = make_map(&k.b2_map[cls][1], (const __half*)a.lo + off, dim, str, box2, 128, "corr.in2.lo(half)")) return e;
+            }
         }
     }
-    int variant = 2;
+    int variant = 4;     // 4 = CTA pairs (default), 2 = single CTA with resident A, 3 = A operand in TMEM (experimental)
     if (const char* e = getenv("FT_DEV_CORR_VARIANT")) variant = atoi(e);
+    if (k.planar) variant = 4;
+    if (variant == 4) return split ? launch_corr_pair<true>(k, (cudaStream_t)stream) : launch_corr_pair<false>(k, (cudaStream_t)stream);
     if (variant == 3) return split ? launch_corr3<true>(k, (cudaStream_t)stream) : launch_corr3<false>(k, (cudaStream_t)stream);
     return split ? launch_corr<true>(k, (cudaStream_t)stream) : launch_corr<false>(k, (cudaStream_t)stream);
 }
@@ -709,4 +1072,18 @@ extern "C" int ft_correlation_forward_ws(const float* in1, const float* in2, flo
 // dev tool: copy the per-CTA wait-cycle counters of the last instrumented corr_tc3_kernel launch (FT_DEV_SKIP bit 64) to the host
 extern "C" int ft_dev_corr_profile(long long* host_out /* [148][16] */) {
     return cudaMemcpyFromSymbol(host_out, g_corr_prof, sizeof(long long) * 148 * 16) == cudaSuccess ? 0 : 1;
+}
+
+extern "C" int ft_pack_corr_planar(const float* planar, const ft_act* dst, void* stream) {
+    FT_REQUIRE(planar && dst && dst->hi, "pack_corr_planar: null pointer");
+    FT_REQUIRE(dst->c % 8 == 0 && dst->c >= CDS * CDS && dst->ld % 8 == 0 && dst->coff % 8 == 0 && dst->coff + dst->c <= dst->ld,
+               "pack_corr_planar: the destination view needs >= 441 channels in multiples of 8 (c=%d ld=%d coff=%d)", dst->c, dst->ld, dst->coff);
+    const int H2 = (dst->h + 1) / 2, W2 = (dst->w + 1) / 2;
+    // the index space is [n][4 classes][H2][W2] x groups; for odd H or W the absent pixels of a class are skipped
+    ft_act d = *dst;
+    const size_t total = (size_t)d.n * 4 * H2 * W2 * (d.c / 8);
+    FT_REQUIRE((size_t)4 * H2 * W2 == (size_t)d.h * d.w, "pack_corr_planar: H and W must be even (got %d x %d)", d.h, d.w);
+    const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    corr_planar_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(planar, d, H2, W2);
+    return check_launch("corr_planar_pack_kernel");
 }

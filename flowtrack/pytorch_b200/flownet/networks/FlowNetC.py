@@ -35,19 +35,22 @@ def build(p, L, frames, B, tag=""):
     c2b = p.conv(L["conv2"], t1.view(0, 64, B, B), p.act(B, H // 4, W // 4, 128))
     h8, w8 = H // 8, W // 8
     merged = p.act(B, h8, w8, 32 + 441, zero=True)                                  # [conv_redir(32) | corr(441 -> 448)]
-    corr = p.f32(B, 441, h8, w8)
-    if lib.ft_correlation_tc_supported(256, h8, w8, 20, 1, 20, 1, 2):
-        # tcgen05 banded GEMM straight on the split-fp16 activations of the two conv3 streams (ft_corr.cu), LeakyReLU fused
+    if lib.ft_correlation_tc_supported(256, h8, w8, 20, 1, 20, 1, 2) and h8 % 2 == 0 and w8 % 2 == 0:
+        # tcgen05 banded GEMM straight on the split-fp16 activations of the two conv3 streams (ft_corr.cu), LeakyReLU fused;
+        # parity-planar fp32 in between (dense 128-byte warp stores), re-laid out into the merge buffer by ft_pack_corr_planar
         c3a = p.conv(L["conv3"], c2a, p.act(B, h8, w8, 256))
         c3b = p.conv(L["conv3"], c2b, p.act(B, h8, w8, 256))
-        p.call("correlation", lib.ft_correlation_act, c3a.struct(), c3b.struct(), corr.data_ptr(), 1, p.precision)
+        corr = p.f32(B, 441, 4, h8 // 2, w8 // 2)
+        p.call("correlation", lib.ft_correlation_act_planar, c3a.struct(), c3b.struct(), corr.data_ptr(), 1, p.precision)
+        p.call("pack_corr", lib.ft_pack_corr_planar, corr.data_ptr(), merged.view(32, 441).struct())
     else:                                                                          # frames wider than 512 px: CUDA-core kernel on fp32 copies
+        corr = p.f32(B, 441, h8, w8)
         a3f, b3f = p.f32(B, 256, h8, w8), p.f32(B, 256, h8, w8)
         c3a = p.conv(L["conv3"], c2a, p.act(B, h8, w8, 256), out_f32=a3f)
         p.conv(L["conv3"], c2b, None, out_f32=b3f)
         p.call("correlation", lib.ft_correlation_forward, a3f.data_ptr(), b3f.data_ptr(), corr.data_ptr(), B, 256, h8, w8, 20, 1, 20, 1, 2, 1)
-    st = corr.stride()
-    p.call("pack_image", lib.ft_pack_image, corr.data_ptr(), st[0], st[1], st[2], st[3], 441, 1.0, merged.view(32, 441).struct(), 0, 0)
+        st = corr.stride()
+        p.call("pack_image", lib.ft_pack_image, corr.data_ptr(), st[0], st[1], st[2], st[3], 441, 1.0, merged.view(32, 441).struct(), 0, 0)
     p.conv(L["conv_redir"], c3a, merged.view(0, 32))
     p.taps[tag + "corr"] = corr
     c3 = p.conv(L["conv3_1"], merged, cat[3].view(0, 256))

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 8
+#define FT_ABI_VERSION 9
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -144,6 +144,12 @@ int ft_correlation_forward(const float* in1, const float* in2, float* out, int B
  *                             workspace: 256-byte aligned, >= ft_correlation_workspace_bytes(B,C,H,W).          */
 int    ft_correlation_tc_supported(int C, int H, int W, int pad, int ksize, int max_disp, int stride1, int stride2);
 int    ft_correlation_act(const ft_act* in1, const ft_act* in2, float* out, int fuse_leaky, int precision, void* stream);
+/* Same kernel, pipeline-internal output layout: parity-planar fp32 [B,441,4,H/2,W/2] -- class py*2+px holds the pixels
+ * (2a+py, 2b+px) as a dense [H/2,W/2] plane, so a warp store is 128 contiguous bytes (in NCHW the stride-2 stores fill
+ * half of every 32-byte sector).  ft_pack_corr_planar converts it into channels [0,441) of a split-fp16 NHWC view
+ * (FlowNetC's 473-channel merge buffer, FlowNetC.py:101); H and W must be even.                                      */
+int    ft_correlation_act_planar(const ft_act* in1, const ft_act* in2, float* out, int fuse_leaky, int precision, void* stream);
+int    ft_pack_corr_planar(const float* planar, const ft_act* dst, void* stream);
 size_t ft_correlation_workspace_bytes(int B, int C, int H, int W);
 int    ft_correlation_forward_ws(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
                                  int pad, int ksize, int max_disp, int stride1, int stride2, int fuse_leaky,

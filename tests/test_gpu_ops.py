@@ -61,7 +61,9 @@ def _corr_ws(a, b, leaky=0, precision=_lib.PREC_SPLIT):
                                    (1, 64, 13, 31),       # odd H and W: the parity classes differ in size
                                    (2, 128, 50, 64),      # H/2 not a multiple of the 4-row tile
                                    (1, 192, 2, 2)])       # one pixel per parity class
-def test_correlation_tensor_core_vs_oracle(shape):
+@pytest.mark.parametrize("variant", ["4", "2", "3"], ids=["cta_pair", "single_cta", "a_in_tmem"])
+def test_correlation_tensor_core_vs_oracle(shape, variant, monkeypatch):
+    monkeypatch.setenv("FT_DEV_CORR_VARIANT", variant)       # read by the library at every call
     assert L().ft_correlation_tc_supported(shape[1], shape[2], shape[3], 20, 1, 20, 1, 2) == 1
     g = torch.Generator().manual_seed(7 + sum(shape))
     a, b = torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)
@@ -95,6 +97,32 @@ def test_correlation_tensor_core_full_size_properties():
     o2 = _corr_ws(b, a)
     assert (o2[:, 220] - o[:, 220]).abs().max() < 1e-5
     assert (o2[:, (10 - 2) * 21 + 10, 4:, :] - o[:, (10 + 2) * 21 + 10, :44, :]).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 48, 64), (3, 128, 16, 24), (1, 64, 6, 2)])
+def test_correlation_planar_layout_and_pack(shape):
+    """ft_correlation_act_planar (parity-planar fp32 [B,441,4,H/2,W/2]) == the NCHW result re-indexed, and
+    ft_pack_corr_planar lands it in channels [32, 473) of a 480-channel NHWC merge buffer like ft_pack_image does."""
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(3 + sum(shape))
+    a, b = torch.randn(*shape, generator=g).cuda(), torch.randn(*shape, generator=g).cuda()
+    aa, ba = gpu_util.pack_nchw(a), gpu_util.pack_nchw(b)
+    nchw = torch.full((B, 441, H, W), float("nan"), device="cuda")
+    planar = torch.full((B, 441, 4, H // 2, W // 2), float("nan"), device="cuda")
+    _lib.check(L().ft_correlation_act(aa.struct(), ba.struct(), nchw.data_ptr(), 1, _lib.PREC_SPLIT, gpu_util.sp()), "corr_act")
+    _lib.check(L().ft_correlation_act_planar(aa.struct(), ba.struct(), planar.data_ptr(), 1, _lib.PREC_SPLIT, gpu_util.sp()), "corr_planar")
+    torch.cuda.synchronize()
+    want = torch.stack([nchw[:, :, py::2, px::2] for py in (0, 1) for px in (0, 1)], dim=2)
+    assert torch.equal(planar, want)
+    ref = ops_oracle.correlation_torch(a.cpu(), b.cpu(), 20, 1, 20, 1, 2)
+    ref = torch.where(ref > 0, ref, 0.1 * ref)
+    assert (nchw.cpu() - ref).abs().max() < 1e-5 * max(1.0, ref.abs().max().item())
+    m1, m2 = engine.Act(B, H, W, 32 + 441, "cuda", zero=True), engine.Act(B, H, W, 32 + 441, "cuda", zero=True)
+    st = nchw.stride()
+    _lib.check(L().ft_pack_image(nchw.data_ptr(), st[0], st[1], st[2], st[3], 441, 1.0, m1.view(32, 441).struct(), 0, 0, gpu_util.sp()), "pack_image")
+    _lib.check(L().ft_pack_corr_planar(planar.data_ptr(), m2.view(32, 441).struct(), gpu_util.sp()), "pack_corr_planar")
+    torch.cuda.synchronize()
+    assert torch.equal(m1.hi, m2.hi) and torch.equal(m1.lo, m2.lo)
 
 
 def test_correlation_leaky_and_linearity():
