@@ -152,6 +152,85 @@ __global__ void __launch_bounds__(1024) nms_kernel(const float* __restrict__ det
     }
 }
 
+// OKS-NMS over poses (nms_oks / compute_oks(ground_truth=False), lib/pose/utils/evaluation.py:60-101): same one-CTA-per-frame
+// scheme as the box NMS; pose i suppresses a lower-scored pose j when
+//   mean_{k: score_i[k] >= t and score_j[k] >= t} exp(-|p_i[k]-p_j[k]|^2 / (2 delta[k]^2 ((area_i+area_j)/2 + eps))) > oks_thresh
+// (no counted joint: OKS = 0).  Arithmetic in double like the numpy reference.
+__global__ void __launch_bounds__(1024) nms_oks_kernel(const float* __restrict__ joints, const float* __restrict__ scores, const float* __restrict__ areas,
+                                                       const float* __restrict__ delta, const int32_t* __restrict__ counts, int N, int K, float oks_thresh,
+                                                       float kpt_thresh, int32_t* __restrict__ keep, int32_t* __restrict__ num_keep) {
+    extern __shared__ uint32_t nms_smem[];
+    float* key = reinterpret_cast<float*>(nms_smem);
+    int* idx = reinterpret_cast<int*>(nms_smem + NMS_MAX);
+    uint32_t* mask = nms_smem + 2 * NMS_MAX;
+    const int f = blockIdx.x, t = threadIdx.x;
+    const int n = counts ? min(max(counts[f], 0), N) : N;
+    const float* J = joints + (size_t)f * N * K * 3;
+    const float* A = areas + (size_t)f * N;
+    int32_t* kp = keep + (size_t)f * N;
+    int np2 = 32;
+    while (np2 < n) np2 <<= 1;
+    key[t] = t < n ? scores[(size_t)f * N + t] : -INFINITY;
+    idx[t] = t < n ? t : 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int p = t ^ j;
+            if (t < np2 && p > t) {
+                const bool desc = (t & k) == 0;
+                const float a = key[t], b = key[p];
+                const int ia = idx[t], ib = idx[p];
+                const bool a_first = a > b || (a == b && ia < ib);
+                if (desc ? !a_first : a_first) key[t] = b, key[p] = a, idx[t] = ib, idx[p] = ia;
+            }
+            __syncthreads();
+        }
+    const int words = (n + 31) >> 5;
+    if (t < n) {
+        const float* ji = J + (size_t)idx[t] * K * 3;
+        const double ai = A[idx[t]];
+        for (int w = 0; w < words; ++w) {
+            uint32_t bits = 0;
+            if (w >= (t >> 5)) {
+                for (int b = 0; b < 32; ++b) {
+                    const int j = w * 32 + b;
+                    if (j <= t || j >= n) continue;
+                    const float* jj = J + (size_t)idx[j] * K * 3;
+                    const double scale = (ai + (double)A[idx[j]]) / 2 + 2.220446049250313e-16;
+                    double sum = 0;
+                    int cnt = 0;
+                    for (int k = 0; k < K; ++k) {
+                        if (ji[3 * k + 2] >= kpt_thresh && jj[3 * k + 2] >= kpt_thresh) {
+                            const double dx = (double)ji[3 * k] - (double)jj[3 * k], dy = (double)ji[3 * k + 1] - (double)jj[3 * k + 1];
+                            const double d2 = (double)delta[k] * (double)delta[k];
+                            sum += exp(-(dx * dx + dy * dy) / 2 / d2 / scale);
+                            ++cnt;
+                        }
+                    }
+                    const double oks = cnt ? sum / cnt : 0.0;
+                    if (oks > (double)oks_thresh) bits |= 1u << b;
+                }
+            }
+            mask[t * words + w] = bits;
+        }
+    }
+    __syncthreads();
+    if (t < 32) {
+        uint32_t removed = 0;
+        int kept = 0;
+        for (int i = 0; i < n; ++i) {
+            const uint32_t wv = __shfl_sync(0xffffffffu, removed, i >> 5);
+            if (!((wv >> (i & 31)) & 1u)) {
+                if (t == 0) kp[kept] = idx[i];
+                ++kept;
+                if (t < words) removed |= mask[i * words + t];
+            }
+        }
+        if (t == 0) num_keep[f] = kept;
+        for (int i = kept + t; i < N; i += 32) kp[i] = -1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Flip test (tools/pose/main.py:289-299; swaplr_image / swap, lib/pose/utils/transforms.py:140-170).
 // ------------------------------------------------------------------------------------------------
@@ -233,4 +312,23 @@ extern "C" int ft_flip_merge(const float* hm, const float* hm_flipped, const int
     const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     flip_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(hm, hm_flipped, perm, N, C, H, W, out);
     return check_launch("flip_merge_kernel");
+}
+
+extern "C" int ft_nms_oks(const float* joints, const float* scores, const float* areas, const float* delta, const int32_t* counts, int frames, int N, int K,
+                          float oks_thresh, float kpt_thresh, int32_t* keep, int32_t* num_keep, void* stream) {
+    FT_REQUIRE(joints && scores && areas && delta && keep && num_keep && frames > 0 && K > 0, "nms_oks: null pointer / bad shape");
+    FT_REQUIRE(N >= 0 && N <= NMS_MAX, "nms_oks: at most %d poses per frame (got %d)", NMS_MAX, N);
+    const int words = (N + 31) / 32;
+    const int smem = (2 * NMS_MAX + (N > 0 ? N * words : 1)) * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(nms_oks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * NMS_MAX + NMS_MAX * NMS_WORDS) * 4);
+        if (e != cudaSuccess) {
+            set_error("nms_oks_kernel: cannot opt in to shared memory: %s", cudaGetErrorString(e));
+            return 1;
+        }
+        attr_set = true;
+    }
+    nms_oks_kernel<<<frames, 1024, smem, (cudaStream_t)stream>>>(joints, scores, areas, delta, counts, N, K, oks_thresh, kpt_thresh, keep, num_keep);
+    return check_launch("nms_oks_kernel");
 }

@@ -56,3 +56,23 @@ def flip_test_forward(model, inputs, dataset="coco"):
     out = torch.empty(B, K, h, w, device=x.device, dtype=torch.float32)
     _lib.check(L.ft_flip_merge(hm[:B].data_ptr(), hm[B:].data_ptr(), perm.data_ptr(), B, K, h, w, out.data_ptr(), engine.stream_ptr()), "flip_merge")
     return out
+
+
+def nms_oks(pred, oks_thresh, delta, kpt_thresh=0):
+    """evaluation.py:83-101 signature: pred = list of {'score', 'joints' [K,3], 'area'} -> list of kept indices, highest
+    score first.  Runs ft_nms_oks on the GPU (one launch; the reference loops in numpy)."""
+    from ... import _lib, engine
+    n = len(pred)
+    if n == 0:
+        return []
+    dev = torch.device("cuda")
+    joints = torch.as_tensor(np.array([p["joints"] for p in pred], dtype=np.float32)).to(dev).contiguous().unsqueeze(0)
+    scores = torch.as_tensor(np.array([p["score"] for p in pred], dtype=np.float32)).to(dev).unsqueeze(0)
+    areas = torch.as_tensor(np.array([p["area"] for p in pred], dtype=np.float32)).to(dev).unsqueeze(0)
+    dl = torch.as_tensor(np.asarray(delta, dtype=np.float32)).to(dev)
+    K = joints.shape[2]
+    keep = torch.empty(1, n, dtype=torch.int32, device=dev)
+    num = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().ft_nms_oks(joints.data_ptr(), scores.data_ptr(), areas.data_ptr(), dl.data_ptr(), None, 1, n, K, float(oks_thresh),
+                                     float(kpt_thresh), keep.data_ptr(), num.data_ptr(), engine.stream_ptr()), "nms_oks")
+    return keep[0, :int(num[0].item())].cpu().tolist()

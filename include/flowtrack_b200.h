@@ -30,6 +30,7 @@
  *   ft_box_propagation       box_propagation                                       lib/tracking/flow_utils.py:7-35
  *   ft_crop_affine           transform_image (cv2.warpAffine) per person box         lib/tracking/net_utils.py:48-57, lib/pose/utils/transforms.py:231-240
  *   ft_flip_w / ft_flip_merge  flip test: np.flip + swaplr_image + average                  tools/pose/main.py:289-299, lib/pose/utils/transforms.py:140-170
+ *   ft_nms_oks               nms_oks + compute_oks                                   lib/pose/utils/evaluation.py:60-101
  *   ft_nms                   pth_nms / cpu_nms / nms_kernel                          lib/detection/nms/pth_nms.py:5-46, src/nms.c:36-62, src/cuda/nms_kernel.cu:13-70
  */
 #ifndef FLOWTRACK_B200_H_
@@ -42,7 +43,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 9
+#define FT_ABI_VERSION 10
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -232,6 +233,14 @@ int ft_flip_merge(const float* hm, const float* hm_flipped, const int32_t* perm,
  * (-1 beyond num_keep[frame]).                                                                        */
 int ft_nms(const float* dets, const int32_t* counts, int frames, int N, float thresh, int inclusive,
            int32_t* keep, int32_t* num_keep, void* stream);
+
+/* OKS-NMS over poses (nms_oks + compute_oks(ground_truth=False), lib/pose/utils/evaluation.py:60-101).  joints
+ * [frames,N,K,3] = (x, y, score), scores [frames,N] (pose score), areas [frames,N], delta [K] (per-joint falloff),
+ * counts [frames] or NULL, N <= 1024.  A pose suppresses a lower-scored one when their OKS (mean over the joints both
+ * score >= kpt_thresh, scale = mean of the two areas) exceeds oks_thresh.  keep / num_keep as in ft_nms.            */
+int ft_nms_oks(const float* joints, const float* scores, const float* areas, const float* delta, const int32_t* counts,
+               int frames, int N, int K, float oks_thresh, float kpt_thresh, int32_t* keep, int32_t* num_keep,
+               void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,8 @@ CPU legs may import this.
   get_pairs / swaplr_image / flip_test_merge
                                lib/pose/utils/transforms.py:60-96,140-170 and tools/pose/main.py:289-299 (flip test); pinned
                                against the reference's own swaplr_image (reference_track.npz, keys swap_*).
+  compute_oks / nms_oks        lib/pose/utils/evaluation.py:60-101, restated line by line (pinned against the reference functions
+                               themselves: reference_track.npz keys oks_*)
   nms_cpu                      lib/detection/nms/src/nms.c:36-62 (cpu_nms: suppress at IoU >= thresh) with the ordering
                                of pth_nms.py:13-22; inclusive=False gives the GPU variant (nms_kernel.cu:62, IoU > thresh).
                                The reference extension needs TH/cffi (gone): parity of this restatement is pinned by
@@ -144,3 +146,41 @@ def swaplr_image(img, dataset="coco"):
 def flip_test_merge(output, output_flipped, dataset="coco"):
     """tools/pose/main.py:296-299: (output + swaplr_image(output_flipped)) * 0.5"""
     return (np.asarray(output) + swaplr_image(output_flipped, dataset)) * np.float32(0.5)
+
+
+def compute_oks(pred, anno, ref_scale, delta, ground_truth=True, threshold=0):
+    """evaluation.py:60-81."""
+    pred, anno = np.asarray(pred), np.asarray(anno)
+    batch_size = pred.shape[0]
+    if anno.ndim < 3:
+        anno = np.tile(anno[np.newaxis, :, :], (batch_size, 1, 1))
+    oks = np.zeros((batch_size))
+    for i in range(batch_size):
+        pj, aj, scale = pred[i], anno[i], ref_scale[i]
+        if ground_truth:
+            is_count = aj[:, 2] > 0
+        else:
+            is_count = np.logical_and(aj[:, 2] >= threshold, pj[:, 2] >= threshold)
+        if is_count.sum() != 0:
+            dist = pow((aj[is_count, :2] - pj[is_count, :2]), 2).sum(1)
+            d = pow(delta[is_count], 2)
+            oks[i] = np.exp(-dist / 2 / d / (scale + np.spacing(1))).mean()
+    return oks
+
+
+def nms_oks(pred, oks_thresh, delta, kpt_thresh=0):
+    """evaluation.py:83-101."""
+    num_preds = len(pred)
+    scores = np.array([pred[i]["score"] for i in range(num_preds)])
+    joints = np.array([pred[i]["joints"] for i in range(num_preds)])
+    areas = np.array([pred[i]["area"] for i in range(num_preds)])
+    order = scores.argsort()[::-1]
+    keep = []
+    while order.size > 0:
+        i = order[0]
+        keep.append(int(i))
+        ref_scale = (areas[i] + areas[order[1:]]) / 2
+        oks = compute_oks(joints[order[1:]], joints[i], ref_scale, delta, ground_truth=False, threshold=kpt_thresh)
+        ind = np.where(oks <= oks_thresh)[0]
+        order = order[ind + 1]
+    return keep

@@ -135,7 +135,7 @@ def make_decode(ref_eval, ref_tf, out):
     print("decode ok", coords.shape, scores.shape)
 
 
-def make_track(ref_tf):
+def make_track(ref_tf, ref_eval=None):
     """Person crops through the reference's own transform_image (transforms.py:231-240) with pose_est's centre/scale
     rule (net_utils.py:49-50); stored in a separate small file (reference_track.npz)."""
     img = recipes.track_frame()
@@ -147,9 +147,16 @@ def make_track(ref_tf):
     crops_f = np.stack([ref_tf.transform_image(img.astype(np.float32), centers[i], scales[i], res).numpy() for i in range(len(boxes))])
     hm = recipes.flip_heatmaps()
     swapped = {ds: ref_tf.swaplr_image(hm[:, :k].copy(), ds) for ds, k in (("coco", 17), ("mpii", 16), ("aic", 14))}
+    extra = {}
+    if ref_eval is not None:      # OKS-NMS through the reference's own nms_oks / compute_oks (evaluation.py:60-101)
+        preds = recipes.oks_poses()
+        for th, kt in ((0.9, 0.0), (0.5, 0.2), (0.3, 0.5)):
+            extra["oks_keep_%g_%g" % (th, kt)] = np.array(ref_eval.nms_oks(preds, th, recipes.COCO_DELTA, kt), np.int64)
+        j = np.array([p["joints"] for p in preds])
+        extra["oks_pairwise0"] = ref_eval.compute_oks(j[1:], j[0], np.full(len(preds) - 1, 5000.0), recipes.COCO_DELTA, ground_truth=False, threshold=0.2)
     path = os.path.join(HERE, "reference_track.npz")
     np.savez_compressed(path, crops_u8=crops, crops_f32=crops_f, centers=centers, scales=scales,
-                        **{"swap_" + ds: v for ds, v in swapped.items()})
+                        **{"swap_" + ds: v for ds, v in swapped.items()}, **extra)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB", crops.shape, crops.dtype)
 
 
@@ -157,9 +164,9 @@ def main():
     out = {}
     ref_pose, ref_eval, ref_tf = import_reference_pose()
     if "--track-only" in sys.argv:
-        make_track(ref_tf)
+        make_track(ref_tf, ref_eval)
         return
-    make_track(ref_tf)
+    make_track(ref_tf, ref_eval)
     make_pose(ref_pose, out)
     make_decode(ref_eval, ref_tf, out)
     ref_flow = import_reference_flow()

@@ -52,3 +52,21 @@ def track_frame():
 
 def flip_heatmaps():
     return np.random.default_rng(9).standard_normal((2, 17, 8, 6)).astype(np.float32)
+
+
+COCO_DELTA = 2 * np.array([.26, .25, .25, .35, .35, .79, .79, .72, .72, .62, .62, 1.07, 1.07, .87, .87, .89, .89]) / 10.0
+
+
+def oks_poses(n=40, seed=12):
+    """n synthetic 17-joint poses in clusters (near-duplicates around a few people) with distinct pose scores."""
+    rng = np.random.default_rng(seed)
+    centres = rng.uniform(50, 400, (6, 1, 2))
+    base = centres + rng.uniform(-40, 40, (6, 17, 2))
+    preds = []
+    for i in range(n):
+        c = i % 6
+        xy = base[c] + rng.normal(0, 1.5 + 3.0 * (i // 6), (17, 2))
+        sc = rng.uniform(0.05, 1.0, (17, 1))
+        preds.append({"score": float(1.0 - i * 0.011 + 0.003 * rng.random()), "joints": np.concatenate([xy, sc], 1).astype(np.float32),
+                      "area": float(rng.uniform(3000, 9000))})
+    return preds

@@ -184,3 +184,19 @@ def test_process_frame_entry_point(tmp_path):
     assert fdemo.main(["--input1", str(tmp_path / "a.png"), "--input2", str(tmp_path / "b.png"), "--resume", str(ck), "--save", str(tmp_path / "out")]) == 0
     flo = flow_utils.readFlow(str(tmp_path / "out" / "output.flo"))
     assert flo.shape == (128, 192, 2) and np.isfinite(flo).all()
+
+
+def test_nms_oks_matches_reference_outputs():
+    """ft_nms_oks == the reference's own nms_oks on the golden poses (tests/golden/reference_track.npz) and == the oracle on
+    random pose sets, incl. the reference-signature wrapper."""
+    from flowtrack.pytorch_b200.pose.utils import evaluation
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_track.npz"))
+    preds = recipes.oks_poses()
+    for th, kt in ((0.9, 0.0), (0.5, 0.2), (0.3, 0.5)):
+        assert evaluation.nms_oks(preds, th, recipes.COCO_DELTA, kt) == g["oks_keep_%g_%g" % (th, kt)].tolist()
+    for seed, n in ((1, 7), (2, 90), (3, 300)):
+        p2 = recipes.oks_poses(n, seed)
+        for i, p in enumerate(p2):                       # distinct scores for any n
+            p["score"] = float(1.0 - i / (2.0 * n))
+        assert evaluation.nms_oks(p2, 0.4, recipes.COCO_DELTA, 0.3) == track_oracle.nms_oks(p2, 0.4, recipes.COCO_DELTA, 0.3)
+    assert evaluation.nms_oks([], 0.5, recipes.COCO_DELTA) == []

@@ -170,3 +170,14 @@ def test_flip_oracle_matches_reference_swaplr_image():
     for ds, k in (("coco", 17), ("mpii", 16), ("aic", 14)):
         perm = transforms.swap_permutation(k, ds)
         np.testing.assert_array_equal(hm[:, :k][:, perm][:, :, :, ::-1], g["swap_" + ds])     # the permutation form the kernel uses
+
+
+def test_oks_oracle_matches_reference_nms_oks():
+    from oracle import track_oracle
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_track.npz"))
+    preds = recipes.oks_poses()
+    for th, kt in ((0.9, 0.0), (0.5, 0.2), (0.3, 0.5)):
+        assert track_oracle.nms_oks(preds, th, recipes.COCO_DELTA, kt) == g["oks_keep_%g_%g" % (th, kt)].tolist()
+    j = np.array([p["joints"] for p in preds])
+    oks = track_oracle.compute_oks(j[1:], j[0], np.full(len(preds) - 1, 5000.0), recipes.COCO_DELTA, ground_truth=False, threshold=0.2)
+    np.testing.assert_allclose(oks, g["oks_pairwise0"], rtol=1e-12, atol=0)

@@ -16,6 +16,12 @@ LAYERS = [
     ("l4 3x3 512->512 @8x6 B64", lambda: nn.Conv2d(512, 512, 3, 1, 1, bias=False), (64, 512, 8, 6)),
     ("flow conv3_1 256->256 @48x64 B16", lambda: nn.Conv2d(256, 256, 3, 1, 1), (16, 256, 48, 64)),
     ("l2 1x1 512->128 @32x24 B64", lambda: nn.Conv2d(512, 128, 1, bias=False), (64, 512, 32, 24)),
+    ("l3 1x1 256->1024 @16x12 B64", lambda: nn.Conv2d(256, 1024, 1, bias=False), (64, 256, 16, 12)),
+    ("l3 1x1 1024->256 @16x12 B64", lambda: nn.Conv2d(1024, 256, 1, bias=False), (64, 1024, 16, 12)),
+    ("l2 1x1 128->512 @32x24 B64", lambda: nn.Conv2d(128, 512, 1, bias=False), (64, 128, 32, 24)),
+    ("l1 1x1 64->256 @64x48 B64", lambda: nn.Conv2d(64, 256, 1, bias=False), (64, 64, 64, 48)),
+    ("l4 1x1 512->2048 @8x6 B64", lambda: nn.Conv2d(512, 2048, 1, bias=False), (64, 512, 8, 6)),
+    ("flow deconv2 392->64 @48x64 B16", lambda: nn.ConvTranspose2d(392, 64, 4, 2, 1), (16, 392, 48, 64)),
 ]
 ONLY = os.environ.get("CB_ONLY")            # e.g. "0:128:0,0:128:1" = layer index : block_n : pair
 only = set(tuple(int(v) for v in item.split(":")) for item in ONLY.split(",")) if ONLY else None
