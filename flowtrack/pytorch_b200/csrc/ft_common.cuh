@@ -35,6 +35,14 @@ __device__ __forceinline__ void split_f32(float v, __half& hi, __half& lo) {
     lo = __float2half_rn(c - __half2float(hi));
 }
 
+// Two values at once: one saturating packed conversion per plane (F2FP.SATFINITE) instead of clamp + two scalar conversions.
+// Identical to split_f32 for |v| <= 65504; beyond that hi saturates to +-65504 and lo carries what it can of the rest.
+__device__ __forceinline__ void split_f32x2(float v0, float v1, uint32_t& hi2, uint32_t& lo2) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(v1), "f"(v0));
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(v1 - f.y), "f"(v0 - f.x));
+}
+
 __device__ __forceinline__ float join_f16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
 
 struct alignas(16) Half8 {

@@ -65,11 +65,12 @@ struct alignas(64) ConvK {
     int in_stride, out_mul;
     int n_phase, taps, cb, kb_main, kb_total, k_pad, chunk;
     int rev;        // tile_order: walk the tile list from the end (see ft_conv_desc.tile_order)
-    int dbg_skip;   // bring-up/profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no weight loads, 4 = no MMAs (results are garbage)
+    int dbg_skip;   // bring-up/profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no weight loads, 4 = no MMAs, 8 = no TMA stores (results are garbage)
     int M, m_tiles, n_tiles, num_tiles;
     int bw, bh, bn, lg_bw, lg_bh, tiles_w, tiles_h;
     int act;
     float slope;
+    float act_mul;   // tensor-core epilogue: out = max(v, act_mul * v)
     int8_t tap_dy[4][64];
     int8_t tap_dx[4][64];
     int8_t ph_oy[4];
@@ -459,7 +460,11 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                         const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
                         const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) o[g8 * 8 + k] = apply_act(fmaf(__uint_as_float(acc[j * SLAB + g8 * 8 + k]), scv[k], shv[k]), p.act, p.slope);
+                        for (int k = 0; k < 8; ++k) {
+                            // branch-free activation: max(v, s*v) with s = 1 (none), 0 (ReLU), slope (LeakyReLU, 0 <= slope <= 1)
+                            const float v = fmaf(__uint_as_float(acc[j * SLAB + g8 * 8 + k]), scv[k], shv[k]);
+                            o[g8 * 8 + k] = fmaxf(v, v * p.act_mul);
+                        }
                         if (p.out_f32 && valid) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k)
@@ -476,14 +481,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                         if (cbase + g8 * 8 >= p.cout_p8) break;
                         uint32_t hv[4], lv[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            __half h0, l0, h1, l1;
-                            split_f32(o[g8 * 8 + 2 * k], h0, l0);
-                            split_f32(o[g8 * 8 + 2 * k + 1], h1, l1);
-                            const __half2 h2 = __halves2half2(h0, h1), l2 = __halves2half2(l0, l1);
-                            hv[k] = *reinterpret_cast<const uint32_t*>(&h2);
-                            lv[k] = *reinterpret_cast<const uint32_t*>(&l2);
-                        }
+                        for (int k = 0; k < 4; ++k) split_f32x2(o[g8 * 8 + 2 * k], o[g8 * 8 + 2 * k + 1], hv[k], lv[k]);
                         uint32_t off = (uint32_t)row * RB + (uint32_t)g8 * 16u;
                         off ^= ((off >> 7) & SW_MASK) << 4;
                         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + off), "r"(hv[0]), "r"(hv[1]), "r"(hv[2]), "r"(hv[3]) : "memory");
@@ -492,7 +490,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                     }
                     fence_proxy_async();              // generic-proxy smem writes -> visible to the TMA (async proxy)
                     named_bar_sync(1 + group, 128);
-                    if (leader) {
+                    if (leader && !(p.dbg_skip & 8)) {
                         tma_store_4d(&p.out_map[tc.phase][0], buf, cbase, tc.qx0, tc.qy0, tc.n0);
                         if (p.out_lo) tma_store_4d(&p.out_map[tc.phase][1], buf + G::SLAB_PLANE, cbase, tc.qx0, tc.qy0, tc.n0);
                         bulk_commit();
@@ -715,6 +713,8 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     k.kb_main = k.k_pad / BK;
     k.cout = d->cout, k.cout_p8 = round_up(d->cout, 8), k.cout_pad = d->cout_pad;
     k.scale = d->scale, k.shift = d->shift, k.act = d->act, k.slope = d->slope;
+    FT_REQUIRE(d->act != FT_ACT_LEAKY || (d->slope >= 0.f && d->slope <= 1.f), "conv2d: LeakyReLU slope must lie in [0, 1] (got %g)", (double)d->slope);
+    k.act_mul = d->act == FT_ACT_RELU ? 0.f : d->act == FT_ACT_LEAKY ? d->slope : 1.f;
     k.w_tile = (const uint8_t*)d->w_tile, k.w_gemm = d->w_gemm;
     if (d->out.hi) {
         if (int e = check_view(d->out, "conv2d.out")) return e;
