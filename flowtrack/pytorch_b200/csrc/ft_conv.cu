@@ -43,6 +43,23 @@
 
 namespace ft {
 
+// Division by a runtime constant as multiply-high + shift (Granlund-Montgomery round-up magic; exact for n < 2^31):
+// tile_coord runs in every role once per tile, and four hardware-less integer divisions were ~15 % of the epilogue's
+// instructions on the small-K layers.
+struct FastDiv {
+    uint32_t m, l;
+    int d;
+};
+static inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = d;
+    f.l = 0;
+    while ((1u << f.l) < (uint32_t)d) ++f.l;                       // ceil(log2 d)
+    f.m = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << f.l) - (uint64_t)d)) / (uint64_t)d + 1);
+    return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return (int)((__umulhi((uint32_t)n, f.m) + (uint32_t)n) >> f.l); }
+
 struct alignas(64) ConvK {
     CUtensorMap in_map[4][2];    // [input parity view][hi, lo]   (stride 1: only view 0)
     CUtensorMap out_map[4][2];   // [output phase][hi, lo]        (plain conv: only phase 0)
@@ -64,6 +81,7 @@ struct alignas(64) ConvK {
     int res_ld, res_coff;
     int in_stride, out_mul;
     int n_phase, taps, cb, kb_main, kb_total, k_pad, chunk;
+    FastDiv fd_n_tiles, fd_m_units, fd_tiles_w, fd_tiles_h;
     int rev;        // tile_order: walk the tile list from the end (see ft_conv_desc.tile_order)
     int dbg_skip;   // bring-up/profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no weight loads, 4 = no MMAs, 8 = no TMA stores (results are garbage)
     int M, m_tiles, n_tiles, num_tiles;
@@ -118,23 +136,20 @@ template <bool GATHER, bool PAIR = false>
 __device__ __forceinline__ TileCoord tile_coord(const ConvK& p, int tile, int cta_rank = 0) {
     TileCoord t;
     if (p.rev) tile = p.num_tiles - 1 - tile;
-    t.nt = tile % p.n_tiles;               // consecutive CTAs share the A tile (L2 reuse), differ in weights
-    const int r = tile / p.n_tiles;
-    if (PAIR) {                            // a pair tile = two consecutive m-tiles (one per CTA) x one n-tile
-        const int mp = (p.m_tiles + 1) >> 1;
-        t.mt = (r % mp) * 2 + cta_rank;    // may be == m_tiles for the odd tail: an all-padding box (zero loads, clipped stores)
-        t.phase = r / mp;
-    } else {
-        t.mt = r % p.m_tiles;
-        t.phase = r / p.m_tiles;
-    }
+    const int r = fdiv(tile, p.fd_n_tiles);
+    t.nt = tile - r * p.n_tiles;           // consecutive CTAs share the A tile (L2 reuse), differ in weights
+    // fd_m_units divides by the m-tiles (single CTA) or the m-tile pairs (PAIR: two consecutive m-tiles, one per CTA, x one n-tile)
+    t.phase = fdiv(r, p.fd_m_units);
+    const int mu = r - t.phase * p.fd_m_units.d;
+    t.mt = PAIR ? mu * 2 + cta_rank : mu;  // pair: may be == m_tiles for the odd tail: an all-padding box (zero loads, clipped stores)
     if (GATHER) {
         t.qx0 = t.mt * BM, t.qy0 = 0, t.n0 = 0;   // linear pixel index; the output map is [C, M]
     } else {
-        const int tw = t.mt % p.tiles_w, r2 = t.mt / p.tiles_w;
+        const int r2 = fdiv(t.mt, p.fd_tiles_w), tw = t.mt - r2 * p.tiles_w;
+        const int r3 = fdiv(r2, p.fd_tiles_h);
         t.qx0 = tw * p.bw;
-        t.qy0 = (r2 % p.tiles_h) * p.bh;
-        t.n0 = (r2 / p.tiles_h) * p.bn;
+        t.qy0 = (r2 - r3 * p.tiles_h) * p.bh;
+        t.n0 = r3 * p.bn;
     }
     return t;
 }
@@ -823,6 +838,8 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     const bool pair = d->cta_pair != 0;
     FT_REQUIRE(!pair || (!gather && BN >= 64), "conv2d: cta_pair needs the TMA variant and block_n >= 64");
     k.num_tiles = k.n_phase * (pair ? (k.m_tiles + 1) / 2 : k.m_tiles) * k.n_tiles;
+    k.fd_n_tiles = make_fastdiv(k.n_tiles), k.fd_m_units = make_fastdiv(pair ? (k.m_tiles + 1) / 2 : k.m_tiles);
+    k.fd_tiles_w = make_fastdiv(k.tiles_w > 0 ? k.tiles_w : 1), k.fd_tiles_h = make_fastdiv(k.tiles_h > 0 ? k.tiles_h : 1);
 
 #define FT_CASE(BN_)                                                                                                          \
     case BN_:                                                                                                                 \
