@@ -153,3 +153,41 @@ def emulate_corr_banded(in1, in2):
                                     out[n, (tj + D) * 21 + ti + D, y, x] = v / C
                 assert len(written) == ROWS * 21
     return out
+
+
+def corr_pair_unit_coverage(H, parts=3):
+    """Mirror of corr_pair_unit (csrc/ft_corr.cu): for a parity class with H2c rows, the (in1' row, displacement row) pairs
+    every CTA of every pair unit handles.  Returns {(a, tj): count} over all units -- each in-image pair must appear once."""
+    D, ROWS = 10, 4
+    out = {}
+    for py in (0, 1):
+        H2c = (H - py + 1) // 2
+        a_tiles = ((H + 1) // 2 + ROWS - 1) // ROWS
+        ap_tiles = (a_tiles + 1) // 2
+        cover = {}
+        for ap in range(ap_tiles):
+            A0 = ap * 2 * ROWS
+            r_lo, r_end = max(0, A0 - D), min(H2c, A0 + 2 * ROWS + D)
+            chunks = (r_end - r_lo + ROWS - 1) // ROWS if r_end > r_lo else 0
+            per = (chunks + parts - 1) // parts
+            for part in range(parts):
+                c_lo = min(chunks, part * per)
+                nch = min(chunks, c_lo + per) - c_lo
+                for rank in (0, 1):
+                    for q in range(ROWS):
+                        a = A0 + rank * ROWS + q
+                        if a >= H2c:
+                            continue                                   # rows beyond the image: nothing is stored
+                        if part == 0:                                  # the zero loop
+                            for tj in range(-D, D + 1):
+                                if not (0 <= a + tj < H2c):
+                                    cover[(a, tj)] = cover.get((a, tj), 0) + 1
+                        for j in range(nch):
+                            r0 = r_lo + (c_lo + j) * ROWS
+                            for rr in range(ROWS):
+                                row = r0 + rr
+                                tj = row - a
+                                if -D <= tj <= D and row < H2c:
+                                    cover[(a, tj)] = cover.get((a, tj), 0) + 1
+        out[py] = (H2c, cover)
+    return out

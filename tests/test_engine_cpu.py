@@ -178,3 +178,14 @@ def test_correlation_banded_gemm_decomposition(shape):
     out = emulate.emulate_corr_banded(a, b)
     assert not torch.isnan(out).any()
     assert (out - ref).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("H", [2, 6, 13, 16, 48, 50, 96])
+@pytest.mark.parametrize("parts", [1, 2, 3, 5])
+def test_correlation_pair_units_cover_every_displacement_once(H, parts):
+    """The CTA-pair work decomposition of the correlation kernel (corr_pair_unit): every (in1' row, displacement row) of
+    every parity class is produced exactly once -- by a chunk when the in2' row exists, by the zero loop when it does not."""
+    for py, (H2c, cover) in emulate.corr_pair_unit_coverage(H, parts).items():
+        want = {(a, tj) for a in range(H2c) for tj in range(-10, 11)}
+        assert set(cover) == want, (py, sorted(want - set(cover))[:5], sorted(set(cover) - want)[:5])
+        assert all(v == 1 for v in cover.values())
