@@ -22,6 +22,8 @@ LAYERS = [
     ("l1 1x1 64->256 @64x48 B64", lambda: nn.Conv2d(64, 256, 1, bias=False), (64, 64, 64, 48)),
     ("l4 1x1 512->2048 @8x6 B64", lambda: nn.Conv2d(512, 2048, 1, bias=False), (64, 512, 8, 6)),
     ("flow deconv2 392->64 @48x64 B16", lambda: nn.ConvTranspose2d(392, 64, 4, 2, 1), (16, 392, 48, 64)),
+    ("pose stem 7x7/2 3->64 @256x192 B64", lambda: nn.Conv2d(3, 64, 7, 2, 3, bias=False), (64, 3, 256, 192)),
+    ("l1 3x3 64->64 @64x48 B64", lambda: nn.Conv2d(64, 64, 3, 1, 1, bias=False), (64, 64, 64, 48)),
 ]
 ONLY = os.environ.get("CB_ONLY")            # e.g. "0:128:0,0:128:1" = layer index : block_n : pair
 only = set(tuple(int(v) for v in item.split(":")) for item in ONLY.split(",")) if ONLY else None
@@ -32,7 +34,7 @@ for li, (name, ctor, shape) in enumerate(LAYERS):
         continue
     mod = ctor()
     layer = engine.conv_from_modules(mod, None, _lib.ACT_RELU, device="cuda")
-    xa = gpu_util.pack_nchw(torch.randn(*shape, device="cuda"), layer.cin_p)
+    xa = gpu_util.pack_nchw(torch.randn(*shape, device="cuda"), layer.cin_p, xpad=layer.in_xpad)
     ho, wo = layer.out_hw(shape[2], shape[3])
     out = engine.Act(shape[0], ho, wo, layer.cout, "cuda")
     fl = layer.flops(shape[0], shape[2], shape[3])
