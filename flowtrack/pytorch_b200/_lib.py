@@ -21,7 +21,7 @@ class FtConvDesc(ctypes.Structure):
                 ("pad", ctypes.c_int32), ("cout", ctypes.c_int32), ("cout_pad", ctypes.c_int32), ("k_pad", ctypes.c_int32),
                 ("block_n", ctypes.c_int32), ("act", ctypes.c_int32), ("slope", c_float), ("precision", ctypes.c_int32),
                 ("impl", ctypes.c_int32), ("k_mode", ctypes.c_int32), ("in_xpad_l", ctypes.c_int32), ("in_xpad_r", ctypes.c_int32),
-                ("cta_pair", ctypes.c_int32), ("res_blocks", ctypes.c_int32), ("tile_order", ctypes.c_int32)]
+                ("cta_pair", ctypes.c_int32), ("res_blocks", ctypes.c_int32), ("pad_hi", ctypes.c_int32), ("tile_order", ctypes.c_int32)]
 
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
@@ -29,7 +29,7 @@ KIND_CONV, KIND_DECONV = 0, 1
 PREC_SPLIT, PREC_FAST = 0, 1
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
 K_PACKED, K_TAP64, K_ROW = 0, 1, 2
-ABI_VERSION = 10        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
+ABI_VERSION = 11        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
 
 # name -> (restype, argtypes): every symbol include/flowtrack_b200.h declares
 SIGNATURES = {
@@ -51,6 +51,7 @@ SIGNATURES = {
     "ft_conv2d_fprop": (c_int, [ctypes.POINTER(FtConvDesc), c_void_p]),
     "ft_maxpool3x3s2": (c_int, [ctypes.POINTER(FtAct)] * 2 + [c_void_p]),
     "ft_pack_image": (c_int, [c_void_p] + [c_ll] * 4 + [c_int, c_float, ctypes.POINTER(FtAct), c_int, c_int, c_void_p]),
+    "ft_pack_image_s2d": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(FtAct), c_int, c_int, c_void_p]),
     "ft_pack_pair_ws_floats": (c_int, [c_int]),
     "ft_pack_pair": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, ctypes.POINTER(FtAct), c_int, c_int, c_void_p]),
     "ft_upsample4x": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_float, c_int, c_void_p]),

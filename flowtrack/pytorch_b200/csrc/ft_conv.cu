@@ -683,8 +683,10 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     if (d->kind == FT_CONV) {
         FT_REQUIRE(d->kh > 0 && d->kw > 0 && d->kh * d->kw <= 64 && d->stride > 0 && d->pad >= 0, "conv2d: unsupported window %dx%d s%d p%d", d->kh, d->kw, d->stride, d->pad);
         k.n_phase = 1, k.taps = d->kh * d->kw;
-        k.Ho = (k.H + 2 * d->pad - d->kh) / d->stride + 1;
-        k.Wo = (k.W + 2 * d->pad - d->kw) / d->stride + 1;
+        const int pad_hi = d->pad_hi > 0 ? d->pad_hi : d->pad;
+        FT_REQUIRE(pad_hi <= d->pad, "conv2d: pad_hi %d must not exceed pad %d", pad_hi, d->pad);
+        k.Ho = (k.H + d->pad + pad_hi - d->kh) / d->stride + 1;
+        k.Wo = (k.W + d->pad + pad_hi - d->kw) / d->stride + 1;
         k.Qh = k.Ho, k.Qw = k.Wo, k.in_stride = d->stride, k.out_mul = 1;
         for (int r = 0; r < d->kh; ++r)
             for (int s = 0; s < d->kw; ++s) {

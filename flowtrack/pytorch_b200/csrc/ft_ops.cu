@@ -256,6 +256,27 @@ __global__ void pack_image_kernel(const float* __restrict__ src, long long sb, l
     }
 }
 
+// space-to-depth packing of a 3-channel image (see ft_pack_image_s2d): one thread per s2d pixel = 16 channels
+__global__ void pack_image_s2d_kernel(const float* __restrict__ src, int B, int H, int W, ft_act d, int xl) {
+    const int H2 = H >> 1, W2 = W >> 1;
+    const size_t total = (size_t)B * H2 * W2;
+    const size_t plane = (size_t)H * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int X = (int)(i % W2), Y = (int)((i / W2) % H2), b = (int)(i / ((size_t)W2 * H2));
+        const float* s = src + (size_t)b * 3 * plane + (size_t)(2 * Y) * W + 2 * X;
+        float v[16];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 r0 = __ldg(reinterpret_cast<const float2*>(s + c * plane)), r1 = __ldg(reinterpret_cast<const float2*>(s + c * plane + W));
+            v[0 + c] = r0.x, v[4 + c] = r0.y, v[8 + c] = r1.x, v[12 + c] = r1.y;
+        }
+        v[3] = v[7] = v[11] = v[15] = 0.f;
+        const size_t pix = ((size_t)b * H2 + Y) * d.w + X + xl;
+        store8(d, pix, 0, v);
+        store8(d, pix, 8, v + 8);
+    }
+}
+
 __global__ void maxpool3x3s2_kernel(ft_act in, ft_act out) {
     const int groups = out.c / 8;
     const size_t total = (size_t)out.n * out.h * out.w * groups;
@@ -654,6 +675,16 @@ int ft_pack_image(const float* src, long long sb, long long sc, long long sh, lo
     const int W = dst->w - xpad_l - xpad_r;
     pack_image_kernel<<<grid_for((size_t)dst->n * dst->h * W * (dst->c / 8), 256), 256, 0, (cudaStream_t)stream>>>(src, sb, sc, sh, sw, C, mul, *dst, W, xpad_l);
     return check_launch("pack_image_kernel");
+}
+
+int ft_pack_image_s2d(const float* src, int B, int H, int W, const ft_act* dst, int xpad_l, int xpad_r, void* stream) {
+    if (int e = check_act(dst, "pack_image_s2d.dst", false)) return e;
+    FT_REQUIRE(src && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "pack_image_s2d: H and W must be even (got %d x %d)", H, W);
+    FT_REQUIRE(((uintptr_t)src & 7) == 0, "pack_image_s2d: src must be 8-byte aligned");
+    FT_REQUIRE(dst->c == 16 && dst->n == B && dst->h == H / 2 && xpad_l >= 0 && xpad_r >= 0 && dst->w == W / 2 + xpad_l + xpad_r,
+               "pack_image_s2d: destination must be [B, H/2, xpad_l + W/2 + xpad_r, 16] (got n=%d h=%d w=%d c=%d)", dst->n, dst->h, dst->w, dst->c);
+    pack_image_s2d_kernel<<<grid_for((size_t)B * (H / 2) * (W / 2), 256), 256, 0, (cudaStream_t)stream>>>(src, B, H, W, *dst, xpad_l);
+    return check_launch("pack_image_s2d_kernel");
 }
 
 int ft_pack_pair_ws_floats(int B) { return B * 3 * (2 * PAIR_MEAN_CHUNKS + 1); }

@@ -200,12 +200,16 @@ class ConvLayer:
     """conv / deconv(k4,s2,p1) + per-channel scale/shift + optional residual + activation, weights resident on the GPU."""
 
     def __init__(self, kind, weight, scale, shift, stride=1, pad=0, act=_lib.ACT_NONE, slope=0.1, cin_p=None, device=None, block_n=None, keep_host=False,
-                 residual=False, k_mode=None):
+                 residual=False, k_mode=None, pad_hi=None, flops_per_pixel=None):
+        """pad_hi: zero padding after the last row/column when it differs from `pad` (space-to-depth stems);
+        flops_per_pixel: algorithmic FLOPs per output pixel when the packed weights carry structural zeros."""
         if kind == _lib.KIND_CONV:
             self.cout, cin, self.kh, self.kw = weight.shape
         else:
             cin, self.cout, self.kh, self.kw = weight.shape
         self.kind, self.stride, self.pad, self.act, self.slope = kind, stride, pad, act, slope
+        self.pad_hi = pad if pad_hi is None else pad_hi
+        self.flops_per_pixel = flops_per_pixel
         self.cin, self.cin_p = cin, cin_p or pad8(cin)
         assert self.cin_p % 8 == 0 and self.cin_p >= cin
         # K layout: small-Cin plain convolutions (the stems) pack K across taps and are gathered by cp.async;
@@ -272,13 +276,15 @@ class ConvLayer:
     def out_hw(self, h, w):
         if self.kind == _lib.KIND_DECONV:
             return 2 * h, 2 * w
-        return (h + 2 * self.pad - self.kh) // self.stride + 1, (w + 2 * self.pad - self.kw) // self.stride + 1
+        return (h + self.pad + self.pad_hi - self.kh) // self.stride + 1, (w + self.pad + self.pad_hi - self.kw) // self.stride + 1
 
     def flops(self, n, h, w):
         """Algorithmic FLOPs (2 x MACs over the real, un-padded channels) of one forward on an n x h x w input."""
         if self.kind == _lib.KIND_DECONV:
             return 2 * n * h * w * self.cin * self.cout * self.kh * self.kw
         ho, wo = self.out_hw(h, w)
+        if self.flops_per_pixel is not None:
+            return n * ho * wo * self.flops_per_pixel
         return 2 * n * ho * wo * self.cin * self.cout * self.kh * self.kw
 
     def desc(self, x, out=None, out_f32=None, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05, tiling=None):
@@ -295,6 +301,7 @@ class ConvLayer:
         d.w_tile, d.w_gemm = self.tile_image(bn).data_ptr(), self.w_gemm.data_ptr()
         d.scale, d.shift = self.scale.data_ptr(), self.shift.data_ptr()
         d.kind, d.kh, d.kw, d.stride, d.pad = self.kind, self.kh, self.kw, self.stride, self.pad
+        d.pad_hi = self.pad_hi if self.pad_hi != self.pad else 0
         d.cout, d.cout_pad, d.k_pad, d.block_n = self.cout, self.cout_pad, self.k_pad, bn
         d.act, d.slope, d.precision, d.impl = self.act, self.slope, precision, impl
         d.k_mode, d.res_blocks, d.cta_pair = self.k_mode, (-(-bn // BK) if self.residual else 0), pair
@@ -322,6 +329,45 @@ def conv_from_modules(conv, bn=None, act=_lib.ACT_NONE, cin_p=None, device=None,
     assert conv.dilation == (1, 1) and conv.groups == 1
     return ConvLayer(_lib.KIND_CONV, conv.weight, scale, shift, stride=conv.stride[0], pad=conv.padding[0], act=act,
                      cin_p=cin_p, device=device, keep_host=keep_host, residual=residual, k_mode=k_mode)
+
+
+def stem_s2d_weights(weight):
+    """Conv2d(3, Cout, 7, stride 2, pad 3) weight [Cout,3,7,7] -> the equivalent 4x4 stride-1 (pad 2 before, 1 after) weight
+    [Cout,16,4,4] over the space-to-depth image of ft_pack_image_s2d (channel (py*2+px)*4 + c = src[c, 2Y+py, 2X+px]):
+    input row 2y-3+ky is s2d row y-2+r with parity py, ky = 2r + py - 1 (ky = -1 does not exist: zero weight)."""
+    w = weight.detach().float().cpu()
+    cout, cin, kh, kw = w.shape
+    assert (cin, kh, kw) == (3, 7, 7)
+    w4 = torch.zeros(cout, 16, 4, 4)
+    for r in range(4):
+        for py in range(2):
+            ky = 2 * r + py - 1
+            if not 0 <= ky < 7:
+                continue
+            for s_ in range(4):
+                for px in range(2):
+                    kx = 2 * s_ + px - 1
+                    if 0 <= kx < 7:
+                        w4[:, (py * 2 + px) * 4:(py * 2 + px) * 4 + 3, r, s_] = w[:, :, ky, kx]
+    return w4
+
+
+def stem_s2d_from_modules(conv, bn=None, act=_lib.ACT_NONE, device=None, keep_host=False):
+    """7x7 stride-2 pad-3 three-channel stem (+ eval BatchNorm) -> the space-to-depth ConvLayer (FT_K_ROW, 4 k-blocks of 64
+    instead of 7; input from ft_pack_image_s2d).  Same arithmetic: every product of the original appears exactly once."""
+    assert conv.kernel_size == (7, 7) and conv.stride == (2, 2) and conv.padding == (3, 3) and conv.in_channels == 3 and conv.groups == 1
+    cout = conv.out_channels
+    if bn is not None:
+        scale, shift = fold_bn(bn)
+        if conv.bias is not None:
+            shift = shift + conv.bias.detach().float().cpu().numpy() * scale
+    else:
+        scale = np.ones(cout, np.float32)
+        shift = conv.bias.detach().float().cpu().numpy() if conv.bias is not None else np.zeros(cout, np.float32)
+    layer = ConvLayer(_lib.KIND_CONV, stem_s2d_weights(conv.weight), scale, shift, stride=1, pad=2, pad_hi=1, act=act, cin_p=16, device=device,
+                      keep_host=keep_host, flops_per_pixel=2 * 3 * 49 * cout)
+    assert layer.k_mode == _lib.K_ROW
+    return layer
 
 
 class FlowHead:

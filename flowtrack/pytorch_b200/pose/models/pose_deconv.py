@@ -111,7 +111,10 @@ class DeconvResnet(nn.Module):
         R, N = _lib.ACT_RELU, _lib.ACT_NONE
         mk = lambda conv, bn, act, cin_p=None, residual=False: engine.conv_from_modules(conv, bn, act, cin_p=cin_p, device=device, keep_host=keep_host,
                                                                                         residual=residual)
-        L = {"stem": mk(self.conv1, self.bn1, R, 8), "blocks": []}
+        # stem: space-to-depth form (4 k-blocks per tile instead of 7, half the packed input bytes); FT_STEM_S2D=0 keeps the 7x7 form
+        self._stem_s2d = os.environ.get("FT_STEM_S2D", "1") != "0"
+        stem = engine.stem_s2d_from_modules(self.conv1, self.bn1, R, device=device, keep_host=keep_host) if self._stem_s2d else mk(self.conv1, self.bn1, R, 8)
+        L = {"stem": stem, "blocks": []}
         for li in range(1, 5):
             for blk in getattr(self, "layer%d" % li):
                 L["blocks"].append(dict(
@@ -127,10 +130,15 @@ class DeconvResnet(nn.Module):
         L = self._layers
         p = engine.Plan(device, precision, impl)
         src = p.f32(B, 3, H, W)                                 # static fp32 NCHW input (graph-capturable)
-        x = p.act(B, H, W, 8, xpad=L["stem"].in_xpad)           # packed input, 3 -> 8 channels, rows zero-padded for the FT_K_ROW stem
-        xs, st = x.struct(), src.stride()
-        p.call("pack_image", _lib.lib().ft_pack_image, src.data_ptr(), st[0], st[1], st[2], st[3], 3, 1.0, xs, x.xl, x.xr)
-        h, w = L["stem"].out_hw(H, W)
+        if L["stem"].cin_p == 16:                               # space-to-depth stem: [B, H/2, W/2, 16], rows zero-padded for FT_K_ROW
+            x = p.act(B, H // 2, W // 2, 16, xpad=L["stem"].in_xpad)
+            p.call("pack_image_s2d", _lib.lib().ft_pack_image_s2d, src.data_ptr(), B, H, W, x.struct(), x.xl, x.xr)
+            h, w = L["stem"].out_hw(H // 2, W // 2)
+        else:
+            x = p.act(B, H, W, 8, xpad=L["stem"].in_xpad)       # packed input, 3 -> 8 channels, rows zero-padded for the FT_K_ROW stem
+            xs, st = x.struct(), src.stride()
+            p.call("pack_image", _lib.lib().ft_pack_image, src.data_ptr(), st[0], st[1], st[2], st[3], 3, 1.0, xs, x.xl, x.xr)
+            h, w = L["stem"].out_hw(H, W)
         y = p.conv(L["stem"], x, p.act(B, h, w, 64), name="stem")
         h, w = (h + 1) // 2, (w + 1) // 2
         pooled = p.act(B, h, w, 64)

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 10
+#define FT_ABI_VERSION 11
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -111,6 +111,8 @@ typedef struct {
                                Block j holds diag(f) for channels [64j, 64j+64) of the tile, where
                                f[c] = 1/scale[c] must be a power of two (the host folds BatchNorm's
                                scale into the weights of such layers), so acc += res * f exactly.   */
+    int32_t pad_hi;         /* zero padding after the last row / column; 0 = same as `pad`.  The space-to-depth form of a 7x7
+                               stride-2 stem is a 4x4 stride-1 convolution padded 2 before and 1 after.                */
     int32_t tile_order;     /* 0: the persistent CTAs walk the output tiles first image -> last image, 1: last -> first.
                                A layer that runs in the opposite order of its producer starts on the part of its
                                input that is still in the 126 MB L2 (engine.py alternates the order along a plan). */
@@ -169,6 +171,11 @@ int ft_maxpool3x3s2(const ft_act* in, const ft_act* out, void* stream);
  * (the caller zero-fills them once; FT_K_ROW convolutions read them as the convolution's zero border). */
 int ft_pack_image(const float* src, long long sb, long long sc, long long sh, long long sw, int C,
                   float mul, const ft_act* dst, int xpad_l, int xpad_r, void* stream);
+/* Space-to-depth packing for 3-channel 7x7 stride-2 stems: src [B,3,H,W] fp32 contiguous (H, W even) -> split-fp16 NHWC
+ * view dst [B, H/2, xpad_l + W/2 + xpad_r, 16]: channel (py*2+px)*4 + c holds src[b, c, 2Y+py, 2X+px], the 4th channel of
+ * every sub-pixel is zero.  The stem then runs as a 4x4 stride-1 convolution (pad 2, pad_hi 1) whose kernel row is exactly
+ * one 64-element k-block: K = 256 instead of 448, and half the packed bytes.                                            */
+int ft_pack_image_s2d(const float* src, int B, int H, int W, const ft_act* dst, int xpad_l, int xpad_r, void* stream);
 /* FlowNet2 input normalisation: pair [B,3,2,H,W] (RGB 0..255) -> x = (pair - mean_bc) / rgb_max laid
  * out as [B,6,H,W] fp32 (x_f32, optional) and as split-fp16 NHWC (dst, optional, 6 -> 8 channels).
  * `mean_ws` is an 8-byte aligned workspace of ft_pack_pair_ws_floats(B) floats (partial sums + means). */

@@ -75,10 +75,23 @@ def nhwc(x, cpad):
     return torch.nn.functional.pad(x, (0, cpad - x.shape[-1])).contiguous()
 
 
+def space_to_depth16(x):
+    """[B,3,H,W] -> [B,H/2,W/2,16] NHWC: channel (py*2+px)*4 + c = x[:, c, 2Y+py, 2X+px] (ft_pack_image_s2d)."""
+    B, C, H, W = x.shape
+    out = torch.zeros(B, H // 2, W // 2, 16, dtype=x.dtype)
+    for py in range(2):
+        for px in range(2):
+            out[..., (py * 2 + px) * 4:(py * 2 + px) * 4 + C] = x[:, :, py::2, px::2].permute(0, 2, 3, 1)
+    return out
+
+
 def emulate_pose(model, x):
     """Walk DeconvResnet exactly like DeconvResnet._build_plan does, on the CPU."""
     L = model._pack(None, keep_host=True)
-    t = emulate_layer(L["stem"], nhwc(x, 8))
+    if L["stem"].cin_p == 16:          # space-to-depth stem: mirror of ft_pack_image_s2d
+        t = emulate_layer(L["stem"], space_to_depth16(x))
+    else:
+        t = emulate_layer(L["stem"], nhwc(x, 8))
     t = torch.nn.functional.max_pool2d(t.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
     for blk in L["blocks"]:
         a = emulate_layer(blk["c2"], emulate_layer(blk["c1"], t))

@@ -134,7 +134,7 @@ def test_library_exports_every_declared_symbol():
     declared -= {"ft_act", "ft_conv_desc"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     l = _lib.lib()                                         # loads the .so and resolves every symbol
-    assert l.ft_abi_version() == _lib.ABI_VERSION == 10
+    assert l.ft_abi_version() == _lib.ABI_VERSION == 11
     assert l.ft_sizeof(0) == ctypes.sizeof(_lib.FtAct) == 40 and l.ft_sizeof(1) == ctypes.sizeof(_lib.FtConvDesc)
 
 
@@ -189,3 +189,26 @@ def test_correlation_pair_units_cover_every_displacement_once(H, parts):
         want = {(a, tj) for a in range(H2c) for tj in range(-10, 11)}
         assert set(cover) == want, (py, sorted(want - set(cover))[:5], sorted(set(cover) - want)[:5])
         assert all(v == 1 for v in cover.values())
+
+
+def test_stem_space_to_depth_transform():
+    """7x7 stride-2 pad-3 stem == 4x4 stride-1 (pad 2 before, 1 after) conv over the space-to-depth image: the weight
+    transform in plain torch, and the packed FT_K_ROW layer (4 k-blocks) through the CPU emulation of ft_conv2d_fprop."""
+    torch.manual_seed(0)
+    conv = nn.Conv2d(3, 64, 7, 2, 3, bias=False).double()
+    bn = nn.BatchNorm2d(64).double().eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5), bn.bias.normal_(0, 0.1), bn.running_mean.normal_(0, 0.1), bn.running_var.uniform_(0.75, 1.25)
+    x = torch.randn(2, 3, 32, 24, dtype=torch.float64)
+    ref = torch.relu(bn(conv(x)))
+    s2d = torch.zeros(2, 16, 16, 12, dtype=torch.float64)
+    for py in range(2):
+        for px in range(2):
+            s2d[:, (py * 2 + px) * 4:(py * 2 + px) * 4 + 3] = x[:, :, py::2, px::2]
+    w4 = engine.stem_s2d_weights(conv.weight).double()
+    assert (torch.nn.functional.conv2d(torch.nn.functional.pad(s2d, (2, 1, 2, 1)), w4) - conv(x)).abs().max() < 1e-12
+    layer = engine.stem_s2d_from_modules(conv.float(), bn.float(), _lib.ACT_RELU, device=None, keep_host=True)
+    assert layer.k_mode == _lib.K_ROW and layer.k_pad == 256 and layer.out_hw(16, 12) == (16, 12) and (layer.pad, layer.pad_hi) == (2, 1)
+    assert layer.flops(2, 16, 12) == 2 * 2 * 16 * 12 * 3 * 49 * 64            # algorithmic FLOPs of the 7x7 convolution
+    y = emulate.emulate_layer(layer, s2d.permute(0, 2, 3, 1).float().contiguous())
+    assert (y.permute(0, 3, 1, 2)[:, :64].double() - ref).abs().max() < 1e-5

@@ -215,3 +215,32 @@ def test_reverse_tile_order_is_bit_identical(name, ctor, shape, act):
     a, fa = gpu_util.run_layer(layer, xa, want_f32=True, tile_order=0)
     b, fb = gpu_util.run_layer(layer, xa, want_f32=True, tile_order=1)
     assert torch.equal(fa, fb) and torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 48), (5, 3, 96, 160)])
+def test_stem_space_to_depth_path(shape):
+    """ft_pack_image_s2d + the 4x4 stride-1 FT_K_ROW stem (pad 2 / pad_hi 1) == Conv2d(3, 64, 7, 2, 3) + BN + ReLU."""
+    torch.manual_seed(3)
+    conv = nn.Conv2d(3, 64, 7, 2, 3, bias=False).double()
+    bn = nn.BatchNorm2d(64).double().eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5), bn.bias.normal_(0, 0.1), bn.running_mean.normal_(0, 0.1), bn.running_var.uniform_(0.75, 1.25)
+    x = torch.randn(*shape, dtype=torch.float64)
+    ref = torch.relu(bn(conv(x))).float()
+    layer = engine.stem_s2d_from_modules(conv.float(), bn.float(), _lib.ACT_RELU, device="cuda")
+    B, _, H, W = shape
+    xd = x.float().cuda().contiguous()
+    xa = engine.Act(B, H // 2, W // 2, 16, "cuda", xpad=layer.in_xpad)
+    _lib.check(_lib.lib().ft_pack_image_s2d(xd.data_ptr(), B, H, W, xa.struct(), xa.xl, xa.xr, gpu_util.sp()), "pack_image_s2d")
+    torch.cuda.synchronize()
+    packed = xa.to_nchw()                                            # [B,16,H/2,W/2]
+    for py in range(2):
+        for px in range(2):
+            c0 = (py * 2 + px) * 4
+            assert (packed[:, c0:c0 + 3].cpu() - x[:, :, py::2, px::2].float()).abs().max() < 1e-6
+            assert packed[:, c0 + 3].abs().max() == 0
+    for impl, tol in ((_lib.IMPL_SIMT, 2e-5), (_lib.IMPL_TCGEN05, 2e-5)):
+        out, f32 = gpu_util.run_layer(layer, xa, impl=impl, want_f32=True)
+        scale = max(1.0, ref.abs().max().item())
+        assert (f32.cpu() - ref).abs().max() < tol * scale
+        assert (out.to_nchw(64).cpu() - ref).abs().max() < tol * scale

@@ -70,3 +70,18 @@ def test_pose_graph_replay_is_deterministic_and_tracks_new_inputs():
     m.refresh()
     c1 = m(x1)
     assert torch.equal(a1, c1)
+
+
+def test_pose_forward_with_the_7x7_stem_form(monkeypatch):
+    """FT_STEM_S2D=0 keeps the original 7x7 FT_K_ROW stem; both stem forms give the same heat-maps."""
+    from flowtrack.pytorch_b200.pose import models as pose_models
+    from flowtrack.pytorch_b200.tracking import synthetic
+    torch.manual_seed(0)
+    m = synthetic.condition_pose_weights(pose_models.deconv("resnet50", 17, False), 0)
+    x = torch.randn(2, 3, 128, 96, generator=torch.Generator().manual_seed(1)).cuda()
+    a = m.cuda()(x).clone()
+    monkeypatch.setenv("FT_STEM_S2D", "0")
+    m.refresh()
+    b = m(x).clone()
+    assert m._layers["stem"].cin_p == 8
+    assert (a - b).abs().max() < 2e-4
