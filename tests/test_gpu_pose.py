@@ -85,3 +85,16 @@ def test_pose_forward_with_the_7x7_stem_form(monkeypatch):
     b = m(x).clone()
     assert m._layers["stem"].cin_p == 8
     assert (a - b).abs().max() < 2e-4
+
+
+def test_pose_r50_384x288_vs_oracle():
+    """BASELINE config 5 crop size (384x288 -> 96x72 heat-maps), batch not a multiple of the tile's image count."""
+    orc, m = _pair(50, calib_hw=(384, 288))
+    x = torch.randn(3, 3, 384, 288, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ref = orc(x)
+    out = m(x.cuda()).cpu()
+    err = (out - ref).abs().max().item()
+    print("pose r50 384x288 split max-abs %.3g (heat-map abs-max %.2f)" % (err, ref.abs().max().item()))
+    assert out.shape == (3, 17, 96, 72)
+    assert err < 1e-3, err
