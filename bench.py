@@ -58,7 +58,7 @@ class ClockSampler:
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -257,11 +257,21 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item() / steps                          # ms per step, max over ranks
 
+    # clocks: nvidia-smi needs ~0.1-0.3 s before its first sample and the timed region of 20 steps is < 0.1 s long, so the sampler
+    # starts first, the same device step runs untimed until samples are flowing (pre-roll, identical load), and it keeps sampling
+    # through the timed device steps and the timed e2e steps
     sampler = ClockSampler(local) if rank == 0 else None
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < args.preroll:
+        for _ in range(10):
+            device_step()
+        torch.cuda.synchronize()
     ms = timed(device_step, args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
     pipe.stage(data["pair"], data["crops"], data["centers"], data["scales"], data["prev_keypoints"], slot=1)   # slot 0 was staged by process()
     ms_e2e = timed(host_step, args.steps, max(1, args.warmup // 2), drain=host_drain)
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = "%.1f s untimed pre-roll of the same device step + the timed device steps + the timed e2e steps (20 ms sampling)" % args.preroll
     total_pairs = args.pairs * world
 
     out = None
@@ -385,13 +395,14 @@ def bench_correlation(torch, _lib, peaks):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS, help="frame pairs per GPU per step")
     ap.add_argument("--precision", default="split", choices=["split", "fast"])
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--preroll", type=float, default=0.6, help="seconds of untimed steps while nvidia-smi starts sampling")
     ap.add_argument("--host-crops", action="store_true", help="take ready-made person crops from the host instead of cutting them on the GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
