@@ -262,9 +262,9 @@ def run_ours(args):
     # through the timed device steps and the timed e2e steps
     sampler = ClockSampler(local) if rank == 0 else None
     t_pre = time.perf_counter()
-    while time.perf_counter() - t_pre < args.preroll:
+    while time.perf_counter() - t_pre < args.preroll:      # time-based, so NO collective in here: ranks may run different counts
         for _ in range(10):
-            device_step()
+            pipe.step_device()
         torch.cuda.synchronize()
     ms = timed(device_step, args.steps, args.warmup)
     pipe.stage(data["pair"], data["crops"], data["centers"], data["scales"], data["prev_keypoints"], slot=1)   # slot 0 was staged by process()
