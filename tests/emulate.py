@@ -204,3 +204,61 @@ def corr_pair_unit_coverage(H, parts=3):
                                     cover[(a, tj)] = cover.get((a, tj), 0) + 1
         out[py] = (H2c, cover)
     return out
+
+
+# ---- mirrors of the conv kernel's tile bookkeeping (csrc/ft_conv.cu: make_fastdiv / fdiv / tile_coord / choose_box) ----
+def make_fastdiv(d):
+    l = 0
+    while (1 << l) < d:
+        l += 1
+    m = (((1 << 32) * ((1 << l) - d)) // d + 1) & 0xffffffff
+    return m, l, d
+
+
+def fdiv(n, f):
+    m, l, _ = f
+    return ((((n * m) >> 32) + n) & 0xffffffffffffffff) >> l
+
+
+def choose_box(qw, qh, n):
+    best, box = -1, None
+    for lw in range(7, -1, -1):
+        for lh in range(7 - lw, -1, -1):
+            w, h = 1 << lw, 1 << lh
+            nn = 128 // (w * h)
+            tiles = -(-qw // w) * -(-qh // h) * -(-n // nn)
+            if best < 0 or tiles < best:
+                best, box = tiles, (w, h, nn)
+    return box
+
+
+def conv_tile_coverage(qw, qh, n, n_tiles, n_phase, pair, rev=False):
+    """Every (phase, m-tile, n-tile) the persistent CTAs of conv_tc_kernel visit, decoded like tile_coord does (multiply-high
+    division, CTA pairs taking two consecutive m-tiles).  Returns (visited list, m_tiles, pixel coverage count array)."""
+    bw, bh, bn = choose_box(qw, qh, n)
+    tiles_w, tiles_h = -(-qw // bw), -(-qh // bh)
+    m_tiles = tiles_w * tiles_h * -(-n // bn)
+    m_units = (m_tiles + 1) // 2 if pair else m_tiles
+    num_tiles = n_phase * m_units * n_tiles
+    f_n, f_m, f_w, f_h = make_fastdiv(n_tiles), make_fastdiv(m_units), make_fastdiv(tiles_w), make_fastdiv(tiles_h)
+    visited = []
+    cover = np.zeros((n_phase, n_tiles, n, qh, qw), np.int32)
+    for tile0 in range(num_tiles):
+        for rank in ((0, 1) if pair else (0,)):
+            tile = num_tiles - 1 - tile0 if rev else tile0
+            r = fdiv(tile, f_n)
+            nt = tile - r * n_tiles
+            phase = fdiv(r, f_m)
+            mu = r - phase * m_units
+            mt = mu * 2 + rank if pair else mu
+            assert (r, nt, phase, mu) == (tile // n_tiles, tile % n_tiles, (tile // n_tiles) // m_units, (tile // n_tiles) % m_units)
+            r2 = fdiv(mt, f_w)
+            tw = mt - r2 * tiles_w
+            r3 = fdiv(r2, f_h)
+            qx0, qy0, n0 = tw * bw, (r2 - r3 * tiles_h) * bh, r3 * bn
+            visited.append((phase, mt, nt))
+            if mt >= m_tiles:
+                assert n0 >= n                     # the odd tail of a pair: an all-padding box
+                continue
+            cover[phase, nt, n0:n0 + bn, qy0:qy0 + bh, qx0:qx0 + bw] += 1
+    return visited, m_tiles, cover

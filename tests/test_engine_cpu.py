@@ -212,3 +212,23 @@ def test_stem_space_to_depth_transform():
     assert layer.flops(2, 16, 12) == 2 * 2 * 16 * 12 * 3 * 49 * 64            # algorithmic FLOPs of the 7x7 convolution
     y = emulate.emulate_layer(layer, s2d.permute(0, 2, 3, 1).float().contiguous())
     assert (y.permute(0, 3, 1, 2)[:, :64].double() - ref).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("qw,qh,n", [(48, 64, 64), (6, 8, 64), (6, 8, 5), (96, 128, 3), (12, 16, 1), (150, 20, 1), (3, 3, 2)])
+@pytest.mark.parametrize("n_tiles,n_phase,pair", [(1, 1, False), (2, 1, True), (8, 4, True), (3, 4, False), (16, 1, True)])
+def test_conv_tile_decode_covers_every_output_once(qw, qh, n, n_tiles, n_phase, pair):
+    """tile_coord (multiply-high division, pixel boxes, CTA pairs, reverse order): every (phase, n-tile, pixel) of the output is
+    produced by exactly one tile, in both sweep directions."""
+    for rev in (False, True):
+        visited, m_tiles, cover = emulate.conv_tile_coverage(qw, qh, n, n_tiles, n_phase, pair, rev)
+        real = [v for v in visited if v[1] < m_tiles]
+        assert len(set(real)) == len(real) == n_phase * m_tiles * n_tiles
+        assert (cover == 1).all()
+
+
+def test_fastdiv_magic_is_exact():
+    rng = np.random.default_rng(0)
+    for d in list(range(1, 300)) + [384, 1536, 3072, 6240, 6400, 65536, 99991]:
+        f = emulate.make_fastdiv(d)
+        for nval in [0, 1, d - 1, d, d + 1, 2 * d - 1, 10 ** 6, (1 << 27) - 1] + rng.integers(0, 1 << 28, 40).tolist():
+            assert emulate.fdiv(int(nval), f) == int(nval) // d
