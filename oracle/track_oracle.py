@@ -16,8 +16,10 @@ CPU legs may import this.
                                themselves: reference_track.npz keys oks_*)
   nms_cpu                      lib/detection/nms/src/nms.c:36-62 (cpu_nms: suppress at IoU >= thresh) with the ordering
                                of pth_nms.py:13-22; inclusive=False gives the GPU variant (nms_kernel.cu:62, IoU > thresh).
-                               The reference extension needs TH/cffi (gone): parity of this restatement is pinned by
-                               hand-checked cases and set properties only ("parity unpinned" against reference output).
+                               Pinned against the reference's own cpu_nms: lib/detection/nms/src/nms.c compiles
+                               unmodified against oracle/ref_shims/TH/TH.h into oracle/_ref/libref_nms.so (ref_cpu_nms
+                               below drives it the way pth_nms.py:9-22 does); its outputs on seeded box sets are the
+                               fixtures nms_keep_* of tests/golden/reference_track.npz.
 """
 import numpy as np
 
@@ -184,3 +186,35 @@ def nms_oks(pred, oks_thresh, delta, kpt_thresh=0):
         ind = np.where(oks <= oks_thresh)[0]
         order = order[ind + 1]
     return keep
+
+
+def ref_cpu_nms(dets, thresh):
+    """The reference's own cpu_nms (oracle/_ref/libref_nms.so, built by `make -C oracle ref` from the unmodified nms.c),
+    called like pth_nms.py:9-22 calls it: areas = (x2-x1+1)(y2-y1+1), order = argsort(scores, descending).  Returns the kept
+    indices or None when the library is not there (GPU box without /root/reference and without the prebuilt file)."""
+    import ctypes
+    import os
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_nms.so")
+    if not os.path.exists(so):
+        return None
+    lib = ctypes.CDLL(so)
+
+    class T(ctypes.Structure):
+        _fields_ = [("data", ctypes.c_void_p), ("size", ctypes.c_long * 2)]
+
+    dets = np.ascontiguousarray(dets, dtype=np.float32)
+    n = dets.shape[0]
+    areas = ((dets[:, 2] - dets[:, 0] + 1) * (dets[:, 3] - dets[:, 1] + 1)).astype(np.float32)
+    order = np.lexsort((np.arange(n), -dets[:, 4].astype(np.float64))).astype(np.int64)     # descending score, ties by index
+    keep = np.zeros(max(n, 1), np.int64)
+    num = np.zeros(1, np.int64)
+
+    def t(a, s0, s1=1):
+        return T(a.ctypes.data, (ctypes.c_long * 2)(s0, s1))
+
+    lib.cpu_nms.argtypes = [ctypes.POINTER(T)] * 5 + [ctypes.c_float]
+    lib.cpu_nms.restype = ctypes.c_int
+    rc = lib.cpu_nms(ctypes.byref(t(keep, n)), ctypes.byref(t(num, 1)), ctypes.byref(t(dets, n, 5)), ctypes.byref(t(order, n)),
+                     ctypes.byref(t(areas, n)), ctypes.c_float(thresh))
+    assert rc == 1
+    return keep[:int(num[0])].copy()

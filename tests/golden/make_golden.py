@@ -154,6 +154,12 @@ def make_track(ref_tf, ref_eval=None):
             extra["oks_keep_%g_%g" % (th, kt)] = np.array(ref_eval.nms_oks(preds, th, recipes.COCO_DELTA, kt), np.int64)
         j = np.array([p["joints"] for p in preds])
         extra["oks_pairwise0"] = ref_eval.compute_oks(j[1:], j[0], np.full(len(preds) - 1, 5000.0), recipes.COCO_DELTA, ground_truth=False, threshold=0.2)
+    # box NMS through the reference's own cpu_nms (nms.c compiled unmodified against oracle/ref_shims, `make -C oracle ref`)
+    from oracle import track_oracle
+    for n, seed, th in recipes.NMS_CASES:
+        k = track_oracle.ref_cpu_nms(recipes.nms_boxes(n, seed), th)
+        assert k is not None, "oracle/_ref/libref_nms.so missing: run `make -C oracle ref`"
+        extra["nms_keep_%d_%d_%g" % (n, seed, th)] = k
     path = os.path.join(HERE, "reference_track.npz")
     np.savez_compressed(path, crops_u8=crops, crops_f32=crops_f, centers=centers, scales=scales,
                         **{"swap_" + ds: v for ds, v in swapped.items()}, **extra)

@@ -70,3 +70,16 @@ def oks_poses(n=40, seed=12):
         preds.append({"score": float(1.0 - i * 0.011 + 0.003 * rng.random()), "joints": np.concatenate([xy, sc], 1).astype(np.float32),
                       "area": float(rng.uniform(3000, 9000))})
     return preds
+
+
+def nms_boxes(n, seed):
+    """n seeded person-like boxes with distinct scores (clusters of overlapping boxes)."""
+    rng = np.random.default_rng(seed)
+    centres = rng.uniform(40, 600, (max(1, n // 6), 2))
+    c = centres[rng.integers(0, len(centres), n)] + rng.normal(0, 12, (n, 2))
+    wh = rng.uniform(30, 160, (n, 2))
+    sc = (rng.permutation(n).astype(np.float32) + 1) / (n + 1)
+    return np.concatenate([c - wh / 2, c + wh / 2, sc[:, None]], axis=1).astype(np.float32)
+
+
+NMS_CASES = [(1, 0, 0.5), (17, 1, 0.3), (120, 2, 0.5), (300, 3, 0.7), (1000, 4, 0.3)]

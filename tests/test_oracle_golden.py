@@ -181,3 +181,21 @@ def test_oks_oracle_matches_reference_nms_oks():
     j = np.array([p["joints"] for p in preds])
     oks = track_oracle.compute_oks(j[1:], j[0], np.full(len(preds) - 1, 5000.0), recipes.COCO_DELTA, ground_truth=False, threshold=0.2)
     np.testing.assert_allclose(oks, g["oks_pairwise0"], rtol=1e-12, atol=0)
+
+
+def test_nms_oracle_matches_reference_cpu_nms():
+    """oracle.track_oracle.nms_cpu == the reference's own cpu_nms (nms.c compiled unmodified against oracle/ref_shims): against the
+    committed fixtures everywhere, and against the library itself where it was built (this container)."""
+    from oracle import track_oracle
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_track.npz"))
+    for n, seed, th in recipes.NMS_CASES:
+        dets = recipes.nms_boxes(n, seed)
+        mine = track_oracle.nms_cpu(dets, th, inclusive=True)
+        np.testing.assert_array_equal(mine, g["nms_keep_%d_%d_%g" % (n, seed, th)])
+        live = track_oracle.ref_cpu_nms(dets, th)
+        if live is not None:
+            np.testing.assert_array_equal(mine, live)
+    if track_oracle.ref_cpu_nms(recipes.nms_boxes(5, 9), 0.5) is not None:       # a few more thresholds / sizes against the live library
+        for n, seed, th in [(64, 11, 0.1), (257, 12, 0.45), (700, 13, 0.9)]:
+            dets = recipes.nms_boxes(n, seed)
+            np.testing.assert_array_equal(track_oracle.nms_cpu(dets, th), track_oracle.ref_cpu_nms(dets, th))
