@@ -29,7 +29,7 @@ KIND_CONV, KIND_DECONV = 0, 1
 PREC_SPLIT, PREC_FAST = 0, 1
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
 K_PACKED, K_TAP64, K_ROW = 0, 1, 2
-ABI_VERSION = 11        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
+ABI_VERSION = 12        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
 
 # name -> (restype, argtypes): every symbol include/flowtrack_b200.h declares
 SIGNATURES = {
@@ -38,6 +38,7 @@ SIGNATURES = {
     "ft_last_error": (ctypes.c_char_p, []),
     "ft_launch_count": (c_ll, []),
     "ft_reset_launch_count": (None, []),
+    "ft_set_debug": (c_int, [c_int, c_int]),
     "ft_correlation_shape": (c_int, [c_int] * 7 + [ctypes.POINTER(c_int)] * 3),
     "ft_correlation_forward": (c_int, [c_void_p] * 3 + [c_int] * 10 + [c_void_p]),
     "ft_correlation_tc_supported": (c_int, [c_int] * 8),
@@ -59,7 +60,7 @@ SIGNATURES = {
     "ft_fusion_concat": (c_int, [c_void_p] * 3 + [c_int] * 3 + [ctypes.POINTER(FtAct), c_void_p]),
     "ft_flow_head": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p]),
     "ft_flow_upsample": (c_int, [c_void_p] * 3 + [c_int] * 3 + [ctypes.POINTER(FtAct), c_void_p]),
-    "ft_decode_keypoints": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "ft_decode_keypoints": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "ft_crop_affine": (c_int, [c_void_p, c_int] + [c_ll] * 4 + [c_int] * 3 + [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_void_p]),
     "ft_flip_w": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "ft_flip_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -68,6 +69,7 @@ SIGNATURES = {
     "ft_box_propagation": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
+DEBUG_KNOBS = ("FT_DEV_SKIP", "FT_DEV_CHUNK", "FT_DEV_CORR_PARTS", "FT_DEV_CORR_VARIANT")     # ft_set_debug(which = index)
 _lib = None
 
 
@@ -85,6 +87,10 @@ def lib():
         if l.ft_abi_version() != ABI_VERSION or l.ft_sizeof(0) != ctypes.sizeof(FtAct) or l.ft_sizeof(1) != ctypes.sizeof(FtConvDesc):
             raise RuntimeError("libflowtrack_b200.so struct layout differs from the ctypes binding (stale build?)")
         _lib = l
+        # development knobs of tools/dev: forwarded once, explicitly; the library itself never reads the environment
+        for which, name in enumerate(DEBUG_KNOBS):
+            if os.environ.get(name):
+                l.ft_set_debug(which, int(os.environ[name]))
     return _lib
 
 

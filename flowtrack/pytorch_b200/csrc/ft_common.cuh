@@ -15,6 +15,32 @@ void count_launch(int n = 1);
 // Returns 0 if the last launch was accepted, else records the CUDA error and returns 1.
 int check_launch(const char* what);
 
+// ---- per-device state ------------------------------------------------------------------------------
+// One process may drive several GPUs (cudaSetDevice between calls): function attributes are per device, and so is
+// the SM count the persistent grids are sized with.
+constexpr int MAX_DEVICES = 64;
+int current_device();          // cudaGetDevice(), clamped into [0, MAX_DEVICES)
+int device_sms();              // cudaDevAttrMultiProcessorCount of the current device (cached per device)
+
+// Opt a kernel in to `bytes` of dynamic shared memory once per device.  `done` is a per-kernel flag array.
+template <typename F>
+inline int ensure_dyn_smem(F* func, int bytes, bool (&done)[MAX_DEVICES], const char* what) {
+    const int dev = current_device();
+    if (done[dev]) return 0;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        set_error("%s: cannot opt in to %d B of shared memory on device %d: %s", what, bytes, dev, cudaGetErrorString(e));
+        return 1;
+    }
+    done[dev] = true;
+    return 0;
+}
+
+// Development knobs (profiling experiments of tools/dev): set explicitly through ft_set_debug(), never read from the
+// environment by the library; all zero in production.
+enum { FT_DBG_SKIP = 0, FT_DBG_CHUNK = 1, FT_DBG_CORR_PARTS = 2, FT_DBG_CORR_VARIANT = 3, FT_DBG_COUNT = 8 };
+int dev_knob(int which);
+
 #define FT_REQUIRE(cond, ...)              \
     do {                                   \
         if (!(cond)) {                     \

@@ -570,16 +570,9 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvK p) {
 template <int BN, bool SPLIT, bool GATHER, bool PAIR>
 static int launch_tc(const ConvK& k, cudaStream_t s) {
     using G = Geo<BN, SPLIT, PAIR>;
-    static bool attr_set = false;   // per instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, GATHER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-        if (e != cudaSuccess) {
-            set_error("conv_tc_kernel<%d,%d,%d,%d>: cannot opt in to %d B of shared memory: %s", BN, (int)SPLIT, (int)GATHER, (int)PAIR, G::SMEM, cudaGetErrorString(e));
-            return 1;
-        }
-        attr_set = true;
-    }
-    const int sms = 148;
+    static bool attr_set[MAX_DEVICES];   // per instantiation and device
+    if (ensure_dyn_smem(conv_tc_kernel<BN, SPLIT, GATHER, PAIR>, G::SMEM, attr_set, "conv_tc_kernel")) return 1;
+    const int sms = device_sms();
     if (PAIR) {
         // one cluster of two CTAs (the two SMs of a TPC) per tile; k.num_tiles already counts pair tiles
         const int clusters = k.num_tiles < sms / 2 ? k.num_tiles : sms / 2;
@@ -683,7 +676,7 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     if (d->kind == FT_CONV) {
         FT_REQUIRE(d->kh > 0 && d->kw > 0 && d->kh * d->kw <= 64 && d->stride > 0 && d->pad >= 0, "conv2d: unsupported window %dx%d s%d p%d", d->kh, d->kw, d->stride, d->pad);
         k.n_phase = 1, k.taps = d->kh * d->kw;
-        const int pad_hi = d->pad_hi > 0 ? d->pad_hi : d->pad;
+        const int pad_hi = d->pad_hi >= 0 ? d->pad_hi : d->pad;
         FT_REQUIRE(pad_hi <= d->pad, "conv2d: pad_hi %d must not exceed pad %d", pad_hi, d->pad);
         k.Ho = (k.H + d->pad + pad_hi - d->kh) / d->stride + 1;
         k.Wo = (k.W + d->pad + pad_hi - d->kw) / d->stride + 1;
@@ -755,7 +748,7 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
         FT_REQUIRE(d->w_gemm, "conv2d: SIMT implementation needs w_gemm");
         const size_t total = (size_t)k.n_phase * k.M * k.cout_p8;
         size_t g = (total + 255) / 256;
-        if (g > 148 * 32) g = 148 * 32;
+        if (g > (size_t)device_sms() * 32) g = (size_t)device_sms() * 32;
         conv_simt_kernel<<<(int)g, 256, 0, s>>>(k);
         return check_launch("conv_simt_kernel");
     }
@@ -770,9 +763,8 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     FT_REQUIRE(d->res_blocks == res_blocks, "conv2d: the weight image carries %d residual k-blocks per tile, this call needs %d (residual %s, block_n %d)",
                d->res_blocks, res_blocks, d->res.hi ? "given" : "absent", BN);
     k.kb_total = k.kb_main + res_blocks;
-    if (const char* e = getenv("FT_DEV_SKIP")) k.dbg_skip = atoi(e);
-    int acc_chunk = ACC_CHUNK;
-    if (const char* e = getenv("FT_DEV_CHUNK")) acc_chunk = atoi(e) > 0 ? atoi(e) : ACC_CHUNK;   // dev knob (tools/dev/conv_bench.py)
+    k.dbg_skip = dev_knob(FT_DBG_SKIP);                                      // ft_set_debug(): 0 unless a tools/dev experiment set it
+    const int acc_chunk = dev_knob(FT_DBG_CHUNK) > 0 ? dev_knob(FT_DBG_CHUNK) : ACC_CHUNK;
     k.chunk = (split && k.kb_total > acc_chunk) ? acc_chunk : k.kb_total;   // k-blocks accumulated per TMEM stage (see the MMA warp)
     const int slab = BN >= 64 ? 32 : 16;
 

@@ -626,18 +626,12 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_pair_kernel(const __grid
 template <bool SPLIT>
 static int launch_corr_pair(const CorrK& k0, cudaStream_t s) {
     using G = CorrPairGeo<SPLIT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(corr_pair_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-        if (e != cudaSuccess) {
-            set_error("corr_pair_kernel<%d>: cannot opt in to %d B of shared memory: %s", (int)SPLIT, G::SMEM, cudaGetErrorString(e));
-            return 1;
-        }
-        attr_set = true;
-    }
+    static bool attr_set[MAX_DEVICES];
+    if (ensure_dyn_smem(corr_pair_kernel<SPLIT>, G::SMEM, attr_set, "corr_pair_kernel")) return 1;
     CorrK k = k0;
     k.num_units = k.B * 4 * ((k.a_tiles + 1) / 2) * k.parts;
-    const int clusters = k.num_units < 74 ? k.num_units : 74;
+    const int max_clusters = device_sms() / 2;
+    const int clusters = k.num_units < max_clusters ? k.num_units : max_clusters;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(CORR_THREADS), cfg.dynamicSmemBytes = G::SMEM, cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -663,7 +657,7 @@ static int launch_corr_pair(const CorrK& k0, cudaStream_t s) {
 // tcgen05.ld.
 // ------------------------------------------------------------------------------------------------
 // dev instrumentation (FT_DEV_SKIP bit 64): cycles each role spends waiting, per CTA: [role][slot]
-__device__ long long g_corr_prof[148][16];
+__device__ long long g_corr_prof[192][16];   // dev instrumentation, one row per persistent CTA
 #define MBAR_WAIT1(bar, par) do { if (p.dbg_skip & 32) mbar_wait(bar, par); else mbar_wait_spin(bar, par); } while (0)
 #define TIMED(slot, stmt) do { if (prof) { const long long t_ = clock64(); stmt; pw[slot] += clock64() - t_; } else { stmt; } } while (0)
 constexpr int C3_EPI_WARPS = 8;
@@ -896,16 +890,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) corr_tc3_kernel(const __grid_co
 template <bool SPLIT>
 static int launch_corr3(const CorrK& k, cudaStream_t s) {
     using G = Corr3Geo<SPLIT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(corr_tc3_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-        if (e != cudaSuccess) {
-            set_error("corr_tc3_kernel<%d>: cannot opt in to %d B of shared memory: %s", (int)SPLIT, G::SMEM, cudaGetErrorString(e));
-            return 1;
-        }
-        attr_set = true;
-    }
-    const int grid = k.num_units < 148 ? k.num_units : 148;
+    static bool attr_set[MAX_DEVICES];
+    if (ensure_dyn_smem(corr_tc3_kernel<SPLIT>, G::SMEM, attr_set, "corr_tc3_kernel")) return 1;
+    const int grid = k.num_units < device_sms() ? k.num_units : device_sms();
     corr_tc3_kernel<SPLIT><<<grid, C3_THREADS, G::SMEM, s>>>(k);
     return check_launch("corr_tc3_kernel");
 }
@@ -949,16 +936,9 @@ __global__ void __launch_bounds__(256) corr_planar_pack_kernel(const float* __re
 template <bool SPLIT>
 static int launch_corr(const CorrK& k, cudaStream_t s) {
     using G = CorrGeo<SPLIT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(corr_tc_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-        if (e != cudaSuccess) {
-            set_error("corr_tc_kernel<%d>: cannot opt in to %d B of shared memory: %s", (int)SPLIT, G::SMEM, cudaGetErrorString(e));
-            return 1;
-        }
-        attr_set = true;
-    }
-    const int grid = k.num_units < 148 ? k.num_units : 148;
+    static bool attr_set[MAX_DEVICES];
+    if (ensure_dyn_smem(corr_tc_kernel<SPLIT>, G::SMEM, attr_set, "corr_tc_kernel")) return 1;
+    const int grid = k.num_units < device_sms() ? k.num_units : device_sms();
     corr_tc_kernel<SPLIT><<<grid, CORR_THREADS, G::SMEM, s>>>(k);
     return check_launch("corr_tc_kernel");
 }
@@ -1001,7 +981,7 @@ static int correlation_act_impl(const ft_act* in1, const ft_act* in2, float* out
     CorrK k = {};
     k.out = out, k.B = in1->n, k.H = in1->h, k.W = in1->w, k.C = in1->c, k.kb = in1->c / CORR_BK;
     k.inv = 1.f / (float)k.C, k.leaky = fuse_leaky != 0, k.planar = planar;
-    if (const char* e = getenv("FT_DEV_SKIP")) k.dbg_skip = atoi(e);
+    k.dbg_skip = dev_knob(FT_DBG_SKIP);
     const int H2 = (k.H + 1) / 2;
     k.a_tiles = ceil_div(H2, CORR_ROWS);
     k.num_tiles = k.B * 4 * k.a_tiles;
@@ -1010,7 +990,7 @@ static int correlation_act_impl(const ft_act* in1, const ft_act* in2, float* out
     // [B,256,48,64], parts = 1/2/3/4/5/6: B=32 142/143/132/178/133/148 us, B=16 68/74/66/86/64/72, B=8 51/43/41/51/43/43
     // (parts sharing a factor with 148 pin the large parts to the same CTAs under the static round-robin order).
     k.parts = 3;
-    if (const char* e = getenv("FT_DEV_CORR_PARTS")) k.parts = atoi(e) >= 1 && atoi(e) <= 6 ? atoi(e) : 3;
+    if (const int v = dev_knob(FT_DBG_CORR_PARTS)) k.parts = v >= 1 && v <= 6 ? v : 3;
     k.num_units = k.num_tiles * k.parts;
     const int box[4] = {CORR_BK, CORR_COLS, CORR_ROWS, 1};
     for (int cls = 0; cls < 4; ++cls) {
@@ -1037,7 +1017,7 @@ static int correlation_act_impl(const ft_act* in1, const ft_act* in2, float* out
         }
     }
     int variant = 4;     // 4 = CTA pairs (default), 2 = single CTA with resident A, 3 = A operand in TMEM (experimental)
-    if (const char* e = getenv("FT_DEV_CORR_VARIANT")) variant = atoi(e);
+    if (const int v = dev_knob(FT_DBG_CORR_VARIANT)) variant = v;
     if (k.planar) variant = 4;
     if (variant == 4) return split ? launch_corr_pair<true>(k, (cudaStream_t)stream) : launch_corr_pair<false>(k, (cudaStream_t)stream);
     if (variant == 3) return split ? launch_corr3<true>(k, (cudaStream_t)stream) : launch_corr3<false>(k, (cudaStream_t)stream);
@@ -1083,7 +1063,8 @@ extern "C" int ft_pack_corr_planar(const float* planar, const ft_act* dst, void*
     ft_act d = *dst;
     const size_t total = (size_t)d.n * 4 * H2 * W2 * (d.c / 8);
     FT_REQUIRE((size_t)4 * H2 * W2 == (size_t)d.h * d.w, "pack_corr_planar: H and W must be even (got %d x %d)", d.h, d.w);
-    const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    const size_t cap = (size_t)device_sms() * 32;
+    const int grid = (int)((total + 255) / 256 < cap ? (total + 255) / 256 : cap);
     corr_planar_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(planar, d, H2, W2);
     return check_launch("corr_planar_pack_kernel");
 }

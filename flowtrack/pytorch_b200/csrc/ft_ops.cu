@@ -21,6 +21,24 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < MAX_DEVICES ? dev : MAX_DEVICES - 1;
+}
+int device_sms() {
+    static std::atomic<int> sms[MAX_DEVICES];
+    const int dev = current_device();
+    int v = sms[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;   // B200
+        sms[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+static std::atomic<int> g_knobs[FT_DBG_COUNT];
+int dev_knob(int which) { return (which >= 0 && which < FT_DBG_COUNT) ? g_knobs[which].load(std::memory_order_relaxed) : 0; }
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -516,7 +534,7 @@ __global__ void flow_upsample_kernel(const float* __restrict__ flow, const float
 // Decode (A9) and box propagation (A10)
 // =====================================================================================================
 __global__ void decode_kernel(const float* __restrict__ hm, int C, int h, int w, const float* __restrict__ center,
-                              const float* __restrict__ scale, int adjust, float* __restrict__ kps) {
+                              const float* __restrict__ scale, int adjust, float threshold, float* __restrict__ kps) {
     const int nc = blockIdx.x;  // n*C + c
     const int n = nc / C;
     const float* p = hm + (size_t)nc * h * w;
@@ -539,7 +557,7 @@ __global__ void decode_kernel(const float* __restrict__ hm, int C, int h, int w,
         for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
             if (sv[k] > best || (sv[k] == best && si[k] < bi)) best = sv[k], bi = si[k];
         float cx = (float)(bi % w), cy = (float)(bi / w);
-        if (!(best > 0.f)) cx = 0.f, cy = 0.f;                       // evaluation.py:18-19
+        if (!(best > threshold)) cx = 0.f, cy = 0.f;                 // evaluation.py:18-19
         if (adjust) {
             const int x = (int)cx, y = (int)cy;
             if (x > 0 && x < w - 1 && y > 0 && y < h - 1) {          // evaluation.py:31-33
@@ -593,7 +611,7 @@ __global__ void boxprop_kernel(const float* __restrict__ kps, const int32_t* __r
 
 static int grid_for(size_t total, int threads) {
     size_t g = (total + threads - 1) / threads;
-    const size_t cap = 148 * 16;   // a few resident CTAs per SM, grid-stride beyond that
+    const size_t cap = (size_t)device_sms() * 16;   // a few resident CTAs per SM, grid-stride beyond that
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -617,6 +635,11 @@ int ft_sizeof(int which) { return which == 0 ? (int)sizeof(ft_act) : (int)sizeof
 const char* ft_last_error(void) { return ft::g_err; }
 long long ft_launch_count(void) { return ft::g_launches.load(); }
 void ft_reset_launch_count(void) { ft::g_launches = 0; }
+int ft_set_debug(int which, int value) {
+    FT_REQUIRE(which >= 0 && which < ft::FT_DBG_COUNT, "set_debug: unknown knob %d", which);
+    ft::g_knobs[which].store(value);
+    return 0;
+}
 
 int ft_correlation_shape(int H, int W, int pad, int ksize, int max_disp, int stride1, int stride2, int* outC, int* outH, int* outW) {
     FT_REQUIRE(ksize >= 1 && (ksize & 1) && stride1 >= 1 && stride2 >= 1 && max_disp >= 0 && pad >= 0, "correlation: bad parameters");
@@ -744,9 +767,9 @@ int ft_flow_upsample(const float* flow, const float* w, const float* bias, int B
     return check_launch("flow_upsample_kernel");
 }
 
-int ft_decode_keypoints(const float* hm, int N, int C, int h, int w, const float* center, const float* scale, int adjust, float* kps, void* stream) {
+int ft_decode_keypoints(const float* hm, int N, int C, int h, int w, const float* center, const float* scale, int adjust, float threshold, float* kps, void* stream) {
     FT_REQUIRE(hm && center && scale && kps && N > 0 && C > 0 && h > 0 && w > 0, "decode_keypoints: bad arguments");
-    decode_kernel<<<N * C, 256, 0, (cudaStream_t)stream>>>(hm, C, h, w, center, scale, adjust, kps);
+    decode_kernel<<<N * C, 256, 0, (cudaStream_t)stream>>>(hm, C, h, w, center, scale, adjust, threshold, kps);
     return check_launch("decode_kernel");
 }
 

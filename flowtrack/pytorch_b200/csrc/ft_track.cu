@@ -281,15 +281,8 @@ extern "C" int ft_nms(const float* dets, const int32_t* counts, int frames, int 
     FT_REQUIRE(N >= 0 && N <= NMS_MAX, "nms: at most %d boxes per frame (got %d)", NMS_MAX, N);
     const int words = (N + 31) / 32;
     const int smem = (6 * NMS_MAX + (N > 0 ? N * words : 1)) * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (6 * NMS_MAX + NMS_MAX * NMS_WORDS) * 4);
-        if (e != cudaSuccess) {
-            set_error("nms_kernel: cannot opt in to shared memory: %s", cudaGetErrorString(e));
-            return 1;
-        }
-        attr_set = true;
-    }
+    static bool attr_set[MAX_DEVICES];
+    if (ensure_dyn_smem(nms_kernel, (6 * NMS_MAX + NMS_MAX * NMS_WORDS) * 4, attr_set, "nms_kernel")) return 1;
     nms_kernel<<<frames, 1024, smem, (cudaStream_t)stream>>>(dets, counts, N, thresh, inclusive != 0, keep, num_keep);
     return check_launch("nms_kernel");
 }
@@ -299,7 +292,7 @@ extern "C" int ft_flip_w(const float* src, float* dst, long long rows, int W, vo
     if (rows == 0) return 0;
     FT_REQUIRE(src && dst && src != dst, "flip_w: null pointer / in-place call");
     const long long total = rows * W;
-    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    const int grid = (int)((total + 255) / 256 < (long long)device_sms() * 16 ? (total + 255) / 256 : (long long)device_sms() * 16);
     flip_w_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, rows, W);
     return check_launch("flip_w_kernel");
 }
@@ -309,7 +302,7 @@ extern "C" int ft_flip_merge(const float* hm, const float* hm_flipped, const int
     if (N == 0) return 0;
     FT_REQUIRE(hm && hm_flipped && perm && out, "flip_merge: null pointer");
     const long long total = (long long)N * C * H * W;
-    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    const int grid = (int)((total + 255) / 256 < (long long)device_sms() * 16 ? (total + 255) / 256 : (long long)device_sms() * 16);
     flip_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(hm, hm_flipped, perm, N, C, H, W, out);
     return check_launch("flip_merge_kernel");
 }
@@ -320,15 +313,8 @@ extern "C" int ft_nms_oks(const float* joints, const float* scores, const float*
     FT_REQUIRE(N >= 0 && N <= NMS_MAX, "nms_oks: at most %d poses per frame (got %d)", NMS_MAX, N);
     const int words = (N + 31) / 32;
     const int smem = (2 * NMS_MAX + (N > 0 ? N * words : 1)) * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(nms_oks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * NMS_MAX + NMS_MAX * NMS_WORDS) * 4);
-        if (e != cudaSuccess) {
-            set_error("nms_oks_kernel: cannot opt in to shared memory: %s", cudaGetErrorString(e));
-            return 1;
-        }
-        attr_set = true;
-    }
+    static bool attr_set[MAX_DEVICES];
+    if (ensure_dyn_smem(nms_oks_kernel, (2 * NMS_MAX + NMS_MAX * NMS_WORDS) * 4, attr_set, "nms_oks_kernel")) return 1;
     nms_oks_kernel<<<frames, 1024, smem, (cudaStream_t)stream>>>(joints, scores, areas, delta, counts, N, K, oks_thresh, kpt_thresh, keep, num_keep);
     return check_launch("nms_oks_kernel");
 }

@@ -301,7 +301,7 @@ class ConvLayer:
         d.w_tile, d.w_gemm = self.tile_image(bn).data_ptr(), self.w_gemm.data_ptr()
         d.scale, d.shift = self.scale.data_ptr(), self.shift.data_ptr()
         d.kind, d.kh, d.kw, d.stride, d.pad = self.kind, self.kh, self.kw, self.stride, self.pad
-        d.pad_hi = self.pad_hi if self.pad_hi != self.pad else 0
+        d.pad_hi = self.pad_hi if self.pad_hi != self.pad else -1
         d.cout, d.cout_pad, d.k_pad, d.block_n = self.cout, self.cout_pad, self.k_pad, bn
         d.act, d.slope, d.precision, d.impl = self.act, self.slope, precision, impl
         d.k_mode, d.res_blocks, d.cta_pair = self.k_mode, (-(-bn // BK) if self.residual else 0), pair
@@ -456,40 +456,45 @@ class Plan:
         return dst
 
     def enqueue(self):
-        """Issue every call of the plan on the current stream (also what graph capture records)."""
-        s = stream_ptr()
-        for what, fn, args, _keep in self.calls:
-            _lib.check(fn(*args, s), what)
+        """Issue every call of the plan on the plan device's current stream (also what graph capture records).  The device
+        guard makes the launches land on the GPU that owns the plan's buffers whatever the caller's current device is."""
+        with torch.cuda.device(self.device):
+            s = stream_ptr()
+            for what, fn, args, _keep in self.calls:
+                _lib.check(fn(*args, s), what)
 
     def time_calls(self, reps=3):
         """Per-call device time in ms (CUDA events on the launching stream, averaged over `reps` un-graphed passes).
-        Event pairs around single launches include a few us of launch gap; bench.py uses this for the roofline."""
-        s = stream_ptr()
-        n = len(self.calls)
-        tot = [0.0] * n
-        for _ in range(reps):
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
-            ev[0].record()
-            for i, (what, fn, args, _keep) in enumerate(self.calls):
-                _lib.check(fn(*args, s), what)
-                ev[i + 1].record()
-            torch.cuda.synchronize()
-            for i in range(n):
-                tot[i] += ev[i].elapsed_time(ev[i + 1])
+        Event pairs around single launches include a few us of launch gap."""
+        with torch.cuda.device(self.device):
+            s = stream_ptr()
+            n = len(self.calls)
+            tot = [0.0] * n
+            for _ in range(reps):
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+                ev[0].record()
+                for i, (what, fn, args, _keep) in enumerate(self.calls):
+                    _lib.check(fn(*args, s), what)
+                    ev[i + 1].record()
+                torch.cuda.synchronize()
+                for i in range(n):
+                    tot[i] += ev[i].elapsed_time(ev[i + 1])
         return [t / reps for t in tot]
 
     def run(self):
         if self.graph is not None:
-            self.graph.replay()
+            with torch.cuda.device(self.device):
+                self.graph.replay()
             return
         self.enqueue()
 
     def capture(self):
         """Capture the call list into a CUDA graph (one launch per forward instead of one per layer)."""
-        self.run()                      # warm-up: sets function attributes, faults in code
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.enqueue()
-        self.graph = g
+        with torch.cuda.device(self.device):
+            self.run()                      # warm-up: sets function attributes, faults in code
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.enqueue()
+            self.graph = g
         return self

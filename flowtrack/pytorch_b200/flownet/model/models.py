@@ -87,12 +87,13 @@ class _FlowBase(nn.Module):
         if inputs.dim() != 5 or inputs.shape[1] != 3 or inputs.shape[2] != 2 or inputs.shape[3] % 64 or inputs.shape[4] % 64:
             raise ValueError("expected [B,3,2,H,W] with H, W multiples of 64, got %s" % (tuple(inputs.shape),))
         B, _, _, H, W = inputs.shape
-        p, pair, out = self.plan_for(B, H, W, inputs.device)
-        pair.copy_(inputs)
-        if self.use_cuda_graph and p.graph is None and not torch.cuda.is_current_stream_capturing():
-            p.capture()
-        p.run()
-        return out.clone()
+        with torch.cuda.device(inputs.device):                        # launches follow the tensor's device, not the caller's current one
+            p, pair, out = self.plan_for(B, H, W, inputs.device)
+            pair.copy_(inputs)
+            if self.use_cuda_graph and p.graph is None and not torch.cuda.is_current_stream_capturing():
+                p.capture()
+            p.run()
+            return out.clone()
 
 
 # ---- plan fragments ---------------------------------------------------------------------------------

@@ -17,6 +17,7 @@ class ChannelNorm(Module):
         if not x.is_cuda or x.dtype != torch.float32:
             raise RuntimeError("ChannelNorm needs a CUDA float32 input (no CPU path)")
         b, c, h, w = x.shape
-        out = torch.empty(b, 1, h, w, device=x.device, dtype=torch.float32)
-        _lib.check(_lib.lib().ft_channelnorm_forward(x.data_ptr(), out.data_ptr(), b, c, h, w, engine.stream_ptr()), "channelnorm")
+        with torch.cuda.device(x.device):
+            out = torch.empty(b, 1, h, w, device=x.device, dtype=torch.float32)
+            _lib.check(_lib.lib().ft_channelnorm_forward(x.data_ptr(), out.data_ptr(), b, c, h, w, engine.stream_ptr()), "channelnorm")
         return out

@@ -26,19 +26,20 @@ class Correlation(Module):
             raise RuntimeError("Correlation needs contiguous CUDA float32 inputs (no CPU path)")
         assert input1.shape == input2.shape
         B, C, H, W = input1.shape
-        oc, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
-        L = _lib.lib()
-        _lib.check(L.ft_correlation_shape(H, W, self.pad_size, self.kernel_size, self.max_displacement, self.stride1, self.stride2,
-                                          ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow)), "correlation_shape")
-        out = torch.empty(B, oc.value, oh.value, ow.value, device=input1.device, dtype=torch.float32)
-        geom = (self.pad_size, self.kernel_size, self.max_displacement, self.stride1, self.stride2)
-        if L.ft_correlation_tc_supported(C, H, W, *geom):
-            need = L.ft_correlation_workspace_bytes(B, C, H, W)
-            if self._ws is None or self._ws.numel() < need or self._ws.device != input1.device:
-                self._ws = torch.empty(need, dtype=torch.uint8, device=input1.device)
-            _lib.check(L.ft_correlation_forward_ws(input1.data_ptr(), input2.data_ptr(), out.data_ptr(), B, C, H, W, *geom, int(fuse_leaky),
-                                                   self.precision, self._ws.data_ptr(), self._ws.numel(), engine.stream_ptr()), "correlation")
-        else:
-            _lib.check(L.ft_correlation_forward(input1.data_ptr(), input2.data_ptr(), out.data_ptr(), B, C, H, W, *geom, int(fuse_leaky),
-                                                engine.stream_ptr()), "correlation")
+        with torch.cuda.device(input1.device):
+            oc, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            L = _lib.lib()
+            _lib.check(L.ft_correlation_shape(H, W, self.pad_size, self.kernel_size, self.max_displacement, self.stride1, self.stride2,
+                                              ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow)), "correlation_shape")
+            out = torch.empty(B, oc.value, oh.value, ow.value, device=input1.device, dtype=torch.float32)
+            geom = (self.pad_size, self.kernel_size, self.max_displacement, self.stride1, self.stride2)
+            if L.ft_correlation_tc_supported(C, H, W, *geom):
+                need = L.ft_correlation_workspace_bytes(B, C, H, W)
+                if self._ws is None or self._ws.numel() < need or self._ws.device != input1.device:
+                    self._ws = torch.empty(need, dtype=torch.uint8, device=input1.device)
+                _lib.check(L.ft_correlation_forward_ws(input1.data_ptr(), input2.data_ptr(), out.data_ptr(), B, C, H, W, *geom, int(fuse_leaky),
+                                                       self.precision, self._ws.data_ptr(), self._ws.numel(), engine.stream_ptr()), "correlation")
+            else:
+                _lib.check(L.ft_correlation_forward(input1.data_ptr(), input2.data_ptr(), out.data_ptr(), B, C, H, W, *geom, int(fuse_leaky),
+                                                    engine.stream_ptr()), "correlation")
         return out

@@ -22,6 +22,7 @@ class Resample2d(Module):
         _, d, _, _ = input1_c.size()
         b, two, h, w = input2.size()
         assert two == 2 and input1_c.shape[0] == b and input1_c.shape[2:] == (h, w)
-        out = torch.empty(b, d, h, w, device=input1.device, dtype=torch.float32)
-        _lib.check(_lib.lib().ft_resample2d_forward(input1_c.data_ptr(), input2.data_ptr(), out.data_ptr(), b, d, h, w, engine.stream_ptr()), "resample2d")
+        with torch.cuda.device(input1_c.device):
+            out = torch.empty(b, d, h, w, device=input1.device, dtype=torch.float32)
+            _lib.check(_lib.lib().ft_resample2d_forward(input1_c.data_ptr(), input2.data_ptr(), out.data_ptr(), b, d, h, w, engine.stream_ptr()), "resample2d")
         return out

@@ -181,12 +181,15 @@ class DeconvResnet(nn.Module):
 
     @torch.no_grad()
     def forward(self, x):
-        plan, src, out = self._plan(x)
-        src.copy_(x)
-        if self.use_cuda_graph and plan.graph is None and not torch.cuda.is_current_stream_capturing():
-            plan.capture()
-        plan.run()
-        return out.clone()
+        if not x.is_cuda:
+            raise RuntimeError("DeconvResnet.forward needs a CUDA tensor: this package has no CPU path")
+        with torch.cuda.device(x.device):                             # launches follow the tensor's device, not the caller's current one
+            plan, src, out = self._plan(x)
+            src.copy_(x)
+            if self.use_cuda_graph and plan.graph is None and not torch.cuda.is_current_stream_capturing():
+                plan.capture()
+            plan.run()
+            return out.clone()
 
 
 def deconv(backbone, num_classes, pretrained):

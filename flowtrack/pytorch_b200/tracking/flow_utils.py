@@ -22,12 +22,13 @@ def box_propagation_cuda(keypoints, flow, frame_of=None, out=None):
     assert keypoints.dtype == torch.float32 and flow.dtype == torch.float32 and keypoints.is_contiguous() and flow.is_contiguous()
     N, K, _ = keypoints.shape
     B, _, H, W = flow.shape
-    if out is None:
-        out = torch.empty(N, 4, device=keypoints.device, dtype=torch.float32)
-    if N == 0:
-        return out
-    _lib.check(_lib.lib().ft_box_propagation(keypoints.data_ptr(), frame_of.data_ptr() if frame_of is not None else None, N, K,
-                                             flow.data_ptr(), B, H, W, out.data_ptr(), engine.stream_ptr()), "box_propagation")
+    with torch.cuda.device(keypoints.device):
+        if out is None:
+            out = torch.empty(N, 4, device=keypoints.device, dtype=torch.float32)
+        if N == 0:
+            return out
+        _lib.check(_lib.lib().ft_box_propagation(keypoints.data_ptr(), frame_of.data_ptr() if frame_of is not None else None, N, K,
+                                                 flow.data_ptr(), B, H, W, out.data_ptr(), engine.stream_ptr()), "box_propagation")
     return out
 
 

@@ -43,15 +43,17 @@ def boxes_to_center_scale(boxes, inp_res=(256, 192)):
     return centers, scales
 
 
-def final_preds_cuda(heatmaps, centers, scales, adjust_coords=True, out=None):
+def final_preds_cuda(heatmaps, centers, scales, adjust_coords=True, out=None, threshold=0.0):
     """max_preds + final_preds + transform_preds (lib/pose/utils/evaluation.py:11-35) in one kernel.
-    heatmaps: CUDA fp32 [N,C,h,w]; centers [N,2], scales [N] CUDA fp32 -> CUDA fp32 [N,C,3] = (x, y, score)."""
+    heatmaps: CUDA fp32 [N,C,h,w]; centers [N,2], scales [N] CUDA fp32 -> CUDA fp32 [N,C,3] = (x, y, score).
+    `threshold` is max_preds' argument (:11,18): heat-map coordinates are zeroed unless score > threshold."""
     assert heatmaps.is_cuda and heatmaps.dtype == torch.float32 and heatmaps.is_contiguous()
     N, C, h, w = heatmaps.shape
-    if out is None:
-        out = torch.empty(N, C, 3, device=heatmaps.device, dtype=torch.float32)
-    _lib.check(_lib.lib().ft_decode_keypoints(heatmaps.data_ptr(), N, C, h, w, centers.data_ptr(), scales.data_ptr(), int(bool(adjust_coords)),
-                                              out.data_ptr(), engine.stream_ptr()), "decode_keypoints")
+    with torch.cuda.device(heatmaps.device):
+        if out is None:
+            out = torch.empty(N, C, 3, device=heatmaps.device, dtype=torch.float32)
+        _lib.check(_lib.lib().ft_decode_keypoints(heatmaps.data_ptr(), N, C, h, w, centers.data_ptr(), scales.data_ptr(), int(bool(adjust_coords)),
+                                                  float(threshold), out.data_ptr(), engine.stream_ptr()), "decode_keypoints")
     return out
 
 
@@ -70,11 +72,12 @@ def crop_boxes_cuda(frames, centers, scales, frame_of=None, inp_res=(256, 192), 
         F_, C, H, W = frames.shape
         sn, sc, sh, sw = frames.stride()
     N = centers.shape[0]
-    if out is None:
-        out = torch.empty(N, C, inp_res[0], inp_res[1], device=frames.device, dtype=torch.float32)
-    _lib.check(_lib.lib().ft_crop_affine(frames.data_ptr(), int(is_u8), sn, sc, sh, sw, H, W, C, centers.data_ptr(), scales.data_ptr(),
-                                         frame_of.data_ptr() if frame_of is not None else None, N, inp_res[0], inp_res[1],
-                                         int(bool(reverse_channels)), out.data_ptr(), engine.stream_ptr()), "crop_affine")
+    with torch.cuda.device(frames.device):
+        if out is None:
+            out = torch.empty(N, C, inp_res[0], inp_res[1], device=frames.device, dtype=torch.float32)
+        _lib.check(_lib.lib().ft_crop_affine(frames.data_ptr(), int(is_u8), sn, sc, sh, sw, H, W, C, centers.data_ptr(), scales.data_ptr(),
+                                             frame_of.data_ptr() if frame_of is not None else None, N, inp_res[0], inp_res[1],
+                                             int(bool(reverse_channels)), out.data_ptr(), engine.stream_ptr()), "crop_affine")
     return out
 
 
@@ -85,10 +88,11 @@ def nms_cuda(dets, thresh, counts=None, inclusive=True):
         raise RuntimeError("nms_cuda needs CUDA tensors (no CPU path)")
     assert dets.dtype == torch.float32 and dets.is_contiguous() and dets.dim() == 3 and dets.shape[2] == 5
     F_, N, _ = dets.shape
-    keep = torch.empty(F_, N, dtype=torch.int32, device=dets.device)
-    num = torch.empty(F_, dtype=torch.int32, device=dets.device)
-    _lib.check(_lib.lib().ft_nms(dets.data_ptr(), counts.data_ptr() if counts is not None else None, F_, N, float(thresh), int(bool(inclusive)),
-                                 keep.data_ptr(), num.data_ptr(), engine.stream_ptr()), "nms")
+    with torch.cuda.device(dets.device):
+        keep = torch.empty(F_, N, dtype=torch.int32, device=dets.device)
+        num = torch.empty(F_, dtype=torch.int32, device=dets.device)
+        _lib.check(_lib.lib().ft_nms(dets.data_ptr(), counts.data_ptr() if counts is not None else None, F_, N, float(thresh), int(bool(inclusive)),
+                                     keep.data_ptr(), num.data_ptr(), engine.stream_ptr()), "nms")
     return keep, num
 
 
@@ -125,9 +129,9 @@ def detect(net, im, person_id, thresh=0.3, prop_dets=None):
 @torch.no_grad()
 def pose_est(net, im, boxes, inp_res=(256, 192), max_batch=32, flip_test=False):
     """im: HxWx3 ndarray (BGR, as loaded by cv2); boxes: ndarray [N,4] -> keypoints ndarray [N, num_kpts, 3].
-    The frame is uploaded once; crops, network and decode run on the GPU."""
-    if flip_test:
-        raise NotImplementedError("flip_test is not on the hot path (the reference accepts the flag and ignores it, net_utils.py:36)")
+    The frame is uploaded once; crops, network and decode run on the GPU.  The reference accepts `flip_test` and ignores
+    it (net_utils.py:36); here flip_test=True runs the flip test of tools/pose/main.py:289-299 (mirrored crops in the same
+    batch, left/right joints swapped back, heat-maps averaged) through evaluation.flip_test_forward."""
     boxes = np.asarray(boxes)
     n = boxes.shape[0]
     if n == 0:
@@ -144,7 +148,11 @@ def pose_est(net, im, boxes, inp_res=(256, 192), max_batch=32, flip_test=False):
     for s in range(0, n, max_batch):
         e = min(n, s + max_batch)
         crops = crop_boxes_cuda(frame, c_all[s:e].contiguous(), s_all[s:e].contiguous(), None, inp_res)
-        hm = net(crops)
+        if flip_test:
+            from ..pose.utils.evaluation import flip_test_forward
+            hm = flip_test_forward(net, crops)
+        else:
+            hm = net(crops)
         outs.append(final_preds_cuda(hm, c_all[s:e].contiguous(), s_all[s:e].contiguous(), True))
     return torch.cat(outs).cpu().numpy()
 

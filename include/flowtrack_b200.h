@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 11
+#define FT_ABI_VERSION 12
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -111,8 +111,8 @@ typedef struct {
                                Block j holds diag(f) for channels [64j, 64j+64) of the tile, where
                                f[c] = 1/scale[c] must be a power of two (the host folds BatchNorm's
                                scale into the weights of such layers), so acc += res * f exactly.   */
-    int32_t pad_hi;         /* zero padding after the last row / column; 0 = same as `pad`.  The space-to-depth form of a 7x7
-                               stride-2 stem is a 4x4 stride-1 convolution padded 2 before and 1 after.                */
+    int32_t pad_hi;         /* zero padding after the last row / column (<= pad); -1 = same as `pad`.  The space-to-depth form
+                               of a 7x7 stride-2 stem is a 4x4 stride-1 convolution padded 2 before and 1 after.       */
     int32_t tile_order;     /* 0: the persistent CTAs walk the output tiles first image -> last image, 1: last -> first.
                                A layer that runs in the opposite order of its producer starts on the part of its
                                input that is still in the 126 MB L2 (engine.py alternates the order along a plan). */
@@ -125,6 +125,10 @@ const char* ft_last_error(void);
 /* Number of kernels this library has launched since load / since the last reset (bench accounting). */
 long long   ft_launch_count(void);
 void        ft_reset_launch_count(void);
+/* Development knobs for the profiling experiments under tools/dev (0 = skip mask of the conv / correlation kernels,
+ * 1 = accumulation chunk, 2 = correlation parts, 3 = correlation kernel variant).  All zero by default; the library
+ * never reads the environment.  Results under a non-zero skip mask are garbage by design.                          */
+int         ft_set_debug(int which, int value);
 
 /* ---- the three native ops of the reference (contiguous NCHW fp32, as there) --------------------- */
 int ft_correlation_shape(int H, int W, int pad, int ksize, int max_disp, int stride1, int stride2,
@@ -207,9 +211,11 @@ int ft_flow_upsample(const float* flow, const float* w, const float* bias, int B
 
 /* ---- decode -------------------------------------------------------------------------------------- */
 /* hm: [N,C,h,w] fp32; center: [N,2], scale: [N] fp32 -> kps: [N,C,3] = (x, y, score) in image
- * coordinates (max_preds + optional quarter-pixel shift + inverse crop transform).                   */
+ * coordinates (max_preds + optional quarter-pixel shift + inverse crop transform).  `threshold` is
+ * max_preds' argument (evaluation.py:11,18-19): heat-map coordinates are zeroed unless score > threshold
+ * (final_preds always passes 0).                                                                     */
 int ft_decode_keypoints(const float* hm, int N, int C, int h, int w, const float* center,
-                        const float* scale, int adjust, float* kps, void* stream);
+                        const float* scale, int adjust, float threshold, float* kps, void* stream);
 /* kps: [N,K,3] previous-frame key-points; frame_of: [N] int32 index of each person's frame pair;
  * flow: [B,2,H,W] -> boxes: [N,4] (x0,y0,x1,y1).  Key-point pixels are clamped into the flow field
  * before the look-up (the reference indexes unclamped, lib/tracking/flow_utils.py:23-24).             */

@@ -6,6 +6,17 @@ import torch
 from flowtrack.pytorch_b200 import _lib, engine
 
 
+# The parity bar, stated once (BASELINE.json north_star): every test, smoke() and bench.py's `parity`
+# key hold the CUDA path to these numbers against the oracle / the reference fixtures.
+HEATMAP_TOL = 1e-3      # max-abs on heat-maps (conditioned weights: heat-map abs-max ~4)
+FLOW_TOL = 1e-3         # max-abs on flows, relative to max(1, max|flow|) px -- every FlowNet2 variant
+KEYPOINT_TOL_PX = 1.0   # decoded key-points / propagated boxes
+
+
+def flow_tol(ref):
+    return FLOW_TOL * max(1.0, float(ref.abs().max()))
+
+
 def sp():
     return engine.stream_ptr()
 
