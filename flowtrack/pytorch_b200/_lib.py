@@ -66,6 +66,7 @@ SIGNATURES = {
     "ft_flip_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ft_nms_oks": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "ft_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "ft_flow_to_image": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ft_box_propagation": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

@@ -258,9 +258,84 @@ __global__ void flip_merge_kernel(const float* __restrict__ hm, const float* __r
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Middlebury flow colour coding (flow_to_image / compute_color / make_color_wheel, lib/flownet/utils/flowlib.py:243-282,
+// 430-521) -- the visualisation step after the flow forward (tools/flownet/demo.py:92-99).  Arithmetic follows numpy's
+// promotion on the reference's expressions for a float32 flow: radius and its per-image maximum in float32 (separately
+// rounded multiply / add / sqrt), everything after the normalisation in double.
+// ------------------------------------------------------------------------------------------------
+constexpr float FLOWVIS_UNKNOWN = 1e7f;
+
+__global__ void flowvis_max_kernel(const float* __restrict__ flow, int HW, uint32_t* __restrict__ maxrad_bits) {
+    const int b = blockIdx.y;
+    const float* u = flow + (size_t)b * 2 * HW;
+    const float* v = u + HW;
+    float m = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        float uu = u[i], vv = v[i];
+        if (fabsf(uu) > FLOWVIS_UNKNOWN || fabsf(vv) > FLOWVIS_UNKNOWN) uu = 0.f, vv = 0.f;
+        const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(uu, uu), __fmul_rn(vv, vv)));
+        if (r > m) m = r;                                      // NaN compares false, as in np.max over a NaN-free field
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(maxrad_bits + b, __float_as_uint(m));   // non-negative floats order like their bit patterns
+}
+
+// make_color_wheel (flowlib.py:474-521): RY 15, YG 6, GC 4, CB 11, BM 13, MR 6 = 55 colours, ramps floor(255*i/n)
+__constant__ uint8_t c_flow_wheel[55][3] = {{255,0,0}, {255,17,0}, {255,34,0}, {255,51,0}, {255,68,0}, {255,85,0}, {255,102,0}, {255,119,0}, {255,136,0}, {255,153,0}, {255,170,0}, {255,187,0}, {255,204,0}, {255,221,0}, {255,238,0}, {255,255,0}, {213,255,0}, {170,255,0}, {128,255,0}, {85,255,0}, {43,255,0}, {0,255,0}, {0,255,63}, {0,255,127}, {0,255,191}, {0,255,255}, {0,232,255}, {0,209,255}, {0,186,255}, {0,163,255}, {0,140,255}, {0,116,255}, {0,93,255}, {0,70,255}, {0,47,255}, {0,24,255}, {0,0,255}, {19,0,255}, {39,0,255}, {58,0,255}, {78,0,255}, {98,0,255}, {117,0,255}, {137,0,255}, {156,0,255}, {176,0,255}, {196,0,255}, {215,0,255}, {235,0,255}, {255,0,255}, {255,0,213}, {255,0,170}, {255,0,128}, {255,0,85}, {255,0,43}};
+
+__global__ void flowvis_color_kernel(const float* __restrict__ flow, int HW, const uint32_t* __restrict__ maxrad_bits, uint8_t* __restrict__ img) {
+    const int b = blockIdx.y;
+    const float* u = flow + (size_t)b * 2 * HW;
+    const float* v = u + HW;
+    const double denom = (double)__uint_as_float(maxrad_bits[b]) + 2.220446049250313e-16;      // maxrad + np.finfo(float).eps
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        float uu = u[i], vv = v[i];
+        uint8_t* o = img + ((size_t)b * HW + i) * 3;
+        const bool unknown = fabsf(uu) > FLOWVIS_UNKNOWN || fabsf(vv) > FLOWVIS_UNKNOWN;
+        if (unknown || isnan(uu) || isnan(vv)) {
+            o[0] = o[1] = o[2] = 0;
+            continue;
+        }
+        const double un = (double)uu / denom, vn = (double)vv / denom;
+        const double rad = sqrt(un * un + vn * vn);
+        const double a = atan2(-vn, -un) / 3.141592653589793;
+        const double fk = (a + 1.0) / 2.0 * 54.0 + 1.0;
+        const int k0 = (int)floor(fk);
+        int k1 = k0 + 1;
+        if (k1 == 56) k1 = 1;
+        const double f = fk - (double)k0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double c0 = (double)c_flow_wheel[k0 - 1][c] / 255.0, c1 = (double)c_flow_wheel[k1 - 1][c] / 255.0;
+            double col = (1.0 - f) * c0 + f * c1;
+            col = rad <= 1.0 ? 1.0 - rad * (1.0 - col) : col * 0.75;
+            o[c] = (uint8_t)floor(255.0 * col);
+        }
+    }
+}
+
 }  // namespace ft
 
 using namespace ft;
+
+extern "C" int ft_flow_to_image(const float* flow, int B, int H, int W, void* maxrad_ws, uint8_t* img, void* stream) {
+    FT_REQUIRE(B >= 0 && H > 0 && W > 0, "flow_to_image: bad shape");
+    if (B == 0) return 0;
+    FT_REQUIRE(flow && maxrad_ws && img, "flow_to_image: null pointer");
+    FT_REQUIRE(B <= 65535, "flow_to_image: at most 65535 flows per call");
+    const int HW = H * W;
+    if (cudaMemsetAsync(maxrad_ws, 0, sizeof(uint32_t) * B, (cudaStream_t)stream) != cudaSuccess) {
+        set_error("flow_to_image: memset of the workspace failed");
+        return 1;
+    }
+    const int bx = min(ceil_div(HW, 256), device_sms() * 4);
+    flowvis_max_kernel<<<dim3(bx, B), 256, 0, (cudaStream_t)stream>>>(flow, HW, (uint32_t*)maxrad_ws);
+    if (check_launch("flowvis_max_kernel")) return 1;
+    flowvis_color_kernel<<<dim3(bx, B), 256, 0, (cudaStream_t)stream>>>(flow, HW, (const uint32_t*)maxrad_ws, img);
+    return check_launch("flowvis_color_kernel");
+}
 
 extern "C" int ft_crop_affine(const void* frames, int is_u8, long long sn, long long sc, long long sh, long long sw, int H, int W, int C,
                               const float* centers, const float* scales, const int32_t* frame_of, int N, int out_h, int out_w, int reverse_channels,

@@ -45,3 +45,29 @@ def writeFlow(filename, uv, v=None):
         np.array(width).astype(np.int32).tofile(f)
         np.array(height).astype(np.int32).tofile(f)
         np.stack((u, v), axis=2).astype(np.float32).tofile(f)
+
+
+def flow_to_image_cuda(flow):
+    """Middlebury colour coding on the GPU (ft_flow_to_image; flowlib.flow_to_image, lib/flownet/utils/flowlib.py:243-282).
+    flow: CUDA fp32 [B,2,H,W] or [2,H,W] (the networks' output) -> CUDA uint8 [B,H,W,3] / [H,W,3] RGB."""
+    import torch
+
+    from ... import _lib, engine
+    if not flow.is_cuda:
+        raise RuntimeError("flow_to_image_cuda needs a CUDA tensor (no CPU path)")
+    single = flow.dim() == 3
+    f = (flow.unsqueeze(0) if single else flow).contiguous().float()
+    B, two, H, W = f.shape
+    assert two == 2
+    with torch.cuda.device(f.device):
+        img = torch.empty(B, H, W, 3, dtype=torch.uint8, device=f.device)
+        ws = torch.empty(max(B, 1), dtype=torch.int32, device=f.device)
+        _lib.check(_lib.lib().ft_flow_to_image(f.data_ptr(), B, H, W, ws.data_ptr(), img.data_ptr(), engine.stream_ptr()), "flow_to_image")
+    return img[0] if single else img
+
+
+def flow_to_image(flow):
+    """flowlib.flow_to_image signature: flow ndarray [H,W,2] -> uint8 ndarray [H,W,3] (computed on the GPU)."""
+    import torch
+    f = torch.as_tensor(np.ascontiguousarray(np.asarray(flow, dtype=np.float32).transpose(2, 0, 1))).cuda()
+    return flow_to_image_cuda(f).cpu().numpy()

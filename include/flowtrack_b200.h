@@ -31,6 +31,7 @@
  *   ft_crop_affine           transform_image (cv2.warpAffine) per person box         lib/tracking/net_utils.py:48-57, lib/pose/utils/transforms.py:231-240
  *   ft_flip_w / ft_flip_merge  flip test: np.flip + swaplr_image + average                  tools/pose/main.py:289-299, lib/pose/utils/transforms.py:140-170
  *   ft_nms_oks               nms_oks + compute_oks                                   lib/pose/utils/evaluation.py:60-101
+ *   ft_flow_to_image         flowlib.flow_to_image (Middlebury colour coding)         lib/flownet/utils/flowlib.py:243-282,430-521 (tools/flownet/demo.py:93)
  *   ft_nms                   pth_nms / cpu_nms / nms_kernel                          lib/detection/nms/pth_nms.py:5-46, src/nms.c:36-62, src/cuda/nms_kernel.cu:13-70
  */
 #ifndef FLOWTRACK_B200_H_
@@ -254,6 +255,12 @@ int ft_nms(const float* dets, const int32_t* counts, int frames, int N, float th
 int ft_nms_oks(const float* joints, const float* scores, const float* areas, const float* delta, const int32_t* counts,
                int frames, int N, int K, float oks_thresh, float kpt_thresh, int32_t* keep, int32_t* num_keep,
                void* stream);
+
+/* Middlebury colour coding of flow fields (flowlib.flow_to_image, lib/flownet/utils/flowlib.py:243-282 with compute_color
+ * :430-471 and make_color_wheel :474-521; tools/flownet/demo.py:93).  flow [B,2,H,W] fp32 (the networks' output layout)
+ * -> img [B,H,W,3] uint8 RGB, each flow normalised by its own largest radius; entries with |u| or |v| > 1e7 are "unknown"
+ * and painted black.  maxrad_ws: B x 4 bytes of scratch (cleared by a memset node, then two kernels).                 */
+int ft_flow_to_image(const float* flow, int B, int H, int W, void* maxrad_ws, uint8_t* img, void* stream);
 
 #ifdef __cplusplus
 }

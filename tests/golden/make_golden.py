@@ -166,8 +166,32 @@ def make_track(ref_tf, ref_eval=None):
     print("wrote", path, os.path.getsize(path) // 1024, "KiB", crops.shape, crops.dtype)
 
 
+def make_flowvis():
+    """Middlebury colour coding through the reference's own flowlib.flow_to_image (lib/flownet/utils/flowlib.py:243-282;
+    its matplotlib / pypng imports are display-only and stubbed) -> reference_flowvis.npz."""
+    import importlib.util
+    import types
+    for name in ("png", "matplotlib", "matplotlib.colors", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    spec = importlib.util.spec_from_file_location("ref_flowlib", os.path.join(REF, "lib", "flownet", "utils", "flowlib.py"))
+    flowlib = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(flowlib)
+    out = {}
+    for i, flow in enumerate(recipes.flowvis_flows()):
+        out["flowvis_img%d" % i] = flowlib.flow_to_image(flow.copy())
+        print("flowvis", i, flow.shape, out["flowvis_img%d" % i].shape, out["flowvis_img%d" % i].dtype)
+    out["flowvis_wheel"] = flowlib.make_color_wheel()
+    path = os.path.join(HERE, "reference_flowvis.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 def main():
     out = {}
+    if "--flowvis-only" in sys.argv:
+        make_flowvis()
+        return
+    make_flowvis()
     ref_pose, ref_eval, ref_tf = import_reference_pose()
     if "--track-only" in sys.argv:
         make_track(ref_tf, ref_eval)

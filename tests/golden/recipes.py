@@ -83,3 +83,17 @@ def nms_boxes(n, seed):
 
 
 NMS_CASES = [(1, 0, 0.5), (17, 1, 0.3), (120, 2, 0.5), (300, 3, 0.7), (1000, 4, 0.3)]
+
+
+def flowvis_flows():
+    """Seeded [H,W,2] float32 flows for the colour-coding fixtures: smooth rotation field + noise (every wheel sector),
+    a small-magnitude field, and one with unknown (> 1e7), zero and NaN-free extreme entries."""
+    rng = np.random.default_rng(21)
+    yy, xx = np.mgrid[0:48, 0:64].astype(np.float32)
+    rot = np.stack([(yy - 24) * 0.7, -(xx - 32) * 0.5], axis=2) + rng.normal(0, 0.3, (48, 64, 2)).astype(np.float32)
+    small = rng.normal(0, 0.01, (16, 24, 2)).astype(np.float32)
+    mixed = rng.normal(0, 12.0, (32, 40, 2)).astype(np.float32)
+    mixed[3, 4] = (2e7, 1.0)
+    mixed[5, 6] = (0.0, -3e8)
+    mixed[8:12, 10:14] = 0.0
+    return [rot.astype(np.float32), small, mixed]

@@ -254,3 +254,52 @@ def test_bad_arguments_raise():
     bad.ld = 12
     with pytest.raises(RuntimeError, match="multiples of 8"):
         _lib.check(L().ft_maxpool3x3s2(bad, a.struct(), None), "maxpool")
+
+
+def test_resample2d_and_channelnorm_vs_reference_kernels():
+    """ft_resample2d_forward / ft_channelnorm_forward against the reference's OWN __global__ kernels
+    (Resample2d_kernel.cu:20-66, ChannelNorm_kernel.cu:19-51), compiled unmodified into oracle/_ref/libref_warp.so."""
+    from oracle import ref_gpu
+    if ref_gpu.warp_lib() is None:
+        pytest.skip("oracle/_ref/libref_warp.so not built (needs /root/reference at build time)")
+    g = torch.Generator().manual_seed(13)
+    B, H, W = 2, 384, 512                                                         # FlowNet2's full-resolution warps
+    img, flow = (torch.rand(B, 3, H, W, generator=g) * 255).cuda(), (torch.randn(B, 2, H, W, generator=g) * 12).cuda()
+    flow[0, :, :3] = -700.0                                                       # clamp-to-edge on both sides
+    flow[1, :, -3:] = 900.0
+    want = ref_gpu.resample2d(img, flow)
+    out = torch.empty_like(img)
+    _lib.check(L().ft_resample2d_forward(img.data_ptr(), flow.data_ptr(), out.data_ptr(), B, 3, H, W, gpu_util.sp()), "resample")
+    # the reference forms its four weights in double and accumulates in float; this kernel keeps float weights: <= a few ulp of 255
+    err = (out - want).abs().max().item()
+    assert err <= 255 * 4e-7, err
+    for C in (2, 3):
+        x = (torch.randn(B, C, H, W, generator=g) * 5).cuda()
+        want = ref_gpu.channelnorm(x)
+        n = torch.empty(B, 1, H, W, device="cuda")
+        _lib.check(L().ft_channelnorm_forward(x.data_ptr(), n.data_ptr(), B, C, H, W, gpu_util.sp()), "cnorm")
+        assert (n - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+
+
+def test_flow_to_image_matches_reference_flowlib():
+    """ft_flow_to_image vs fixtures made by the reference's own flowlib.flow_to_image (tests/golden/reference_flowvis.npz) and
+    vs the numpy oracle on a full-size flow.  Double-precision atan2 on the GPU may differ from libm by an ulp, which can move a
+    colour byte across a floor() boundary: <= 1 LSB, on < 0.1 % of the bytes."""
+    import numpy as np
+    from flowtrack.pytorch_b200.flownet.utils import flow_utils
+    from oracle import flowvis_oracle
+    from tests.golden import recipes
+    fix = np.load(os.path.join(ROOT, "tests", "golden", "reference_flowvis.npz"))
+    for i, flow in enumerate(recipes.flowvis_flows()):
+        got = flow_utils.flow_to_image(flow)
+        want = fix["flowvis_img%d" % i]
+        diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert got.shape == want.shape and got.dtype == np.uint8
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (i, diff.max(), (diff > 0).mean())
+    g = torch.Generator().manual_seed(4)
+    f = torch.randn(3, 2, 384, 512, generator=g) * torch.tensor([1.0, 20.0, 0.01]).view(3, 1, 1, 1)
+    got = flow_utils.flow_to_image_cuda(f.cuda()).cpu().numpy()
+    for b in range(3):
+        want = flowvis_oracle.flow_to_image(f[b].permute(1, 2, 0).numpy())
+        diff = np.abs(got[b].astype(np.int32) - want.astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3

@@ -199,3 +199,13 @@ def test_nms_oracle_matches_reference_cpu_nms():
         for n, seed, th in [(64, 11, 0.1), (257, 12, 0.45), (700, 13, 0.9)]:
             dets = recipes.nms_boxes(n, seed)
             np.testing.assert_array_equal(track_oracle.nms_cpu(dets, th), track_oracle.ref_cpu_nms(dets, th))
+
+
+def test_flowvis_oracle_matches_reference_flowlib():
+    """oracle/flowvis_oracle.py == the reference's own flowlib.flow_to_image / make_color_wheel (fixtures by make_golden.py)."""
+    import os
+    from oracle import flowvis_oracle
+    fix = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_flowvis.npz"))
+    assert np.array_equal(flowvis_oracle.make_color_wheel(), fix["flowvis_wheel"])
+    for i, flow in enumerate(recipes.flowvis_flows()):
+        assert np.array_equal(flowvis_oracle.flow_to_image(flow), fix["flowvis_img%d" % i])
