@@ -1,21 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- frame-pairs/sec of the FlowTrack per-frame-pair hot path (pose + flow + box propagation) on B200.
+"""bench.py -- frame-pairs/sec of the FlowTrack per-frame-pair hot path (pose + flow + warp) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (one JSON line on rank 0)
-    python bench.py --impl reference [--gpus N] --steps K --warmup W   # the reference's CPU path on the host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path (one JSON line on rank 0)
+    python bench.py --impl reference [--gpus N] --steps K --warmup W    # the reference's CPU path on the host cores
+    python bench.py --config 5 ...                                      # BASELINE config 5 (PoseResNet-152 384x288 + full FlowNet2)
 
-N > 1 is launched by torchrun (one rank per GPU, NCCL); every rank runs the same per-GPU workload on its own shard of
-frame pairs (weak scaling) and the only collective is the all-gather of the per-person key-point records.
+N > 1 is launched by torchrun (one rank per GPU, NCCL).  Frame pairs (videos) are independent, so they are sharded over the
+ranks and the only collective is the all-gather of the per-person key-point records.  The headline line is weak scaling
+(every GPU runs the N=1 workload on its own 16 pairs); at N > 1 the same run also measures strong scaling -- BASELINE
+config 4's fixed batch of 16 frame pairs split over the N GPUs -- and reports it under `strong_scaling`.
 
-Workload (BASELINE.json config 4, P = 4 people per frame as fixed by SURVEY.md 8d): per GPU and step, 16 frame pairs
-= FlowNet2S on [16,3,2,384,512] + PoseResNet-50 on the 64 person crops [64,3,256,192] + heat-map decode + flow
-look-up box propagation, synthetic inputs, random-init weights.  A "step" is one such batch.
+Workload (BASELINE.json config 4, P = 4 people per frame as fixed by SURVEY.md 8d): per GPU and step 16 frame pairs through
+the tracker's serial chain (tools/tracking/demo.py:35-42): FlowNet2S on [16,3,2,384,512] -> box propagation of the previous
+key-points -> NMS -> 64 person crops [64,3,256,192] cut at the propagated boxes -> PoseResNet-50 -> heat-map decode; synthetic
+uint8 frames, random-init weights.  Inside a step the pose crops depend on the flow; across steps the flow network of step
+t+1 overlaps the pose tail of step t (tracking/tracker.py).
 
-Keys beyond the base contract: `roofline` (dominant kernel = the tcgen05 implicit-GEMM convolution: algorithmic
-FLOPs of all its launches in a step / their summed CUDA-event durations, against the measured dense bf16 GEMM
-peak), `kernels` (the same for the other kernels on the path incl. the FlowNetC correlation at BASELINE config 3),
-`cpu_baseline` (the oracle port of the reference path on the host cores, bounded sample), `e2e` (host buffers in,
-host results out, through FramePairPipeline.submit()/collect(), two batches in flight).
+Keys beyond the base contract: `roofline` (dominant kernel = the tcgen05 implicit-GEMM convolution: algorithmic FLOPs of all
+its launches in a step / their summed durations measured with CUDA events inside a graph replay, against the measured dense
+bf16 GEMM peak), `kernels` (the other kernels of the path, the FlowNetC correlation at BASELINE config 3, and `reference_gpu`:
+the reference modules under cuDNN and the reference correlation kernel on this same GPU), `parity` (one step of the timed
+workload against the CPU oracle), `cpu_baseline`, `e2e` (uint8 host frames in, host results out, two steps in flight).
 """
 import argparse
 import json
@@ -34,8 +39,14 @@ sys.path.insert(0, ROOT)
 METRIC = "frame-pairs/sec (pose+flow+warp) at 256x192/384x512"
 UNIT = "frame-pairs/s"
 PAIRS, PEOPLE = 16, 4
-FRAME_HW, CROP_HW = (384, 512), (256, 192)
-GFLOP_PER_PAIR = 31.58 + PEOPLE * 10.853          # FlowNet2S pair + 4 x R50 crop
+FRAME_HW = (384, 512)
+CONFIGS = {
+    # name -> (pose depth, crop hw, flow class, default pairs per GPU, algorithmic GFLOP per pair)
+    4: dict(depth=50, crop_hw=(256, 192), flow="FlowNet2S", pairs=16, gflop=31.58 + PEOPLE * 10.853,
+            name="config4 joint pipeline (PoseResNet-50 256x192 + FlowNet2S 384x512)"),
+    5: dict(depth=152, crop_hw=(384, 288), flow="FlowNet2", pairs=1, gflop=198.24 + 0.694 + PEOPLE * 57.147,
+            name="config5 joint pipeline (PoseResNet-152 384x288 + full FlowNet2 384x512)"),
+}
 
 
 def load_peaks():
@@ -95,23 +106,63 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------------
-# CPU side: the oracle port of the reference path (reference arm and cpu_baseline)
+# synthetic workload (shared by both arms)
 # --------------------------------------------------------------------------------------------------------
-def cpu_reference_runner(pairs_per_step):
-    """Returns (step_fn, cores, description).  step_fn() runs `pairs_per_step` frame pairs of the reference path on the
-    host: FlowNet2S forward, box propagation, PoseResNet-50 forward on P crops per pair, final_preds -- the reference's
-    own PyTorch CPU kernels through the oracle's restated modules (oracle/{pose,flow,decode}_oracle.py)."""
+def synthetic_video(streams, steps, seed):
+    """uint8 BGR frames [streams, steps+1, H, W, 3]: a random texture drifting a few pixels per frame."""
+    rng = np.random.default_rng(seed)
+    H, W = FRAME_HW
+    out = np.empty((streams, steps + 1, H, W, 3), np.uint8)
+    for f in range(streams):
+        base = rng.integers(0, 255, (H + 2 * steps + 2, W + 3 * steps + 3, 3), dtype=np.uint8)
+        for t in range(steps + 1):
+            out[f, t] = base[2 * t:2 * t + H, 3 * t:3 * t + W]
+    return out
+
+
+def initial_state(streams, crop_hw, seed):
+    """PEOPLE boxes per stream on a grid (96x192 px) with key-points inside them -- the tracker's state before the first step."""
+    from flowtrack.pytorch_b200.tracking import synthetic
+    d = synthetic.frame_pair_batch(streams, PEOPLE, FRAME_HW, crop_hw, seed=seed)
+    dets = np.concatenate([d["boxes"].numpy().reshape(streams, PEOPLE, 4), np.linspace(0.95, 0.6, streams * PEOPLE, dtype=np.float32).reshape(streams, PEOPLE, 1)],
+                          axis=2)
+    return dets, np.full(streams, PEOPLE, np.int32), d["prev_keypoints"].numpy()
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU side: the reference path on the host cores (reference arm and cpu_baseline)
+# --------------------------------------------------------------------------------------------------------
+def cpu_reference_runner(cfg, pairs_per_step):
+    """Returns (step_fn, cores, kind, description).  step_fn() runs `pairs_per_step` frame pairs of the reference's serial
+    chain on the host (tools/tracking/demo.py:35-42): flow net, box propagation, NMS, person crops (cv2.warpAffine), pose
+    net, final_preds.  The networks are the UNMODIFIED reference nn.Modules staged under baseline/_ref when present
+    (kind "reference"; oracle/ref_loader.py), else the oracle's restated modules (kind "port"); the glue functions are the
+    oracle restatements either way (the reference's own are broken under torch 2.11 / numpy 2)."""
     import torch
     from flowtrack.pytorch_b200.tracking import synthetic
-    from oracle import decode_oracle, flow_oracle, pose_oracle, track_oracle
+    from oracle import decode_oracle, flow_oracle, pose_oracle, ref_loader, track_oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    pose = pose_oracle.deconv("resnet50", 17, False).eval()
-    synthetic.condition_pose_weights(pose, 0)
-    flow = flow_oracle.FlowNet2S(None).eval()
-    d = synthetic.frame_pair_batch(pairs_per_step, PEOPLE, FRAME_HW, CROP_HW, seed=1)
-    boxes_np = d["boxes"].numpy()
+    o_pose = synthetic.condition_pose_weights(pose_oracle.deconv("resnet%d" % cfg["depth"], 17, False), 0).eval()
+    o_flow = getattr(flow_oracle, cfg["flow"])(None).eval()
+    kind = "port"
+    pose, flow = o_pose, o_flow
+    if ref_loader.available():
+        try:
+            pose = ref_loader.pose_models().deconv("resnet%d" % cfg["depth"], 17, False).eval()
+            pose.load_state_dict(o_pose.state_dict(), strict=True)
+            flow = getattr(ref_loader.flow_models("oracle"), cfg["flow"])(ref_loader.Args()).eval()
+            flow.load_state_dict(o_flow.state_dict(), strict=True)
+            kind = "reference"
+        except Exception as e:                                   # pragma: no cover - falls back to the port, and says so
+            sys.stderr.write("reference modules unavailable (%s): timing the oracle port\n" % e)
+            pose, flow = o_pose, o_flow
+    crop_hw = cfg["crop_hw"]
+    video = synthetic_video(pairs_per_step, 1, seed=1)
+    dets, count, kps = initial_state(pairs_per_step, crop_hw, seed=1)
+    kps = kps.reshape(pairs_per_step, PEOPLE, 17, 3)
+    pair = np.ascontiguousarray(np.stack([video[:, 0, :, :, ::-1], video[:, 1, :, :, ::-1]], axis=1).transpose(0, 4, 1, 2, 3).astype(np.float32))
     try:
         import cv2  # noqa: F401
         have_cv2 = True
@@ -119,18 +170,26 @@ def cpu_reference_runner(pairs_per_step):
         have_cv2 = False
 
     def step():
+        with torch.set_grad_enabled(cfg["flow"] == "FlowNet2" and kind == "reference"):     # the reference FlowNet2.forward registers hooks
+            fl = flow(torch.from_numpy(pair)).detach().numpy()
+        cur, crops = [], []
+        for f in range(pairs_per_step):
+            prop = decode_oracle.box_propagation(kps[f], fl[f], clamp=True)
+            cand = np.concatenate((prop, dets[f, :, 4:5]), axis=1).astype(np.float32)
+            d = cand[track_oracle.nms_cpu(cand, 0.3)][:PEOPLE]
+            cur.append(d)
+            crops.append(track_oracle.crop_boxes(np.ascontiguousarray(video[f, 1]), d[:, :4], crop_hw, use_cv2=have_cv2))
+        allc = np.concatenate(crops)
         with torch.no_grad():
-            fl = flow(d["pair"]).numpy()
-            boxes = [decode_oracle.box_propagation(d["prev_keypoints"][i * PEOPLE:(i + 1) * PEOPLE].numpy(), fl[i]) for i in range(pairs_per_step)]
-            # pose_est's crop loop (net_utils.py:52-57): one warpAffine per person box out of the pair's current frame (BGR)
-            frames = d["pair"][:, :, 1].permute(0, 2, 3, 1).numpy()[:, :, :, ::-1]
-            crops = np.concatenate([track_oracle.crop_boxes(np.ascontiguousarray(frames[i]), boxes_np[i * PEOPLE:(i + 1) * PEOPLE], CROP_HW, use_cv2=have_cv2)
-                                    for i in range(pairs_per_step)])
-            hm = pose(torch.from_numpy(crops)).numpy()
-            kps, sc = decode_oracle.final_preds(hm, d["centers"].numpy(), d["scales"].numpy(), True)
-        return kps, sc, boxes
+            hm = pose(torch.from_numpy(allc)).numpy()
+        boxes = np.concatenate(cur)
+        centers, scales = track_oracle.boxes_to_center_scale(boxes[:, :4], crop_hw)
+        return decode_oracle.final_preds(hm, centers, scales, True)
 
-    return step, cores, "oracle port (torch CPU fp32, %d threads): FlowNet2S 384x512 + %d PoseResNet-50 crops 256x192 + decode + box propagation per pair" % (cores, PEOPLE)
+    what = ("%s nn.Modules (torch CPU fp32, %d threads): %s on %d pair(s) + box propagation + NMS + %d PoseResNet-%d crops %dx%d + final_preds per step"
+            % ("unmodified reference" if kind == "reference" else "oracle-port", cores, cfg["flow"], pairs_per_step, pairs_per_step * PEOPLE, cfg["depth"],
+               crop_hw[0], crop_hw[1]))
+    return step, cores, kind, what
 
 
 def time_cpu(step, pairs_per_step, steps, warmup):
@@ -143,45 +202,65 @@ def time_cpu(step, pairs_per_step, steps, warmup):
     return pairs_per_step * steps / dt, dt / steps * 1e3
 
 
+def workload_config(cfg, world, pairs_per_gpu, scaling="weak"):
+    return {"workload": "%s: per GPU and step %d frame pairs through the tracker's serial chain -- %s [%d,3,2,%d,%d] from uint8 frames -> box propagation -> NMS -> "
+                        "%d person crops [%d,3,%d,%d] cut at the propagated boxes (P=%d people/frame) -> PoseResNet-%d -> heat-map decode; flow(t+1) overlaps the pose tail of step t"
+                        % (cfg["name"], pairs_per_gpu, cfg["flow"], pairs_per_gpu, FRAME_HW[0], FRAME_HW[1], pairs_per_gpu * PEOPLE, pairs_per_gpu * PEOPLE,
+                           cfg["crop_hw"][0], cfg["crop_hw"][1], PEOPLE, cfg["depth"]),
+            "pairs_per_gpu": pairs_per_gpu, "people_per_frame": PEOPLE, "global_pairs": pairs_per_gpu * world, "scaling_mode": scaling,
+            "parallelism": "frame pairs sharded over %d GPU(s), one all-gather of key-point records per step" % world,
+            "l2": "no explicit flush: a step streams ~19 MB of uint8 frames and several GB of activations, far beyond the 126 MB L2",
+            "weights": "random-init (reference init + conditioned BatchNorm/head, seed 0)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    pps = 1
-    step, cores, desc = cpu_reference_runner(pps)
+    cfg = CONFIGS[args.config]
+    pps = min(4, cfg["pairs"])                                   # CPU rates at flow B=4 / pose B=16 (batch-insensitive beyond that)
+    step, cores, kind, what = cpu_reference_runner(cfg, pps)
     value, ms = time_cpu(step, pps, args.steps, args.warmup)
-    sample = "%d frame pair(s) per step (1 FlowNet2S pair + %d R50 crops + decode + box propagation), %d timed steps" % (pps, PEOPLE, args.steps)
+    sample = "%d frame pair(s) per step (a %d/%d sample of the GPU arm's per-step batch), %d timed steps after %d warm-up" % (pps, pps, cfg["pairs"], args.steps, args.warmup)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(1, pps), "gpu_launches": 0,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "what": desc},
+        "config": workload_config(cfg, 1, cfg["pairs"]), "gpu_launches": 0,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "what": what},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
-
-
-def workload_config(world, pairs_per_gpu):
-    return {"workload": "config4 joint pipeline: per GPU and step %d frame pairs = FlowNet2S [%d,3,2,%d,%d] + PoseResNet-50 on %d crops [%d,3,%d,%d] "
-                        "(P=%d people/frame, crops cut from the current frame by the warpAffine rule of pose_est) + heat-map decode + flow box propagation" % (pairs_per_gpu, pairs_per_gpu, FRAME_HW[0], FRAME_HW[1],
-                                                                                           pairs_per_gpu * PEOPLE, pairs_per_gpu * PEOPLE, CROP_HW[0], CROP_HW[1], PEOPLE),
-            "pairs_per_gpu": pairs_per_gpu, "people_per_frame": PEOPLE, "global_pairs": pairs_per_gpu * world,
-            "parallelism": "frame pairs sharded over %d GPU(s), one all-gather of key-point records per step" % world,
-            "l2": "no explicit flush: a step streams ~75 MB of inputs and several GB of activations, far beyond the 126 MB L2",
-            "weights": "random-init (reference init + conditioned BatchNorm/head, seed 0)"}
 
 
 # --------------------------------------------------------------------------------------------------------
 # GPU side
 # --------------------------------------------------------------------------------------------------------
+def build_pipeline(cfg, pairs, dev, precision, seed):
+    import torch
+    from flowtrack.pytorch_b200.flownet.model import models as flow_models
+    from flowtrack.pytorch_b200.pose import models as pose_models
+    from flowtrack.pytorch_b200.tracking import synthetic
+    from flowtrack.pytorch_b200.tracking import tracker as tk
+    torch.manual_seed(0)
+    pose = synthetic.condition_pose_weights(pose_models.deconv("resnet%d" % cfg["depth"], 17, False), 0).cuda()
+    flow = getattr(flow_models, cfg["flow"])(None).cuda()
+    pose.precision = flow.precision = precision
+    pipe = tk.TrackingPipeline(pose, flow, pairs, PEOPLE, FRAME_HW, cfg["crop_hw"], dev)
+    video = synthetic_video(pairs, len(pipe.lanes), seed=seed)               # one frame pair per lane: (t, t+1)
+    state = initial_state(pairs, cfg["crop_hw"], seed=seed)
+    pipe.seed(*state)
+    for l in range(len(pipe.lanes)):
+        pipe.collect(pipe.submit(pipe.stage(torch.from_numpy(np.ascontiguousarray(video[:, l:l + 2])), lane=l)))      # fills pinned + device buffers, captures
+    pipe.seed(*state)
+    return pipe, pose, flow, video, state
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from flowtrack.pytorch_b200 import _lib
-    from flowtrack.pytorch_b200.flownet.model import models as flow_models
-    from flowtrack.pytorch_b200.pose import models as pose_models
     from flowtrack.pytorch_b200.tracking import pipeline as pl
-    from flowtrack.pytorch_b200.tracking import synthetic
 
+    cfg = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -205,40 +284,44 @@ def run_ours(args):
             os.close(saved)
     _lib.lib()                                           # fail loudly if the CUDA library is missing
 
-    torch.manual_seed(0)
-    pose = synthetic.condition_pose_weights(pose_models.deconv("resnet50", 17, False), 0).cuda()
-    flow = flow_models.FlowNet2S(None).cuda()
-    pose.precision = flow.precision = args.precision
-    pipe = pl.FramePairPipeline(pose, flow, args.pairs, PEOPLE, FRAME_HW, CROP_HW, dev, crops_from_frames=not args.host_crops)
-    data = synthetic.frame_pair_batch(args.pairs, PEOPLE, FRAME_HW, CROP_HW, seed=100 + rank)
-    pipe.process(data["pair"], data["crops"], data["centers"], data["scales"], data["prev_keypoints"])   # fills static + pinned buffers, captures
+    pairs = args.pairs if args.pairs else cfg["pairs"]
+    if args.scaling == "strong":                         # a fixed global batch split over the ranks
+        lo, hi = pl.shard_pairs(pairs, rank, world)
+        pairs_local, total_pairs = hi - lo, pairs
+    else:
+        pairs_local, total_pairs = pairs, pairs * world
+    if pairs_local == 0:
+        raise SystemExit("strong scaling: %d global pairs cannot feed %d ranks" % (pairs, world))
+    pipe, pose, flow, video, state = build_pipeline(cfg, pairs_local, dev, args.precision, seed=100 + rank)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_step():
-        pipe.step_device()
-        return pl.gather_keypoints(pipe.keypoints), pl.gather_keypoints(pipe.boxes)
+    def make_steps(p):
+        def device_step():
+            p.step_device()
+            with torch.cuda.stream(p.s_tail):            # the collective follows the tail that produced the records
+                return pl.gather_keypoints(p.keypoints), pl.gather_keypoints(p.dets)
+        pending = []
 
-    pending = []
+        def host_step():
+            # pipelined host API: submit this step (pinned uint8 frames -> device on the copy stream, flow graph, tail graph, results ->
+            # pinned host), then collect the previous step: every step's copies are inside the timed region
+            pending.append(p.submit())
+            with torch.cuda.stream(p.s_tail):
+                out = (pl.gather_keypoints(p.keypoints), pl.gather_keypoints(p.dets))
+            if len(pending) > 1:
+                p.collect(pending.pop(0))
+            return out
 
-    def host_step():
-        # pipelined host API: submit this step's batch (pinned host -> device on the copy stream, graph replay, results ->
-        # pinned host), then collect the previous step's results -- every step's copies are inside the timed region, the
-        # copy-in of step i+1 overlaps the kernels of step i.  The all-gather runs on the device-resident records.
-        pending.append(pipe.submit())
-        out = (pl.gather_keypoints(pipe.keypoints), pl.gather_keypoints(pipe.boxes))
-        if len(pending) > 1:
-            pipe.collect(pending.pop(0))
-        return out
+        def host_drain():
+            while pending:
+                p.collect(pending.pop(0))
+        return device_step, host_step, host_drain
 
-    def host_drain():
-        while pending:
-            pipe.collect(pending.pop(0))
-
-    def timed(fn, steps, warmup, drain=None):
+    def timed(p, fn, steps, warmup, drain=None):
         for _ in range(warmup):
             fn()
         if drain:
@@ -246,10 +329,12 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        p.fence_in()                                     # the pipeline's streams start after e0 ...
         for _ in range(steps):
             fn()
         if drain:
             drain()                                      # the last step's results are on the host before the clock stops
+        p.fence_out()                                    # ... and e1 waits for all of them
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -257,7 +342,8 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item() / steps                          # ms per step, max over ranks
 
-    # clocks: nvidia-smi needs ~0.1-0.3 s before its first sample and the timed region of 20 steps is < 0.1 s long, so the sampler
+    device_step, host_step, host_drain = make_steps(pipe)
+    # clocks: nvidia-smi needs ~0.1-0.3 s before its first sample and a timed region of 20 steps is < 0.1 s long, so the sampler
     # starts first, the same device step runs untimed until samples are flowing (pre-roll, identical load), and it keeps sampling
     # through the timed device steps and the timed e2e steps
     sampler = ClockSampler(local) if rank == 0 else None
@@ -266,73 +352,235 @@ def run_ours(args):
         for _ in range(10):
             pipe.step_device()
         torch.cuda.synchronize()
-    ms = timed(device_step, args.steps, args.warmup)
-    pipe.stage(data["pair"], data["crops"], data["centers"], data["scales"], data["prev_keypoints"], slot=1)   # slot 0 was staged by process()
-    ms_e2e = timed(host_step, args.steps, max(1, args.warmup // 2), drain=host_drain)
+    ms = timed(pipe, device_step, args.steps, args.warmup)
+    ms_e2e = timed(pipe, host_step, args.steps, max(1, args.warmup // 2), drain=host_drain)
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
         clocks["window"] = "%.1f s untimed pre-roll of the same device step + the timed device steps + the timed e2e steps (20 ms sampling)" % args.preroll
-    total_pairs = args.pairs * world
+
+    strong = None
+    if world > 1 and args.scaling == "weak" and not args.no_strong:
+        # strong scaling of BASELINE config 4: the fixed global batch (one GPU's share at N=1) split over the ranks
+        g_pairs = cfg["pairs"] if not args.pairs else args.pairs
+        lo, hi = pl.shard_pairs(g_pairs, rank, world)
+        if all(pl.shard_pairs(g_pairs, r, world)[1] > pl.shard_pairs(g_pairs, r, world)[0] for r in range(world)):
+            sp, _, _, _, _ = build_pipeline(cfg, hi - lo, dev, args.precision, seed=200 + rank)
+            s_dev, s_host, s_drain = make_steps(sp)
+            s_ms = timed(sp, s_dev, args.steps, args.warmup)
+            s_e2e = timed(sp, s_host, args.steps, max(1, args.warmup // 2), drain=s_drain)
+            strong = {"scaling": "strong", "global_pairs": g_pairs, "pairs_per_gpu": hi - lo, "value": g_pairs / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms,
+                      "e2e_value": g_pairs / (s_e2e * 1e-3), "e2e_ms_per_step": s_e2e,
+                      "note": "the N=1 batch of %d frame pairs split over %d GPUs (contiguous blocks), same pipeline and all-gather" % (g_pairs, world)}
+            del sp
+            torch.cuda.empty_cache()
 
     out = None
     if rank == 0:
         peaks = load_peaks()
-        # ---- per-kernel timing: un-graphed pass, CUDA-event pair around every launch ---------------------
         kern = {}
-        conv_ms, conv_flops, other = 0.0, 0.0, {}
-        for plan in (pipe.pose_plan, pipe.flow_plan):
-            per = plan.time_calls(reps=3)
+        # ---- per-kernel timing: CUDA-event pairs between the launches of a graph replay of each plan ---------------------
+        conv_ms, conv_flops, other, n_conv = 0.0, 0.0, {}, 0
+        for plan in (pipe.pose_plan, pipe.lanes[0].flow_plan):
+            try:
+                per, how = plan.time_calls_graphed(reps=5), "CUDA events (cudaEventRecordExternal) between the launches inside a CUDA-graph replay of each network's plan"
+            except Exception as e:                        # pragma: no cover
+                per, how = plan.time_calls(reps=3), "un-graphed CUDA-event pairs (graph timing unavailable: %s)" % e
             for i, (what, _fn, _a, _k) in enumerate(plan.calls):
                 if what == "conv2d":
                     conv_ms += per[i]
                     conv_flops += plan.flops[i]
+                    n_conv += 1
                 else:
                     other[what] = other.get(what, 0.0) + per[i]
-        n_conv = sum(1 for plan in (pipe.pose_plan, pipe.flow_plan) for c in plan.calls if c[0] == "conv2d")
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
-        traffic, ncu_note = None, None
-        try:     # DRAM bytes per conv launch from the committed ncu --set full capture of the same plans (not measured in this run)
-            with open(os.path.join(ROOT, "profiles", "r01j_conv_traffic.json")) as f:
-                tr = json.load(f)
-            traffic = tr["dram_bytes_per_launch"]
-            ncu_note = {"tensor_pipe_active_pct_time_weighted": tr["tensor_pipe_active_pct_time_weighted"], "source": tr["source"]}
-        except Exception:
-            pass
+        traffic, ncu_note = read_traffic_capture(_lib)
         roof = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv/deconv, %d launches per step)" % n_conv, "bound": "tensor",
                 "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": traffic,
                 "traffic_unit": "DRAM bytes (read+write) per launch, averaged over the conv launches of a step", "ncu": ncu_note,
                 "algorithmic_flop_per_launch": conv_flops / n_conv, "ms_per_launch": conv_ms / n_conv,
                 "algorithmic_gflop_per_step": conv_flops / 1e9, "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / ms,
+                "timing": how + "; share_of_step can exceed the serial share because flow(t+1) and the pose tail of step t overlap in the timed loop",
                 "executed_over_algorithmic": 3.0 if args.precision == "split" else 1.0,
                 "peak_source": peaks["source"] + ", sustained dense bf16 GEMM"}
         kern["other_kernels_ms_per_step"] = other
-        kern["correlation"] = bench_correlation(torch, _lib, peaks)
+        if not args.no_kernels:
+            kern["correlation"] = bench_correlation(torch, _lib, peaks)
+        if not args.no_reference_gpu and world == 1:
+            try:
+                kern["reference_gpu"] = bench_reference_gpu(torch, cfg)
+            except Exception as e:                        # informational leg: never fails the line
+                kern["reference_gpu"] = {"unavailable": repr(e)}
+        parity = None
+        if not args.no_parity:
+            parity = parity_check(torch, cfg, pipe, pose, flow, video, state)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            pps = 1
-            step, cores, desc = cpu_reference_runner(pps)
+            pps = min(4, cfg["pairs"])
+            step, cores, kind, what = cpu_reference_runner(cfg, pps)
             v, _ = time_cpu(step, pps, args.cpu_steps, 1)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "%d timed steps of %d frame pair (1 FlowNet2S pair + %d R50 crops + decode + box propagation) after 1 warm-up" % (args.cpu_steps, pps, PEOPLE),
-                   "what": desc}
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": "%d timed steps of %d frame pairs (a %d/%d sample of one GPU step) after 1 warm-up" % (args.cpu_steps, pps, pps, cfg["pairs"]), "what": what}
         out = {
             "metric": METRIC, "value": total_pairs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "fp32-grade (fp16 hi/lo split operands, 3 tcgen05 MMAs per product, fp32 accumulate)" if args.precision == "split" else "fp16 operands, fp32 accumulate",
-            "data": "synthetic", "config": workload_config(world, args.pairs),
-            "gflop_per_pair": GFLOP_PER_PAIR, "algorithmic_tflops": total_pairs * GFLOP_PER_PAIR / ms,
+            "data": "synthetic", "config": workload_config(cfg, world, pairs_local, args.scaling),
+            "gflop_per_pair": cfg["gflop"], "algorithmic_tflops": total_pairs * cfg["gflop"] / ms,
             "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-                    "api": "FramePairPipeline.submit()/collect(): per step pinned host buffers -> device (copy stream), CUDA-graph replay, results -> pinned host; "
-                           "two slots in flight so the copy-in of step i+1 overlaps the kernels of step i"},
+                    "api": "TrackingPipeline.submit()/collect(): per step the pinned uint8 frame pairs [pairs,2,384,512,3] -> device (copy stream), flow graph + tail graph, "
+                           "boxes/key-points -> pinned host; two steps in flight so copy-in and flow of step t+1 overlap the pose tail of step t; the caller fills the "
+                           "pinned frame buffers in place (stage() is the optional pageable->pinned memcpy and is not timed)"},
             "gpu_launches": pipe.launches_per_step * args.steps, "gpu_launches_per_step": pipe.launches_per_step,
-            "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "kernels": kern, "parity": parity, "strong_scaling": strong, "cpu_baseline": cpu,
+            "build": build_record(),
         }
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out), flush=True)
+
+
+def build_record():
+    try:
+        from flowtrack.pytorch_b200 import build as ft_build
+        info = ft_build.read_info()
+        return {"source_sha256": info.get("source_sha256"), "matches_sources": info.get("source_sha256") == ft_build.source_hash(), "nvcc": info.get("nvcc")}
+    except Exception:
+        return None
+
+
+def read_traffic_capture(_lib):
+    """DRAM bytes per conv launch from the committed `ncu --set full` capture of the same plans (profiles/r02_conv_traffic.json;
+    produced by tools/dev/ncu_conv_traffic.py).  The capture records the SHA-256 of the kernel sources it was taken with; a
+    capture of other sources is refused (traffic = null) instead of being reported against today's kernels."""
+    try:
+        from flowtrack.pytorch_b200 import build as ft_build
+        with open(os.path.join(ROOT, "profiles", "r02_conv_traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("source_sha256") != ft_build.source_hash():
+            return None, {"refused": "profiles/r02_conv_traffic.json was captured with other kernel sources (%s...), not the ones built here"
+                          % str(tr.get("source_sha256"))[:12]}
+        return tr["dram_bytes_per_launch"], {"tensor_pipe_active_pct_time_weighted": tr.get("tensor_pipe_active_pct_time_weighted"), "source": tr.get("source"),
+                                              "source_sha256": tr.get("source_sha256")}
+    except Exception:
+        return None, None
+
+
+def parity_check(torch, cfg, pipe, pose, flow, video, state):
+    """One step of the timed workload against the CPU oracle (same weights, same uint8 frames, same previous state): the flow
+    and the heat-maps of the first frame pair, and every decoded key-point / box of it.  Tolerances of BASELINE.json's
+    north_star: heat-maps 1e-3 max-abs, key-points 1 px (flows: 1e-3 x max|flow|)."""
+    from oracle import flow_oracle, pose_oracle, track_oracle
+    from flowtrack.pytorch_b200.tracking import synthetic
+    torch.manual_seed(0)
+    o_pose = synthetic.condition_pose_weights(pose_oracle.deconv("resnet%d" % cfg["depth"], 17, False), 0).eval()
+    o_flow = getattr(flow_oracle, cfg["flow"])(None).eval()
+    o_pose.load_state_dict({k: v.cpu() for k, v in pose.state_dict().items()}, strict=True)
+    o_flow.load_state_dict({k: v.cpu() for k, v in flow.state_dict().items()}, strict=True)
+    dets, count, kps = state
+    pipe.seed(dets, count, kps)
+    frames = np.ascontiguousarray(video[:, 0:2])
+    g_dets, g_count, g_kps = pipe.process(torch.from_numpy(frames))
+    g_dets, g_kps = g_dets.clone().numpy(), g_kps.clone().numpy().reshape(pipe.F, PEOPLE, 17, 3)
+    ln = pipe.lanes[(pipe._next - 1) % len(pipe.lanes)]
+    g_flow = ln.flow[0].cpu().numpy()
+    g_hm = pipe.heatmaps[:PEOPLE].cpu()
+    g_crops = pipe.crops[:PEOPLE].cpu()
+    w_dets, w_kps, w_flow = track_oracle.process_frame(o_pose, o_flow, frames[0, 0], frames[0, 1], dets[0], kps.reshape(pipe.F, PEOPLE, 17, 3)[0], None,
+                                                       inp_res=cfg["crop_hw"], thresh=0.3, max_people=PEOPLE)
+    with torch.no_grad():
+        w_hm = o_pose(g_crops)
+    m = w_dets.shape[0]
+    res = {"sample": "frame pair 0 of one step of the timed workload (same weights, frames and previous state on both sides)",
+           "flow_max_abs": float(np.abs(g_flow - w_flow).max()), "flow_abs_max": float(np.abs(w_flow).max()),
+           "heatmap_max_abs": float((g_hm - w_hm).abs().max()), "heatmap_abs_max": float(w_hm.abs().max()),
+           "people": int(g_count[0]), "people_oracle": int(m),
+           "box_max_px": float(np.abs(g_dets[0, :m, :4] - w_dets[:, :4]).max()) if m else 0.0,
+           "keypoint_max_px": float(np.abs(g_kps[0, :m, :, :2] - w_kps[:, :, :2]).max()) if m else 0.0,
+           "tolerance": {"heatmap_max_abs": 1e-3, "flow_max_abs_rel": 1e-3, "keypoint_px": 1.0}}
+    res["ok"] = bool(res["heatmap_max_abs"] < 1e-3 and res["flow_max_abs"] <= 1e-3 * max(1.0, res["flow_abs_max"]) and res["keypoint_max_px"] <= 1.0
+                     and res["box_max_px"] <= 1.0 and res["people"] == res["people_oracle"])
+    return res
+
+
+def _time_cuda(torch, fn, iters, flush=None):
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def bench_reference_gpu(torch, cfg):
+    """The GPU-side bar SURVEY.md 2.1 K11 / BASELINE.md 4 name: the reference nn.Modules (unmodified, staged under baseline/_ref;
+    else the oracle's restated modules) under cuDNN on this GPU at the BASELINE config 2 / 3 sizes -- fp32 strict, TF32, and bf16
+    channels-last -- and the reference's own correlation kernel (oracle/_ref/libref_correlation.so) at [32,256,48,64].
+    Informational: these run PyTorch/cuDNN, none of this repo's kernels."""
+    from oracle import flow_oracle, pose_oracle, ref_gpu, ref_loader
+    src = "oracle port"
+    torch.manual_seed(0)
+    pose = pose_oracle.deconv("resnet50", 17, False)
+    flow = flow_oracle.FlowNet2S(None)
+    if ref_loader.available():
+        try:
+            pose = ref_loader.pose_models().deconv("resnet50", 17, False)
+            flow = ref_loader.flow_models("oracle").FlowNet2S(ref_loader.Args())
+            src = "unmodified reference modules (baseline/_ref)"
+        except Exception:
+            pass
+    pose, flow = pose.eval().cuda(), flow.eval().cuda()
+    xp = torch.randn(64, 3, 256, 192, device="cuda")
+    xf = torch.rand(32, 3, 2, 384, 512, device="cuda") * 255
+    out = {"modules": src, "cudnn": torch.backends.cudnn.version()}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        with torch.no_grad():
+            for name, tf32 in (("fp32_strict", False), ("tf32", True)):
+                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tf32
+                out["pose_r50_b64_%s_ms" % name] = _time_cuda(torch, lambda: pose(xp), 5)
+                out["flownet2s_b32_%s_ms" % name] = _time_cuda(torch, lambda: flow(xf), 3)
+            pb = pose.to(memory_format=torch.channels_last).bfloat16()
+            xpb = xp.to(memory_format=torch.channels_last).bfloat16()
+            out["pose_r50_b64_bf16_channels_last_ms"] = _time_cuda(torch, lambda: pb(xpb), 5)
+            fb = flow.bfloat16()
+            xfb = xf.bfloat16()
+            try:
+                out["flownet2s_b32_bf16_ms"] = _time_cuda(torch, lambda: fb(xfb), 3)
+            except Exception as e:
+                out["flownet2s_b32_bf16_ms"] = None
+                out["flownet2s_bf16_note"] = repr(e)[:120]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    for k in list(out):
+        if k.startswith("pose_r50_b64_") and out[k]:
+            out[k.replace("_ms", "_crops_per_s")] = 64 / (out[k] * 1e-3)
+        if k.startswith("flownet2s_b32_") and k.endswith("_ms") and out[k]:
+            out[k.replace("_ms", "_pairs_per_s")] = 32 / (out[k] * 1e-3)
+    del pose, flow, xp, xf
+    if ref_gpu.correlation_lib() is not None:
+        B, C, H, W = 32, 256, 48, 64
+        a, b = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
+        o = torch.zeros(B, 441, H, W, device="cuda")
+        scratch = (torch.zeros(B, H + 40, W + 40, C, device="cuda"), torch.zeros(B, H + 40, W + 40, C, device="cuda"))
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        ms = _time_cuda(torch, lambda: ref_gpu.correlation(a, b, o, scratch), 5, flush)
+        byts = (2 * B * C * H * W + B * 441 * H * W) * 4
+        out["reference_correlation_kernel_ms"] = ms
+        out["reference_correlation_kernel_gbs"] = byts / (ms * 1e-3) / 1e9
+        out["reference_correlation_note"] = "correlation_cuda_kernel.cu compiled unmodified for sm_100a (channels_first rearrange x2 + correlation kernel), [32,256,48,64], L2 flushed"
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_correlation(torch, _lib, peaks):
@@ -398,12 +646,17 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=PAIRS, help="frame pairs per GPU per step")
+    ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS), help="BASELINE.json config: 4 (R50 + FlowNet2S, the metric's) or 5 (R152 384x288 + FlowNet2)")
+    ap.add_argument("--pairs", type=int, default=0, help="frame pairs per GPU per step (weak) / global (strong); default: the config's")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the additional strong-scaling measurement")
     ap.add_argument("--precision", default="split", choices=["split", "fast"])
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true")
     ap.add_argument("--preroll", type=float, default=0.6, help="seconds of untimed steps while nvidia-smi starts sampling")
-    ap.add_argument("--host-crops", action="store_true", help="take ready-made person crops from the host instead of cutting them on the GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

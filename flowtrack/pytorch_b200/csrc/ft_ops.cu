@@ -387,6 +387,59 @@ __global__ void pack_pair_kernel(const float* __restrict__ pair, const float* __
     }
 }
 
+// ---- uint8 frame pairs (the reference's cv2 frames, net_utils.py:83-87): frames [B,2,H,W,3] uint8, channel order BGR (cv2) or RGB ----
+// per (b, memory channel) sums over both frames: exact integer arithmetic, one atomicAdd per block and channel
+__global__ void pair_u8_sum_kernel(const uint8_t* __restrict__ frames, size_t bytes_per_pair, unsigned long long* __restrict__ sums) {
+    const int b = blockIdx.y;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(frames + (size_t)b * bytes_per_pair);
+    const size_t groups = bytes_per_pair / 12;                      // 12 bytes = 4 pixels: the channel of every byte lane is fixed per thread
+    uint32_t s0 = 0, s1 = 0, s2 = 0;
+    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t a = __ldg(w + 3 * g), c = __ldg(w + 3 * g + 1), d = __ldg(w + 3 * g + 2);
+        // bytes: a = c0 c1 c2 c0 | c = c1 c2 c0 c1 | d = c2 c0 c1 c2
+        s0 += (a & 255u) + (a >> 24) + ((c >> 16) & 255u) + ((d >> 8) & 255u);
+        s1 += ((a >> 8) & 255u) + (c & 255u) + (c >> 24) + ((d >> 16) & 255u);
+        s2 += ((a >> 16) & 255u) + ((c >> 8) & 255u) + (d & 255u) + (d >> 24);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o), s1 += __shfl_xor_sync(0xffffffffu, s1, o), s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(sums + b * 3 + 0, (unsigned long long)s0);
+        atomicAdd(sums + b * 3 + 1, (unsigned long long)s1);
+        atomicAdd(sums + b * 3 + 2, (unsigned long long)s2);
+    }
+}
+
+__global__ void pack_pair_u8_kernel(const uint8_t* __restrict__ frames, const unsigned long long* __restrict__ sums, int B, int H, int W, int bgr,
+                                    float rgb_max, float* __restrict__ x_f32, ft_act d, int has_dst, int xl) {
+    const size_t plane = (size_t)H * W;
+    const size_t total = (size_t)B * plane;
+    const double inv_n = 1.0 / (2.0 * (double)plane);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / plane, p = i % plane;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int mc = bgr ? 2 - c : c;                                       // memory channel holding colour c of the RGB flow input
+            const float mean = (float)((double)sums[b * 3 + mc] * inv_n);         // models.py:112 (per sample and colour, both frames)
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                const float t = ((float)frames[((b * 2 + f) * plane + p) * 3 + mc] - mean) / rgb_max;      // x channel = f*3 + c (models.py:116-119)
+                v[f * 3 + c] = t;
+                if (x_f32) x_f32[(b * 6 + f * 3 + c) * plane + p] = t;
+            }
+        }
+        v[6] = v[7] = 0.f;
+        if (has_dst) {
+            const size_t dpix = (b * H + p / W) * d.w + p % W + xl;
+            store8(d, dpix, 0, v);
+            const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int g = 1; g < d.c / 8; ++g) store8(d, dpix, g * 8, z);
+        }
+    }
+}
+
 __global__ void upsample4x_kernel(const float* __restrict__ src, float* __restrict__ dst, int BC, int h, int w, float mul, int mode) {
     const int H = 4 * h, W = 4 * w;
     const size_t total = (size_t)BC * H * W;
@@ -534,9 +587,14 @@ __global__ void flow_upsample_kernel(const float* __restrict__ flow, const float
 // Decode (A9) and box propagation (A10)
 // =====================================================================================================
 __global__ void decode_kernel(const float* __restrict__ hm, int C, int h, int w, const float* __restrict__ center,
-                              const float* __restrict__ scale, int adjust, float threshold, float* __restrict__ kps) {
+                              const float* __restrict__ scale, int adjust, float threshold, const int32_t* __restrict__ valid,
+                              float* __restrict__ kps) {
     const int nc = blockIdx.x;  // n*C + c
     const int n = nc / C;
+    if (valid && !valid[n]) {   // an empty person slot of the tracking pipeline: no key-points
+        if (threadIdx.x < 3) kps[(size_t)nc * 3 + threadIdx.x] = 0.f;
+        return;
+    }
     const float* p = hm + (size_t)nc * h * w;
     float best = -INFINITY;
     int bi = 0x7fffffff;
@@ -733,6 +791,32 @@ int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* m
     return check_launch("pack_pair_kernel");
 }
 
+int ft_pack_pair_u8(const uint8_t* frames, int B, int H, int W, int bgr, float rgb_max, void* sum_ws, float* x_f32, const ft_act* dst, int xpad_l,
+                    int xpad_r, void* stream) {
+    FT_REQUIRE(frames && sum_ws && B > 0 && H > 0 && W > 0, "pack_pair_u8: bad arguments");
+    FT_REQUIRE(((size_t)H * W) % 4 == 0 && ((uintptr_t)frames & 3) == 0, "pack_pair_u8: H*W must be a multiple of 4 and the frames 4-byte aligned");
+    FT_REQUIRE(B <= 65535 && ((uintptr_t)sum_ws & 7) == 0, "pack_pair_u8: at most 65535 pairs; the workspace must be 8-byte aligned");
+    ft_act d = {};
+    if (dst) {
+        if (int e = check_act(dst, "pack_pair_u8.dst", false)) return e;
+        FT_REQUIRE(xpad_l >= 0 && xpad_r >= 0, "pack_pair_u8: bad x-padding");
+        FT_REQUIRE(dst->c >= 8 && dst->n == B && dst->h == H && dst->w == W + xpad_l + xpad_r, "pack_pair_u8: dst shape mismatch");
+        d = *dst;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(sum_ws, 0, sizeof(unsigned long long) * 3 * B, s) != cudaSuccess) {
+        set_error("pack_pair_u8: memset of the workspace failed");
+        return 1;
+    }
+    const size_t bytes_per_pair = (size_t)2 * H * W * 3;
+    const int bx = min(ceil_div((int)(bytes_per_pair / 12), 256), max(1, device_sms() * 8 / B));
+    pair_u8_sum_kernel<<<dim3(bx, B), 256, 0, s>>>(frames, bytes_per_pair, (unsigned long long*)sum_ws);
+    if (check_launch("pair_u8_sum_kernel")) return 1;
+    pack_pair_u8_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, s>>>(frames, (const unsigned long long*)sum_ws, B, H, W, bgr != 0, rgb_max, x_f32, d,
+                                                                          dst != nullptr, xpad_l);
+    return check_launch("pack_pair_u8_kernel");
+}
+
 int ft_upsample4x(const float* src, float* dst, int B, int C, int h, int w, float mul, int mode, void* stream) {
     FT_REQUIRE(src && dst && B > 0 && C > 0 && h > 0 && w > 0 && (mode == 0 || mode == 1), "upsample4x: bad arguments");
     upsample4x_kernel<<<grid_for((size_t)B * C * h * w * 16, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, B * C, h, w, mul, mode);
@@ -767,9 +851,10 @@ int ft_flow_upsample(const float* flow, const float* w, const float* bias, int B
     return check_launch("flow_upsample_kernel");
 }
 
-int ft_decode_keypoints(const float* hm, int N, int C, int h, int w, const float* center, const float* scale, int adjust, float threshold, float* kps, void* stream) {
+int ft_decode_keypoints(const float* hm, int N, int C, int h, int w, const float* center, const float* scale, int adjust, float threshold,
+                        const int32_t* valid, float* kps, void* stream) {
     FT_REQUIRE(hm && center && scale && kps && N > 0 && C > 0 && h > 0 && w > 0, "decode_keypoints: bad arguments");
-    decode_kernel<<<N * C, 256, 0, (cudaStream_t)stream>>>(hm, C, h, w, center, scale, adjust, threshold, kps);
+    decode_kernel<<<N * C, 256, 0, (cudaStream_t)stream>>>(hm, C, h, w, center, scale, adjust, threshold, valid, kps);
     return check_launch("decode_kernel");
 }
 

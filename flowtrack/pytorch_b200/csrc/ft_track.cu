@@ -316,9 +316,86 @@ __global__ void flowvis_color_kernel(const float* __restrict__ flow, int HW, con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The tracker's glue between box propagation and pose_est (tools/tracking/demo.py:35-42 process_frame;
+// lib/tracking/net_utils.py:25-33 detect, :49-50 pose_est), device-resident so the recurrent state (person boxes and
+// key-points of the previous frame) never leaves the GPU:
+//   merge : candidates of frame f = [detector boxes (det_count[f]) | propagated boxes with the previous scores (prev_count[f])]
+//           (np.concatenate((dets, prop_dets)), net_utils.py:27-29; prop_dets = [prop_boxes | prev_dets[:,4]], demo.py:38)
+//   (ft_nms over the candidates)
+//   select: the first min(num_keep, P) survivors become the frame's person slots: dets [F,P,5], count [F], and per slot the crop
+//           centre / scale of pose_est (centre = box centre, scale = max(box_h, box_w / out_w * out_h), computed in double as
+//           numpy does) and a valid flag; empty slots get a harmless whole-frame crop and valid = 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void track_merge_kernel(const float* __restrict__ prop_boxes, const float* __restrict__ prev_dets, const int32_t* __restrict__ prev_count,
+                                   const float* __restrict__ det, const int32_t* __restrict__ det_count, int F, int P, int D,
+                                   float* __restrict__ cand, int32_t* __restrict__ cand_count) {
+    const int N = D + P;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * N) return;
+    const int f = i / N, j = i - f * N;
+    const int nd = det ? min(max(det_count ? det_count[f] : D, 0), D) : 0;
+    const int np = min(max(prev_count[f], 0), P);
+    float* o = cand + (size_t)i * 5;
+    if (j < nd) {
+        const float* d = det + ((size_t)f * D + j) * 5;
+        o[0] = d[0], o[1] = d[1], o[2] = d[2], o[3] = d[3], o[4] = d[4];
+    } else if (j < nd + np) {
+        const int k = j - nd;
+        const float* b = prop_boxes + ((size_t)f * P + k) * 4;
+        o[0] = b[0], o[1] = b[1], o[2] = b[2], o[3] = b[3], o[4] = prev_dets[((size_t)f * P + k) * 5 + 4];
+    } else {
+        o[0] = o[1] = o[2] = o[3] = 0.f, o[4] = -INFINITY;
+    }
+    if (j == 0) cand_count[f] = nd + np;
+}
+
+__global__ void track_select_kernel(const float* __restrict__ cand, const int32_t* __restrict__ keep, const int32_t* __restrict__ num_keep, int F, int N,
+                                    int P, int out_h, int out_w, int frame_h, int frame_w, float* __restrict__ dets, int32_t* __restrict__ count,
+                                    float* __restrict__ centers, float* __restrict__ scales, int32_t* __restrict__ valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * P) return;
+    const int f = i / P, k = i - f * P;
+    const int n = min(max(num_keep[f], 0), P);
+    float* o = dets + (size_t)i * 5;
+    if (k < n) {
+        const float* c = cand + ((size_t)f * N + keep[(size_t)f * N + k]) * 5;
+        o[0] = c[0], o[1] = c[1], o[2] = c[2], o[3] = c[3], o[4] = c[4];
+        centers[2 * i] = (float)(((double)c[0] + (double)c[2]) / 2.0);
+        centers[2 * i + 1] = (float)(((double)c[1] + (double)c[3]) / 2.0);
+        const double bh = (double)c[3] - (double)c[1], bw = ((double)c[2] - (double)c[0]) / (double)out_w * (double)out_h;
+        scales[i] = (float)(bh > bw ? bh : bw);
+        valid[i] = 1;
+    } else {
+        o[0] = o[1] = o[2] = o[3] = o[4] = 0.f;
+        centers[2 * i] = 0.5f * frame_w, centers[2 * i + 1] = 0.5f * frame_h;
+        scales[i] = (float)frame_h;
+        valid[i] = 0;
+    }
+    if (k == 0) count[f] = n;
+}
+
 }  // namespace ft
 
 using namespace ft;
+
+extern "C" int ft_track_merge(const float* prop_boxes, const float* prev_dets, const int32_t* prev_count, const float* det, const int32_t* det_count,
+                              int F, int P, int D, float* cand, int32_t* cand_count, void* stream) {
+    FT_REQUIRE(F > 0 && P > 0 && D >= 0 && D + P <= NMS_MAX, "track_merge: bad shape (F=%d P=%d D=%d; at most %d candidates per frame)", F, P, D, NMS_MAX);
+    FT_REQUIRE(prop_boxes && prev_dets && prev_count && cand && cand_count && (D == 0 || det), "track_merge: null pointer");
+    track_merge_kernel<<<ceil_div(F * (D + P), 128), 128, 0, (cudaStream_t)stream>>>(prop_boxes, prev_dets, prev_count, D ? det : nullptr, det_count, F, P, D, cand,
+                                                                                  cand_count);
+    return check_launch("track_merge_kernel");
+}
+
+extern "C" int ft_track_select(const float* cand, const int32_t* keep, const int32_t* num_keep, int F, int N, int P, int out_h, int out_w, int frame_h,
+                               int frame_w, float* dets, int32_t* count, float* centers, float* scales, int32_t* valid, void* stream) {
+    FT_REQUIRE(F > 0 && P > 0 && N >= P && out_h > 0 && out_w > 0 && frame_h > 0 && frame_w > 0, "track_select: bad shape");
+    FT_REQUIRE(cand && keep && num_keep && dets && count && centers && scales && valid, "track_select: null pointer");
+    track_select_kernel<<<ceil_div(F * P, 128), 128, 0, (cudaStream_t)stream>>>(cand, keep, num_keep, F, N, P, out_h, out_w, frame_h, frame_w, dets, count, centers,
+                                                                             scales, valid);
+    return check_launch("track_select_kernel");
+}
 
 extern "C" int ft_flow_to_image(const float* flow, int B, int H, int W, void* maxrad_ws, uint8_t* img, void* stream) {
     FT_REQUIRE(B >= 0 && H > 0 && W > 0, "flow_to_image: bad shape");

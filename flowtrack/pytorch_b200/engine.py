@@ -481,6 +481,35 @@ class Plan:
                     tot[i] += ev[i].elapsed_time(ev[i + 1])
         return [t / reps for t in tot]
 
+    def time_calls_graphed(self, reps=5):
+        """Per-call device time in ms measured INSIDE a CUDA-graph replay: the plan is captured with an external
+        (cudaEventRecordExternal) timing event between consecutive calls, replayed `reps` times, and the event pairs are read
+        back -- kernels run back to back as in production, no host launch gaps and no per-launch tensor-map encoding in the
+        intervals (time_calls() has both).  The event nodes sit between the kernels, so programmatic dependent launch cannot
+        overlap across them: a call's figure here is its full, un-overlapped duration."""
+        with torch.cuda.device(self.device):
+            n = len(self.calls)
+            self.enqueue()                                        # warm-up outside the capture
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(n + 1)]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                s = stream_ptr()
+                ev[0].record()
+                for i, (what, fn, args, _keep) in enumerate(self.calls):
+                    _lib.check(fn(*args, s), what)
+                    ev[i + 1].record()
+            tot = [0.0] * n
+            g.replay()
+            torch.cuda.synchronize()
+            for _ in range(reps):
+                g.replay()
+                torch.cuda.synchronize()
+                for i in range(n):
+                    tot[i] += ev[i].elapsed_time(ev[i + 1])
+            del g
+        return [t / reps for t in tot]
+
     def run(self):
         if self.graph is not None:
             with torch.cuda.device(self.device):

@@ -62,20 +62,28 @@ class _FlowBase(nn.Module):
     def _build(self, p, L, pair, B, H, W):
         raise NotImplementedError
 
-    def plan_for(self, B, H, W, device):
-        """(plan, static fp32 input [B,3,2,H,W], static fp32 flow [B,2,H,W]) for this batch shape; built once and cached."""
+    def plan_for(self, B, H, W, device, u8=False, tag=0):
+        """(plan, static input, static fp32 flow [B,2,H,W]) for this batch shape; built once and cached.  The static input is the
+        reference's fp32 [B,3,2,H,W] RGB pair, or with u8=True a uint8 [B,2,H,W,3] BGR buffer -- the cv2 frames the reference's
+        callers hold (lib/tracking/net_utils.py:83-87), converted and normalised by the packing kernel.  `tag` lets a caller own
+        several independent plans (own buffers) of one shape, e.g. the two lanes of tracking.tracker.TrackingPipeline."""
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("%s.forward needs a CUDA tensor: this package has no CPU path" % type(self).__name__)
         if H % 64 or W % 64:
             raise ValueError("expected [B,3,2,H,W] with H, W multiples of 64, got %s" % ((B, 3, 2, H, W),))
         prec = _lib.PREC_FAST if self.precision == "fast" else _lib.PREC_SPLIT
-        key = (B, H, W, prec, self._impl, device.index if device.index is not None else torch.cuda.current_device())
+        key = (B, H, W, prec, self._impl, device.index if device.index is not None else torch.cuda.current_device(), bool(u8), tag)
         if key not in self._plans:
             if self._layers is None:
                 self._layers = self._pack(device)
             p = engine.Plan(device, prec, self._impl)
-            pair = p.f32(B, 3, 2, H, W)
+            if u8:
+                pair = torch.zeros(B, 2, H, W, 3, dtype=torch.uint8, device=device)
+                p.keep.append(pair)
+                p.pair_u8 = True
+            else:
+                pair = p.f32(B, 3, 2, H, W)
             out = self._build(p, self._layers, pair, B, H, W)
             self._plans[key] = (p, pair, out)
         return self._plans[key]
@@ -101,9 +109,15 @@ def _normalise(p, pair, B, H, W, want_f32, want_act, xpad=(0, 0)):
     """models.py:112-119: x = (pair - mean_bc)/rgb_max as [B,6,H,W] fp32 and/or split-fp16 NHWC (6 -> 8 channels).
     `xpad`: zero columns the consuming stem convolution wants around every row of the NHWC copy (ConvLayer.in_xpad)."""
     lib = _lib.lib()
-    ws = p.f32(lib.ft_pack_pair_ws_floats(B))
     xf = p.f32(B, 6, H, W) if want_f32 else None
     xa = p.act(B, H, W, 6, xpad=xpad) if want_act else None
+    if getattr(p, "pair_u8", False):          # uint8 BGR frames [B,2,H,W,3] (cv2 layout): flip to RGB, convert, normalise in one pass
+        ws = torch.zeros(B * 3, dtype=torch.int64, device=p.device)
+        p.keep.append(ws)
+        p.call("pack_pair_u8", lib.ft_pack_pair_u8, pair.data_ptr(), B, H, W, 1, p.rgb_max, ws.data_ptr(),
+               xf.data_ptr() if want_f32 else None, xa.struct() if want_act else None, xpad[0], xpad[1])
+        return xf, xa
+    ws = p.f32(lib.ft_pack_pair_ws_floats(B))
     p.call("pack_pair", lib.ft_pack_pair, pair.data_ptr(), B, H, W, p.rgb_max, ws.data_ptr(),
            xf.data_ptr() if want_f32 else None, xa.struct() if want_act else None, xpad[0], xpad[1])
     return xf, xa

@@ -43,7 +43,7 @@ def boxes_to_center_scale(boxes, inp_res=(256, 192)):
     return centers, scales
 
 
-def final_preds_cuda(heatmaps, centers, scales, adjust_coords=True, out=None, threshold=0.0):
+def final_preds_cuda(heatmaps, centers, scales, adjust_coords=True, out=None, threshold=0.0, valid=None):
     """max_preds + final_preds + transform_preds (lib/pose/utils/evaluation.py:11-35) in one kernel.
     heatmaps: CUDA fp32 [N,C,h,w]; centers [N,2], scales [N] CUDA fp32 -> CUDA fp32 [N,C,3] = (x, y, score).
     `threshold` is max_preds' argument (:11,18): heat-map coordinates are zeroed unless score > threshold."""
@@ -53,7 +53,8 @@ def final_preds_cuda(heatmaps, centers, scales, adjust_coords=True, out=None, th
         if out is None:
             out = torch.empty(N, C, 3, device=heatmaps.device, dtype=torch.float32)
         _lib.check(_lib.lib().ft_decode_keypoints(heatmaps.data_ptr(), N, C, h, w, centers.data_ptr(), scales.data_ptr(), int(bool(adjust_coords)),
-                                                  float(threshold), out.data_ptr(), engine.stream_ptr()), "decode_keypoints")
+                                                  float(threshold), valid.data_ptr() if valid is not None else None, out.data_ptr(),
+                                                  engine.stream_ptr()), "decode_keypoints")
     return out
 
 

@@ -32,6 +32,8 @@
  *   ft_flip_w / ft_flip_merge  flip test: np.flip + swaplr_image + average                  tools/pose/main.py:289-299, lib/pose/utils/transforms.py:140-170
  *   ft_nms_oks               nms_oks + compute_oks                                   lib/pose/utils/evaluation.py:60-101
  *   ft_flow_to_image         flowlib.flow_to_image (Middlebury colour coding)         lib/flownet/utils/flowlib.py:243-282,430-521 (tools/flownet/demo.py:93)
+ *   ft_pack_pair_u8          cv2 uint8 frames -> RGB float pair + normalisation      lib/tracking/net_utils.py:83-87, lib/flownet/model/models.py:112-119
+ *   ft_track_merge / ft_track_select   detect()'s merge + pose_est's box -> centre/scale   lib/tracking/net_utils.py:25-33,49-50, tools/tracking/demo.py:35-42
  *   ft_nms                   pth_nms / cpu_nms / nms_kernel                          lib/detection/nms/pth_nms.py:5-46, src/nms.c:36-62, src/cuda/nms_kernel.cu:13-70
  */
 #ifndef FLOWTRACK_B200_H_
@@ -44,7 +46,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 12
+#define FT_ABI_VERSION 13
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -187,6 +189,12 @@ int ft_pack_image_s2d(const float* src, int B, int H, int W, const ft_act* dst, 
 int ft_pack_pair_ws_floats(int B);
 int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* mean_ws, float* x_f32,
                  const ft_act* dst, int xpad_l, int xpad_r, void* stream);   /* dst->w = xpad_l + W + xpad_r, as above */
+/* The same from uint8 frames as the reference's callers hold them (cv2 frames, lib/tracking/net_utils.py:83-87): frames
+ * [B,2,H,W,3] uint8, memory channel order BGR (bgr != 0, cv2) or RGB; the BGR->RGB flip, the float conversion, the per-sample
+ * colour mean over both frames (exact integer sums) and the division by rgb_max happen in the packing pass, so a frame pair
+ * crosses PCIe as 6 bytes per pixel instead of 24.  sum_ws: B*3 x 8 bytes of scratch (cleared by a memset node).          */
+int ft_pack_pair_u8(const uint8_t* frames, int B, int H, int W, int bgr, float rgb_max, void* sum_ws, float* x_f32,
+                    const ft_act* dst, int xpad_l, int xpad_r, void* stream);
 /* src: [B,C,h,w] fp32 -> dst: [B,C,4h,4w] fp32 times `mul`.  mode 0 = bilinear (align_corners=False),
  * 1 = nearest.                                                                                        */
 int ft_upsample4x(const float* src, float* dst, int B, int C, int h, int w, float mul, int mode, void* stream);
@@ -214,9 +222,11 @@ int ft_flow_upsample(const float* flow, const float* w, const float* bias, int B
 /* hm: [N,C,h,w] fp32; center: [N,2], scale: [N] fp32 -> kps: [N,C,3] = (x, y, score) in image
  * coordinates (max_preds + optional quarter-pixel shift + inverse crop transform).  `threshold` is
  * max_preds' argument (evaluation.py:11,18-19): heat-map coordinates are zeroed unless score > threshold
- * (final_preds always passes 0).                                                                     */
+ * (final_preds always passes 0).  valid: optional [N] int32; persons with valid == 0 (empty slots of the
+ * tracking pipeline) get all-zero records.                                                           */
 int ft_decode_keypoints(const float* hm, int N, int C, int h, int w, const float* center,
-                        const float* scale, int adjust, float threshold, float* kps, void* stream);
+                        const float* scale, int adjust, float threshold, const int32_t* valid, float* kps,
+                        void* stream);
 /* kps: [N,K,3] previous-frame key-points; frame_of: [N] int32 index of each person's frame pair;
  * flow: [B,2,H,W] -> boxes: [N,4] (x0,y0,x1,y1).  Key-point pixels are clamped into the flow field
  * before the look-up (the reference indexes unclamped, lib/tracking/flow_utils.py:23-24).             */
@@ -247,6 +257,20 @@ int ft_flip_merge(const float* hm, const float* hm_flipped, const int32_t* perm,
  * (-1 beyond num_keep[frame]).                                                                        */
 int ft_nms(const float* dets, const int32_t* counts, int frames, int N, float thresh, int inclusive,
            int32_t* keep, int32_t* num_keep, void* stream);
+
+/* The tracker's device-resident glue between box propagation and pose_est (tools/tracking/demo.py:35-42 process_frame;
+ * lib/tracking/net_utils.py:25-33 detect, :49-50 pose_est).  F frames (streams), P person slots per frame, D detector boxes.
+ *   ft_track_merge   cand [F,D+P,5] = per frame [det (det_count[f], NULL = D) | prop_boxes with the scores prev_dets[:,4]
+ *                    (prev_count[f])], compact, cand_count [F]: np.concatenate((dets, prop_dets)) of net_utils.py:27-29.
+ *   (ft_nms over cand / cand_count)
+ *   ft_track_select  the first min(num_keep[f], P) survivors, highest score first -> dets [F,P,5], count [F], and for every slot
+ *                    the crop centre [F*P,2] / scale [F*P] of pose_est (box centre; max(box_h, box_w/out_w*out_h)) and
+ *                    valid [F*P] int32; empty slots get a whole-frame crop and valid = 0.                                 */
+int ft_track_merge(const float* prop_boxes, const float* prev_dets, const int32_t* prev_count, const float* det,
+                   const int32_t* det_count, int F, int P, int D, float* cand, int32_t* cand_count, void* stream);
+int ft_track_select(const float* cand, const int32_t* keep, const int32_t* num_keep, int F, int N, int P, int out_h, int out_w,
+                    int frame_h, int frame_w, float* dets, int32_t* count, float* centers, float* scales, int32_t* valid,
+                    void* stream);
 
 /* OKS-NMS over poses (nms_oks + compute_oks(ground_truth=False), lib/pose/utils/evaluation.py:60-101).  joints
  * [frames,N,K,3] = (x, y, score), scores [frames,N] (pose score), areas [frames,N], delta [K] (per-joint falloff),

@@ -63,7 +63,9 @@ def final_preds(heatmap, center, scale, adjust_coords=False):
     return transform_preds(coords, center, scale, (h, w)), scores
 
 
-def box_propagation(keypoints, flow):
+def box_propagation(keypoints, flow, clamp=False):
+    """clamp=True: key-point pixels are clamped into the flow field before the look-up, as ft_box_propagation does (the
+    reference indexes unclamped and raises / wraps for key-points outside the frame)."""
     kp = np.asarray(keypoints, dtype=np.float64)
     flow = np.asarray(flow, dtype=np.float64)
     extend_factor = 0.15
@@ -71,6 +73,8 @@ def box_propagation(keypoints, flow):
     num_kpts = kp.shape[1]
     flow_t = flow.transpose((2, 1, 0))         # [W, H, 2]
     pos = kp[:, :, :2].reshape(-1, 2).T.astype(int)
+    if clamp:
+        pos[0], pos[1] = np.clip(pos[0], 0, W - 1), np.clip(pos[1], 0, H - 1)
     offset = flow_t[pos[0], pos[1]].reshape(-1, num_kpts, 2)
     shift = kp[:, :, :2] + offset
     mask = (kp[:, :, 2] > 0)[:, :, np.newaxis]

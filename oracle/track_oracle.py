@@ -218,3 +218,36 @@ def ref_cpu_nms(dets, thresh):
                      ctypes.byref(t(areas, n)), ctypes.c_float(thresh))
     assert rc == 1
     return keep[:int(num[0])].copy()
+
+
+def process_frame(pose_net, flow_net, prev_im, cur_im, prev_dets, prev_keypoints, det=None, inp_res=(256, 192), thresh=0.3, max_people=None):
+    """The reference's per-frame tracking step, tools/tracking/demo.py:35-42, with flow_est / detect / pose_est restated from
+    lib/tracking/net_utils.py (:73-92, :25-33 minus the detector network, :36-71 with the `min` fix of :61) over CPU oracle
+    networks.  prev_im, cur_im: HxWx3 uint8 BGR; prev_dets [n,5]; prev_keypoints [n,K,3]; det: optional detector boxes [d,5].
+    Returns (cur_dets [m,5], cur_keypoints [m,K,3], flow [2,H,W]); max_people truncates to the highest-scored boxes (the
+    capacity of the device pipeline's person slots)."""
+    import torch
+    from oracle import decode_oracle
+    pair = np.stack([prev_im[:, :, ::-1], cur_im[:, :, ::-1]])[None].transpose(0, 4, 1, 2, 3).astype(np.float32)      # [1,3(RGB),2,H,W]
+    with torch.no_grad():
+        flow = flow_net(torch.from_numpy(np.ascontiguousarray(pair)))[0].numpy()
+    prev_dets = np.asarray(prev_dets, np.float32).reshape(-1, 5)
+    if prev_dets.shape[0]:
+        prop_boxes = decode_oracle.box_propagation(np.asarray(prev_keypoints), flow, clamp=True)
+        prop_dets = np.concatenate((prop_boxes, prev_dets[:, 4][:, np.newaxis]), axis=1).astype(np.float32)
+    else:
+        prop_dets = np.zeros((0, 5), np.float32)
+    dets = np.zeros((0, 5), np.float32) if det is None else np.asarray(det, np.float32).reshape(-1, 5)
+    dets = np.concatenate((dets, prop_dets), axis=0)
+    if dets.shape[0]:
+        dets = dets[nms_cpu(dets, thresh, inclusive=True)]
+    if max_people is not None:
+        dets = dets[:max_people]
+    if dets.shape[0] == 0:
+        return dets, np.zeros((0, 17, 3), np.float32), flow
+    crops = crop_boxes(np.ascontiguousarray(cur_im), dets[:, :4], inp_res)
+    with torch.no_grad():
+        hm = pose_net(torch.from_numpy(crops)).numpy()
+    centers, scales = boxes_to_center_scale(dets[:, :4], inp_res)
+    xy, sc = decode_oracle.final_preds(hm, centers, scales, True)
+    return dets, np.concatenate((xy, sc), axis=2).astype(np.float32), flow

@@ -214,7 +214,7 @@ def test_decode_matches_oracle_and_golden(golden):
     hm_d = hm.cuda()
     for adjust, key in ((1, "decode_coords_adjust"), (0, "decode_coords_plain")):
         kps = torch.empty(3, 17, 3, device="cuda")
-        _lib.check(L().ft_decode_keypoints(hm_d.data_ptr(), 3, 17, 64, 48, center.data_ptr(), scale.data_ptr(), adjust, 0.0, kps.data_ptr(), gpu_util.sp()), "decode")
+        _lib.check(L().ft_decode_keypoints(hm_d.data_ptr(), 3, 17, 64, 48, center.data_ptr(), scale.data_ptr(), adjust, 0.0, None, kps.data_ptr(), gpu_util.sp()), "decode")
         kps = kps.cpu().numpy()
         np.testing.assert_allclose(kps[:, :, :2], golden[key], atol=2e-3)          # fixtures made by the real final_preds
         np.testing.assert_array_equal(kps[:, :, 2:], golden["decode_scores"])
@@ -227,7 +227,7 @@ def test_decode_matches_oracle_and_golden(golden):
     one = torch.tensor([[3.0, 2.0]]).cuda()
     sc = torch.tensor([4.0]).cuda()                                                # s = h/scale = 1 -> identity + offset
     flat_d = flat.cuda()
-    _lib.check(L().ft_decode_keypoints(flat_d.data_ptr(), 1, 1, 4, 6, one.data_ptr(), sc.data_ptr(), 0, 0.0, kps.data_ptr(), gpu_util.sp()), "decode")
+    _lib.check(L().ft_decode_keypoints(flat_d.data_ptr(), 1, 1, 4, 6, one.data_ptr(), sc.data_ptr(), 0, 0.0, None, kps.data_ptr(), gpu_util.sp()), "decode")
     assert kps.cpu().tolist() == [[[2.0, 1.0, 1.0]]]
 
 
