@@ -499,8 +499,12 @@ def parity_check(torch, cfg, pipe, pose, flow, video, state):
            "people": int(g_count[0]), "people_oracle": int(m),
            "box_max_px": float(np.abs(g_dets[0, :m, :4] - w_dets[:, :4]).max()) if m else 0.0,
            "keypoint_max_px": float(np.abs(g_kps[0, :m, :, :2] - w_kps[:, :, :2]).max()) if m else 0.0,
-           "tolerance": {"heatmap_max_abs": 1e-3, "flow_max_abs_rel": 1e-3, "keypoint_px": 1.0}}
-    res["ok"] = bool(res["heatmap_max_abs"] < 1e-3 and res["flow_max_abs"] <= 1e-3 * max(1.0, res["flow_abs_max"]) and res["keypoint_max_px"] <= 1.0
+           "tolerance": {"heatmap_max_abs": 1e-3, "flow_max_abs_rel": 1e-3, "keypoint_px": 1.0,
+                         "heatmap_scale_rule": "1e-3 holds at the calibrated heat-map magnitude (abs-max <= 4, SURVEY.md 8d); the tracker feeds raw 0..255 crops "
+                                               "(pose_est, net_utils.py:48-57), which scales the synthetic heat-maps, so the bound scales with abs_max / 4"}}
+    res["heatmap_rel_to_abs_max"] = res["heatmap_max_abs"] / max(res["heatmap_abs_max"], 1e-30)
+    hm_tol = 1e-3 * max(1.0, res["heatmap_abs_max"] / 4.0)
+    res["ok"] = bool(res["heatmap_max_abs"] < hm_tol and res["flow_max_abs"] <= 1e-3 * max(1.0, res["flow_abs_max"]) and res["keypoint_max_px"] <= 1.0
                      and res["box_max_px"] <= 1.0 and res["people"] == res["people_oracle"])
     return res
 

@@ -21,7 +21,8 @@ class FtConvDesc(ctypes.Structure):
                 ("pad", ctypes.c_int32), ("cout", ctypes.c_int32), ("cout_pad", ctypes.c_int32), ("k_pad", ctypes.c_int32),
                 ("block_n", ctypes.c_int32), ("act", ctypes.c_int32), ("slope", c_float), ("precision", ctypes.c_int32),
                 ("impl", ctypes.c_int32), ("k_mode", ctypes.c_int32), ("in_xpad_l", ctypes.c_int32), ("in_xpad_r", ctypes.c_int32),
-                ("cta_pair", ctypes.c_int32), ("res_blocks", ctypes.c_int32), ("pad_hi", ctypes.c_int32), ("tile_order", ctypes.c_int32)]
+                ("cta_pair", ctypes.c_int32), ("res_blocks", ctypes.c_int32), ("pad_hi", ctypes.c_int32), ("tile_order", ctypes.c_int32),
+                ("epilogue_buffers", ctypes.c_int32)]
 
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
@@ -29,7 +30,7 @@ KIND_CONV, KIND_DECONV = 0, 1
 PREC_SPLIT, PREC_FAST = 0, 1
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
 K_PACKED, K_TAP64, K_ROW = 0, 1, 2
-ABI_VERSION = 13        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
+ABI_VERSION = 14        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
 
 # name -> (restype, argtypes): every symbol include/flowtrack_b200.h declares
 SIGNATURES = {
@@ -73,7 +74,7 @@ SIGNATURES = {
     "ft_box_propagation": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
-DEBUG_KNOBS = ("FT_DEV_SKIP", "FT_DEV_CHUNK", "FT_DEV_CORR_PARTS", "FT_DEV_CORR_VARIANT")     # ft_set_debug(which = index)
+DEBUG_KNOBS = ("FT_DEV_SKIP", "FT_DEV_CHUNK", "FT_DEV_CORR_PARTS", "FT_DEV_CORR_VARIANT", "FT_DEV_NO_PDL")     # ft_set_debug(which = index)
 _lib = None
 
 

@@ -108,17 +108,21 @@ constexpr int THREADS_TMA = (EPI_WARPS + 2) * 32, THREADS_GATHER = (EPI_WARPS + 
 constexpr int ACC_CHUNK = 4;         // split mode: k-blocks (of 64) per tensor-core accumulation chain
 constexpr int SMEM_LIMIT = 232448;   // 227 KiB opt-in maximum per CTA
 
-template <int BN, bool SPLIT, bool PAIR = false>
+template <int BN, bool SPLIT, bool PAIR = false, int NBUF = 1>
 struct Geo {
     static constexpr int PLANES = SPLIT ? 2 : 1;
     static constexpr int B_TILE = BN * BK * 2;                     // whole weight k-block of the n-tile (one plane)
     static constexpr int B_LOCAL = PAIR ? B_TILE / 2 : B_TILE;     // pair: each CTA stages its half of the BN rows
     static constexpr int STAGE = PLANES * (A_TILE + B_LOCAL);
-    // epilogue staging slab: SLAB output channels x 128 pixels x 2 planes, double buffered
+    // epilogue staging: per warp group NBUF slabs of (SLAB output channels x 128 pixels x 2 planes).  NBUF = 2 lets a group fill
+    // one slab while the TMA store of its previous slab is still reading the other (the small-K 1x1 layers are bound by the
+    // epilogue's store hand-off chain, not by the tensor pipe); it costs 32 KiB of shared memory, i.e. a pipeline stage.
     static constexpr int SLAB = BN >= 64 ? 32 : 16;
     static constexpr int SLAB_PLANE = BM * SLAB * 2;
-    static constexpr int STAGING = 2 * 2 * SLAB_PLANE;
-    static constexpr int FIXED = 1024 /*align slack*/ + 512 /*barriers*/ + STAGING;
+    static constexpr int GROUP_STAGING = NBUF * 2 * SLAB_PLANE;
+    static constexpr int STAGING = 2 * GROUP_STAGING;
+    static constexpr int SS_BYTES = 2 * 2 * BN * 4;        // the n-tile's scale | shift, double buffered across tiles (see the epilogue)
+    static constexpr int FIXED = 1024 /*align slack*/ + 512 /*barriers*/ + SS_BYTES + STAGING;
     static_assert(STAGE % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
     static constexpr int STAGES_FIT = (SMEM_LIMIT - FIXED) / STAGE;
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
@@ -160,10 +164,10 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvK& p, int tile, int ct
 // bytes -- the main loop of the single-CTA variant is bound by shared-memory fill bandwidth (~48 B/clk/SM measured),
 // not by the tensor pipe.  CTA rank 0 (the leader) issues every MMA; the peer's MMA warp only relays "my stage is
 // full" to the leader.
-template <int BN, bool SPLIT, bool GATHER, bool PAIR>
+template <int BN, bool SPLIT, bool GATHER, bool PAIR, int NBUF = 1>
 __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv_tc_kernel(const __grid_constant__ ConvK p) {
     static_assert(!(GATHER && PAIR), "the gather variant is single-CTA");
-    using G = Geo<BN, SPLIT, PAIR>;
+    using G = Geo<BN, SPLIT, PAIR, NBUF>;
     const int cta_rank = PAIR ? (int)cluster_ctarank() : 0;
     const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // pair: a cluster owns a tile
     const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -178,6 +182,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
     auto acce_bar = [&](int a) { return bar_base + 8u * (2 * G::STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * G::STAGES + 4);
     auto peer_full_bar = [&](int s) { return bar_base + 8u * (2 * G::STAGES + 5 + s); };   // leader only: the peer's stage s is full
+    const uint32_t ss_base = bar_base + 512u;            // [2 tile parities][scale BN | shift BN] floats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -207,6 +212,10 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
     __syncthreads();
     if (PAIR) cluster_sync_all();          // both CTAs' barriers exist before any cross-CTA arrive / multicast commit
     tc_fence_after();
+    // PDL: this CTA is set up -- let the next kernel of the stream take SMs as they free up, then wait until the previous kernel's
+    // results are complete and visible before the first global read / write of this one (all roles, see ft_tc.cuh)
+    pdl_launch_dependents();
+    pdl_wait();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -398,12 +407,24 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         const int group = warp >> 2, quarter = warp & 3;      // TMEM lanes [32*quarter, +32) are this warp's
         const bool leader = (threadIdx.x & 127) == 0;         // issues this group's TMA stores
         const int row = quarter * 32 + lane;
-        const uint32_t buf = staging + (uint32_t)group * (2 * G::SLAB_PLANE);   // one staging slab (hi | lo) per group
+        const uint32_t buf0 = staging + (uint32_t)group * G::GROUP_STAGING;     // NBUF staging slabs (hi | lo) per group
         constexpr int MINE = (NSLAB + 1) / 2;         // slabs per group
         int acc_it = 0;
+        uint32_t slab_it = 0;                         // slabs this group has staged so far (selects the ping-pong buffer)
+        uint32_t tile_it = 0;
         const uint32_t acce_remote0 = PAIR ? map_to_cta(acce_bar(0), 0) : 0u;     // the leader's acc_empty barriers, as cluster addresses
-        for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+        for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++tile_it) {
             const TileCoord tc = tile_coord<GATHER, PAIR>(p, tile, cta_rank);
+            // This n-tile's scale / shift go through shared memory: every lane needs the same 2*BN values, so the epilogue reads
+            // them as broadcast LDS instead of four LDG.128 per 8 channels whose latency sat in front of every FFMA (long-scoreboard
+            // stalls were ~20 % of the epilogue warps' samples).  Double buffered by tile parity; the barrier below orders tile i's
+            // readers before tile i+2's writers.
+            const uint32_t ss = ss_base + (tile_it & 1u) * (uint32_t)(2 * BN * 4);
+            for (int e = threadIdx.x; e < 2 * BN; e += EPI_THREADS) {
+                const int c = tc.nt * BN + (e < BN ? e : e - BN);
+                const float v = c < p.cout_pad ? __ldg((e < BN ? p.scale : p.shift) + c) : 0.f;
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(ss + 4u * e), "f"(v) : "memory");
+            }
             bool valid;
             int n, oy, ox;
             if (GATHER) {
@@ -459,6 +480,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                 if (PAIR) mbar_arrive_remote(acce_remote0 + 8u * a);   // leader's barrier counts the epilogue threads of both CTAs
                 else mbar_arrive(acce_bar(a));        // this thread is done with the TMEM stage
             }
+            named_bar_sync(3, EPI_THREADS);           // scale/shift of this tile are staged (all eight epilogue warps)
             // ---- finalize: scale/shift, activation, split, store ----
 #pragma unroll
             for (int j = 0; j < MINE; ++j) {
@@ -470,10 +492,12 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                 for (int g8 = 0; g8 < SLAB / 8; ++g8) {
                     const int c0 = cbase + g8 * 8;
                     if (c0 < p.cout_p8) {
-                        const float4 sc0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0)), sc1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
-                        const float4 sh0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0)), sh1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
-                        const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-                        const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+                        float scv[8], shv[8];
+                        const uint32_t so = ss + 4u * (uint32_t)(cc * SLAB + g8 * 8);
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(scv[0]), "=f"(scv[1]), "=f"(scv[2]), "=f"(scv[3]) : "r"(so));
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(scv[4]), "=f"(scv[5]), "=f"(scv[6]), "=f"(scv[7]) : "r"(so + 16u));
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(shv[0]), "=f"(shv[1]), "=f"(shv[2]), "=f"(shv[3]) : "r"(so + 4u * BN));
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(shv[4]), "=f"(shv[5]), "=f"(shv[6]), "=f"(shv[7]) : "r"(so + 4u * BN + 16u));
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             // branch-free activation: max(v, s*v) with s = 1 (none), 0 (ReLU), slope (LeakyReLU, 0 <= slope <= 1)
@@ -488,8 +512,10 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                     }
                 }
                 if (p.out_hi) {
-                    // the TMA store that last read this group's staging slab must have drained it
-                    if (leader) bulk_wait_read<0>();
+                    // the TMA store that last read this staging slab must have drained it (NBUF = 2: the store before the last one)
+                    const uint32_t buf = buf0 + (NBUF > 1 ? (slab_it & 1u) * (2 * G::SLAB_PLANE) : 0u);
+                    ++slab_it;
+                    if (leader) bulk_wait_read<NBUF - 1>();
                     named_bar_sync(1 + group, 128);
 #pragma unroll
                     for (int g8 = 0; g8 < SLAB / 8; ++g8) {
@@ -567,31 +593,37 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvK p) {
     }
 }
 
-template <int BN, bool SPLIT, bool GATHER, bool PAIR>
+template <int BN, bool SPLIT, bool GATHER, bool PAIR, int NBUF = 1>
 static int launch_tc(const ConvK& k, cudaStream_t s) {
-    using G = Geo<BN, SPLIT, PAIR>;
+    using G = Geo<BN, SPLIT, PAIR, NBUF>;
     static bool attr_set[MAX_DEVICES];   // per instantiation and device
-    if (ensure_dyn_smem(conv_tc_kernel<BN, SPLIT, GATHER, PAIR>, G::SMEM, attr_set, "conv_tc_kernel")) return 1;
+    if (ensure_dyn_smem(conv_tc_kernel<BN, SPLIT, GATHER, PAIR, NBUF>, G::SMEM, attr_set, "conv_tc_kernel")) return 1;
     const int sms = device_sms();
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (!dev_knob(FT_DBG_NO_PDL)) {      // programmatic dependent launch: see pdl_wait() in the kernel
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     if (PAIR) {
         // one cluster of two CTAs (the two SMs of a TPC) per tile; k.num_tiles already counts pair tiles
         const int clusters = k.num_tiles < sms / 2 ? k.num_tiles : sms / 2;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(THREADS_TMA), cfg.dynamicSmemBytes = G::SMEM, cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr, cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, GATHER, PAIR>, k);
-        if (e != cudaSuccess) {
-            set_error("conv_tc_kernel<%d,%d,pair>: cluster launch failed: %s", BN, (int)SPLIT, cudaGetErrorString(e));
-            return 1;
-        }
-        return check_launch("conv_tc_kernel(pair)");
+        cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(THREADS_TMA);
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+        ++na;
+    } else {
+        cfg.gridDim = dim3(k.num_tiles < sms ? k.num_tiles : sms), cfg.blockDim = dim3(GATHER ? THREADS_GATHER : THREADS_TMA);
     }
-    const int grid = k.num_tiles < sms ? k.num_tiles : sms;
-    conv_tc_kernel<BN, SPLIT, GATHER, PAIR><<<grid, GATHER ? THREADS_GATHER : THREADS_TMA, G::SMEM, s>>>(k);
-    return check_launch("conv_tc_kernel");
+    cfg.dynamicSmemBytes = G::SMEM, cfg.stream = s, cfg.attrs = attr, cfg.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, GATHER, PAIR, NBUF>, k);
+    if (e != cudaSuccess) {
+        set_error("conv_tc_kernel<%d,%d,%d,%d>: launch failed: %s", BN, (int)SPLIT, (int)GATHER, (int)PAIR, cudaGetErrorString(e));
+        return 1;
+    }
+    return check_launch(PAIR ? "conv_tc_kernel(pair)" : "conv_tc_kernel");
 }
 
 static int check_view(const ft_act& a, const char* name) {
@@ -830,6 +862,9 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     }
     k.rev = d->tile_order != 0;
     const bool pair = d->cta_pair != 0;
+    const bool epi2 = d->epilogue_buffers == 2;
+    FT_REQUIRE(d->epilogue_buffers >= 0 && d->epilogue_buffers <= 2 && (!epi2 || (BN >= 64 && BN <= 128 && !gather)),
+               "conv2d: epilogue_buffers must be 0/1 or 2 (2: TMA variant with block_n 64 or 128)");
     FT_REQUIRE(!pair || (!gather && BN >= 64), "conv2d: cta_pair needs the TMA variant and block_n >= 64");
     k.num_tiles = k.n_phase * (pair ? (k.m_tiles + 1) / 2 : k.m_tiles) * k.n_tiles;
     k.fd_n_tiles = make_fastdiv(k.n_tiles), k.fd_m_units = make_fastdiv(pair ? (k.m_tiles + 1) / 2 : k.m_tiles);
@@ -841,6 +876,10 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
         return split ? launch_tc<BN_, true, false, false>(k, s) : launch_tc<BN_, false, false, false>(k, s);
 #define FT_CASE_PAIR(BN_)                                                                                                     \
     case BN_:                                                                                                                 \
+        if (epi2 && !gather) {                                                                                                \
+            if (pair) return split ? launch_tc<BN_, true, false, true, 2>(k, s) : launch_tc<BN_, false, false, true, 2>(k, s);   \
+            return split ? launch_tc<BN_, true, false, false, 2>(k, s) : launch_tc<BN_, false, false, false, 2>(k, s);        \
+        }                                                                                                                     \
         if (pair) return split ? launch_tc<BN_, true, false, true>(k, s) : launch_tc<BN_, false, false, true>(k, s);          \
         if (gather) return split ? launch_tc<BN_, true, true, false>(k, s) : launch_tc<BN_, false, true, false>(k, s);        \
         return split ? launch_tc<BN_, true, false, false>(k, s) : launch_tc<BN_, false, false, false>(k, s);
@@ -849,7 +888,9 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
         FT_CASE(32)
         FT_CASE_PAIR(64)
         FT_CASE_PAIR(128)
-        FT_CASE_PAIR(256)
+        case 256:      // CTA pairs only (a single CTA could not hold two stages of a 256-wide weight tile), no ping-pong staging
+            FT_REQUIRE(pair, "conv2d: block_n 256 needs cta_pair");
+            return split ? launch_tc<256, true, false, true>(k, s) : launch_tc<256, false, false, true>(k, s);
     }
 #undef FT_CASE
 #undef FT_CASE_PAIR

@@ -78,6 +78,13 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// as soon as every CTA of its predecessor in the stream has executed pdl_launch_dependents() (or exited): its CTAs take the
+// SMs the predecessor's tail has already left and run their prologue (barrier init, TMEM allocation, descriptor set-up) under
+// the predecessor's last tiles.  pdl_wait() blocks until the predecessor grid has COMPLETED and its memory is visible; every
+// global read of activations and every global write comes after it.  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }

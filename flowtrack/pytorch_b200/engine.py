@@ -297,7 +297,9 @@ class ConvLayer:
         d.out = out.struct() if out is not None else NULL_ACT
         d.res = res.struct() if res is not None else NULL_ACT
         d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
-        bn, pair = tiling if tiling is not None else self.choose_tiling(x.n, x.h, x.w, precision)
+        tiling = tiling if tiling is not None else self.choose_tiling(x.n, x.h, x.w, precision)
+        bn, pair = tiling[0], tiling[1]
+        d.epilogue_buffers = tiling[2] if len(tiling) > 2 else 1
         d.w_tile, d.w_gemm = self.tile_image(bn).data_ptr(), self.w_gemm.data_ptr()
         d.scale, d.shift = self.scale.data_ptr(), self.shift.data_ptr()
         d.kind, d.kh, d.kw, d.stride, d.pad = self.kind, self.kh, self.kw, self.stride, self.pad
@@ -408,6 +410,8 @@ class Plan:
         self.graph = None
         self.taps = {}       # name -> Act / tensor, for layer-by-layer tests
         self.flops = {}      # call index -> algorithmic FLOPs (convolutions only)
+        self._conv_args = {}  # call index -> (layer, x, out, out_f32, res): what autotune() rebuilds a descriptor from
+        self.tuned = {}      # call index -> (block_n, cta_pair, us) chosen by autotune()
         self.alternate_tile_order = os.environ.get("FT_TILE_ORDER", "alternate") == "alternate"
         self._rev = 0        # tile order of the next convolution (alternates: a consumer starts where its producer ended, in L2)
 
@@ -427,6 +431,7 @@ class Plan:
             d.tile_order = self._rev
             self._rev ^= 1
         self.calls.append(("conv2d", _lib.lib().ft_conv2d_fprop, (ctypes.byref(d),), d))
+        self._conv_args[len(self.calls) - 1] = (layer, x, out, out_f32, res)
         self.flops[len(self.calls) - 1] = layer.flops(x.n, x.h, x.w)
         if name:
             self.taps[name] = out if out is not None else out_f32
@@ -480,6 +485,67 @@ class Plan:
                 for i in range(n):
                     tot[i] += ev[i].elapsed_time(ev[i + 1])
         return [t / reps for t in tot]
+
+    def autotune(self, launches=4):
+        """Pick the tile shape of every tensor-core convolution of the plan by measurement on this GPU and this batch shape:
+        candidates = tile widths {64, 128, 256 (pairs only)} x {single CTA, CTA pair} x {1, 2 epilogue staging buffers}; each candidate is captured as a small CUDA graph of
+        `launches` back-to-back launches on the plan's own buffers and timed with CUDA events.  Which shape wins depends on
+        how many tiles a layer has against the 148 SMs (wave quantisation) -- layer3/4 of a 64-crop batch, every layer of a
+        2-pair strong-scaling shard -- which a static rule cannot see.  Results are bit-identical across tile shapes (the K
+        order of every accumulation chain is the same); buffers hold whatever the last run left, timing does not depend on it."""
+        if self.impl != _lib.IMPL_TCGEN05 or torch.device(self.device).type != "cuda":
+            return self
+        fn = _lib.lib().ft_conv2d_fprop
+        with torch.cuda.device(self.device):
+            for i, (layer, x, out, out_f32, res) in sorted(self._conv_args.items()):
+                base = self.calls[i][3]
+                cands = []
+                for bn in (64, 128, 256):
+                    if layer.cout_pad % bn or layer.block_n < 64 or (bn > max(layer.block_n, 64) and not (bn == 256 and layer.cout >= 256)):
+                        continue
+                    for pair in (0, 1):
+                        if (pair and layer.k_mode == _lib.K_PACKED) or (bn == 256 and not pair):
+                            continue
+                        cands.append((bn, pair, 1))
+                        if layer.k_mode != _lib.K_PACKED and out is not None and bn <= 128:
+                            cands.append((bn, pair, 2))      # ping-pong epilogue staging (ft_conv_desc.epilogue_buffers)
+                if len(cands) < 2:
+                    continue
+                best = None
+                for bn, pair, nbuf in cands:
+                    d = layer.desc(x, out, out_f32, res, self.precision, self.impl, tiling=(bn, pair, nbuf))
+                    d.tile_order = base.tile_order
+                    try:
+                        s = stream_ptr()
+                        _lib.check(fn(ctypes.byref(d), s), "conv2d(autotune)")
+                        torch.cuda.synchronize()
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            s = stream_ptr()
+                            for _ in range(launches):
+                                _lib.check(fn(ctypes.byref(d), s), "conv2d(autotune)")
+                        g.replay()
+                        torch.cuda.synchronize()
+                        ts = []
+                        for _ in range(3):
+                            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            e0.record()
+                            g.replay()
+                            e1.record()
+                            torch.cuda.synchronize()
+                            ts.append(e0.elapsed_time(e1) / launches)
+                        del g
+                        t = min(ts)
+                    except RuntimeError:
+                        continue
+                    if best is None or t < best[0]:
+                        best = (t, bn, pair, nbuf, d)
+                if best is not None:
+                    t, bn, pair, nbuf, d = best
+                    self.calls[i] = ("conv2d", fn, (ctypes.byref(d),), d)
+                    self.tuned[i] = (bn, pair, t * 1e3, nbuf)
+        self.graph = None
+        return self
 
     def time_calls_graphed(self, reps=5):
         """Per-call device time in ms measured INSIDE a CUDA-graph replay: the plan is captured with an external

@@ -9,6 +9,8 @@ state_dict keys equal the reference's (`conv1.0.weight`, `deconv5.0.bias`, `pred
 Inference only: eval-mode outputs (the full-resolution flow); the training tuple (flow2..flow6) is out of scope.
 args.fp16 must be False -- the path computes in split-fp16 (fp32-grade) or, with precision='fast', fp16 operands.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -85,6 +87,8 @@ class _FlowBase(nn.Module):
             else:
                 pair = p.f32(B, 3, 2, H, W)
             out = self._build(p, self._layers, pair, B, H, W)
+            if os.environ.get("FT_AUTOTUNE", "1") != "0":
+                p.autotune()                         # per-layer tile shape by measurement (engine.Plan.autotune)
             self._plans[key] = (p, pair, out)
         return self._plans[key]
 

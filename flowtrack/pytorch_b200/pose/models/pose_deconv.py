@@ -169,6 +169,8 @@ class DeconvResnet(nn.Module):
         key = (B, H, W, prec, self._impl, device.index if device.index is not None else torch.cuda.current_device())
         if key not in self._plans:
             self._plans[key] = self._build_plan(B, H, W, device, prec, self._impl)
+            if os.environ.get("FT_AUTOTUNE", "1") != "0":
+                self._plans[key][0].autotune()       # per-layer tile shape by measurement (engine.Plan.autotune)
         return self._plans[key]
 
     def _plan(self, x):

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 13
+#define FT_ABI_VERSION 14
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -119,6 +119,10 @@ typedef struct {
     int32_t tile_order;     /* 0: the persistent CTAs walk the output tiles first image -> last image, 1: last -> first.
                                A layer that runs in the opposite order of its producer starts on the part of its
                                input that is still in the 126 MB L2 (engine.py alternates the order along a plan). */
+    int32_t epilogue_buffers; /* 0 / 1: one staging slab per epilogue warp group; 2: two (ping-pong: a group fills one slab while
+                               the TMA store of its previous slab still reads the other).  2 costs 32 KiB of shared memory =
+                               one pipeline stage, and pays on the small-K 1x1 layers whose time is the epilogue's store
+                               hand-off chain.  block_n 64 / 128, TMA variants only; engine.Plan.autotune() chooses.        */
 } ft_conv_desc;
 
 int         ft_abi_version(void);
@@ -129,7 +133,8 @@ const char* ft_last_error(void);
 long long   ft_launch_count(void);
 void        ft_reset_launch_count(void);
 /* Development knobs for the profiling experiments under tools/dev (0 = skip mask of the conv / correlation kernels,
- * 1 = accumulation chunk, 2 = correlation parts, 3 = correlation kernel variant).  All zero by default; the library
+ * 1 = accumulation chunk, 2 = correlation parts, 3 = correlation kernel variant, 4 = no programmatic dependent launch).
+ * All zero by default; the library
  * never reads the environment.  Results under a non-zero skip mask are garbage by design.                          */
 int         ft_set_debug(int which, int value);
 

@@ -8,6 +8,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# the per-layer tile autotuner (engine.Plan.autotune) costs ~1 s per plan; the suite builds dozens of small plans, so it is
+# off by default here and exercised by tests/test_gpu_conv.py::test_autotune_* explicitly
+os.environ.setdefault("FT_AUTOTUNE", "0")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 

@@ -244,3 +244,63 @@ def test_stem_space_to_depth_path(shape):
         scale = max(1.0, ref.abs().max().item())
         assert (f32.cpu() - ref).abs().max() < tol * scale
         assert (out.to_nchw(64).cpu() - ref).abs().max() < tol * scale
+
+
+def test_autotune_picks_tilings_and_keeps_results_bit_identical(monkeypatch):
+    """engine.Plan.autotune: per-layer (block_n, cta_pair) chosen by timing; the forward is bit-identical to the untuned plan."""
+    from flowtrack.pytorch_b200.pose import models as pose_models
+    from flowtrack.pytorch_b200.tracking import synthetic
+    torch.manual_seed(0)
+    m = synthetic.condition_pose_weights(pose_models.deconv("resnet50", 17, False), 0).cuda()
+    x = torch.randn(4, 3, 128, 96, generator=torch.Generator().manual_seed(2)).cuda()
+    monkeypatch.setenv("FT_AUTOTUNE", "0")
+    a = m(x).clone()
+    monkeypatch.setenv("FT_AUTOTUNE", "1")
+    m.refresh()
+    b = m(x).clone()
+    plan = next(iter(m._plans.values()))[0]
+    assert len(plan.tuned) > 40 and all(bn in (64, 128, 256) and pair in (0, 1) and us > 0 and nbuf in (1, 2) for bn, pair, us, nbuf in plan.tuned.values())
+    assert torch.equal(a, b)
+
+
+def test_pdl_off_gives_identical_results():
+    """Programmatic dependent launch only changes when a kernel's prologue runs: FT_DBG_NO_PDL (ft_set_debug(4, 1)) is bit-identical."""
+    from flowtrack.pytorch_b200.pose import models as pose_models
+    from flowtrack.pytorch_b200.tracking import synthetic
+    torch.manual_seed(0)
+    m = synthetic.condition_pose_weights(pose_models.deconv("resnet50", 17, False), 0).cuda()
+    x = torch.randn(3, 3, 128, 96, generator=torch.Generator().manual_seed(3)).cuda()
+    a = m(x).clone()
+    try:
+        _lib.lib().ft_set_debug(4, 1)
+        m.refresh()
+        b = m(x).clone()
+    finally:
+        _lib.lib().ft_set_debug(4, 0)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("bn,pair", [(64, 0), (64, 1), (128, 0), (128, 1)])
+def test_ping_pong_epilogue_staging_is_bit_identical(bn, pair):
+    """ft_conv_desc.epilogue_buffers = 2 (two staging slabs per epilogue warp group) changes scheduling only: same bits as 1,
+    on a many-tile 1x1 + residual layer (every staging buffer wraps several times per CTA) and on a 3x3 layer."""
+    g = torch.Generator().manual_seed(21)
+    conv = nn.Conv2d(64, 256, 1, bias=False)
+    bnm = nn.BatchNorm2d(256).eval()
+    with torch.no_grad():
+        bnm.weight.copy_(torch.rand(256, generator=g) * 0.2 + 0.1)
+        bnm.running_var.copy_(torch.rand(256, generator=g) + 0.5)
+    x, r = torch.randn(40, 64, 32, 24, generator=g), torch.randn(40, 256, 32, 24, generator=g)      # 240 m-tiles x 2-4 n-tiles
+    layer = engine.conv_from_modules(conv, bnm, _lib.ACT_RELU, device="cuda", residual=True)
+    xa, ra = gpu_util.pack_nchw(x.cuda()), gpu_util.pack_nchw(r.cuda())
+    a = gpu_util.run_layer(layer, xa, res=ra, tiling=(bn, pair, 1))
+    b = gpu_util.run_layer(layer, xa, res=ra, tiling=(bn, pair, 2))
+    assert torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)
+    with torch.no_grad():
+        ref = torch.relu(bnm(conv(x)) + r)
+    assert (b.to_nchw().cpu() - ref).abs().max() <= 2e-5 * ref.abs().max()
+    conv3 = nn.Conv2d(64, 128, 3, 1, 1)
+    layer3 = engine.conv_from_modules(conv3, None, _lib.ACT_LEAKY, device="cuda")
+    a = gpu_util.run_layer(layer3, xa, tiling=(bn, pair, 1))
+    b = gpu_util.run_layer(layer3, xa, tiling=(bn, pair, 2))
+    assert torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)

@@ -15,14 +15,14 @@ which = sys.argv[1] if len(sys.argv) > 1 else "both"
 prec = sys.argv[2] if len(sys.argv) > 2 else "split"
 PB = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 FB = int(sys.argv[4]) if len(sys.argv) > 4 else 16
-PEAK = 1662.1
+PEAK = 1630.9    # measured burst bf16 TFLOP/s (MEASURED_PEAKS.json)
 
 
 def table(name, plan):
     for _ in range(2):
         plan.enqueue()
     torch.cuda.synchronize()
-    per = plan.time_calls(reps=5)
+    per = plan.time_calls_graphed(reps=5) if os.environ.get("LT_GRAPHED", "1") != "0" else plan.time_calls(reps=5)
     tot = sum(per)
     tot_fl = 0.0
     print("== %s (%s): %d calls, %.3f ms summed" % (name, prec, len(per), tot))
@@ -33,8 +33,8 @@ def table(name, plan):
             tot_fl += fl
             M = d.in_.n * (d.in_.h * d.in_.w if d.kind else ((d.in_.h + 2 * d.pad - d.kh) // d.stride + 1) * ((d.in_.w + 2 * d.pad - d.kw) // d.stride + 1))
             tiles = (4 if d.kind else 1) * ((M + 127) // 128) * (d.cout_pad // d.block_n)
-            print("%3d %-6s k%d s%d cin_p=%-4d cout=%-4d in=%3dx%-3d M=%-7d BN=%-3d%s kpad=%-5d tiles=%-5d %8.1f us %7.1f TF/s alg (%4.1f%% of peak)"
-                  % (i, "deconv" if d.kind else "conv", d.kh, d.stride, d.in_.c, d.cout, d.in_.h, d.in_.w, M, d.block_n, "P" if d.cta_pair else " ", d.k_pad, tiles,
+            print("%3d %-6s k%d s%d cin_p=%-4d cout=%-4d in=%3dx%-3d M=%-7d BN=%-3d%-2s kpad=%-5d tiles=%-5d %8.1f us %7.1f TF/s alg (%4.1f%% of peak)"
+                  % (i, "deconv" if d.kind else "conv", d.kh, d.stride, d.in_.c, d.cout, d.in_.h, d.in_.w, M, d.block_n, ("P" if d.cta_pair else " ") + ("2" if d.epilogue_buffers == 2 else " "), d.k_pad, tiles,
                      per[i] * 1e3, fl / per[i] / 1e9, fl / per[i] / 1e9 / PEAK * 100))
         else:
             print("%3d %-40s %8.1f us" % (i, what, per[i] * 1e3))
