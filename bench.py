@@ -301,17 +301,14 @@ def run_ours(args):
 
     def make_steps(p):
         def device_step():
-            p.step_device()
-            with torch.cuda.stream(p.s_tail):            # the collective follows the tail that produced the records
-                return pl.gather_keypoints(p.keypoints), pl.gather_keypoints(p.dets)
+            return p.gather(p.step_device())             # one all-gather of the step's packed records, on its own stream behind the tail
         pending = []
 
         def host_step():
             # pipelined host API: submit this step (pinned uint8 frames -> device on the copy stream, flow graph, tail graph, results ->
             # pinned host), then collect the previous step: every step's copies are inside the timed region
             pending.append(p.submit())
-            with torch.cuda.stream(p.s_tail):
-                out = (pl.gather_keypoints(p.keypoints), pl.gather_keypoints(p.dets))
+            out = p.gather(pending[-1])
             if len(pending) > 1:
                 p.collect(pending.pop(0))
             return out

@@ -85,6 +85,11 @@ struct alignas(64) ConvK {
     int rev;        // tile_order: walk the tile list from the end (see ft_conv_desc.tile_order)
     int dbg_skip;   // bring-up/profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no weight loads, 4 = no MMAs, 8 = no TMA stores (results are garbage)
     int M, m_tiles, n_tiles, num_tiles;
+    // split-K (ft_conv_desc.splitk): a work item is (tile, k-split); items = num_tiles * splits, item -> split = item / num_tiles
+    int splits, kb_split, num_items;
+    FastDiv fd_num_tiles;
+    float* sk_ws;            // partial accumulators [cta tile][split][BN columns][128 rows] fp32
+    unsigned* sk_cnt;        // arrivals per cta tile (zero between launches: the last arriver resets its slot)
     int bw, bh, bn, lg_bw, lg_bh, tiles_w, tiles_h;
     int act;
     float slope;
@@ -122,7 +127,7 @@ struct Geo {
     static constexpr int GROUP_STAGING = NBUF * 2 * SLAB_PLANE;
     static constexpr int STAGING = 2 * GROUP_STAGING;
     static constexpr int SS_BYTES = 2 * 2 * BN * 4;        // the n-tile's scale | shift, double buffered across tiles (see the epilogue)
-    static constexpr int FIXED = 1024 /*align slack*/ + 512 /*barriers*/ + SS_BYTES + STAGING;
+    static constexpr int FIXED = 1024 /*align slack*/ + 512 /*barriers*/ + SS_BYTES + 16 /*split-K flag*/ + STAGING;
     static_assert(STAGE % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
     static constexpr int STAGES_FIT = (SMEM_LIMIT - FIXED) / STAGE;
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
@@ -156,6 +161,20 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvK& p, int tile, int ct
         t.n0 = r3 * p.bn;
     }
     return t;
+}
+
+// Work item -> (tile, k-block range).  Without split-K an item is a whole tile.  With it, the `splits` parts of a tile are
+// `num_tiles` items apart, so they run on different CTAs at the same time and a layer with fewer tiles than SMs still fills the GPU.
+struct Item {
+    int tile, sp, kb_lo, kb_hi;
+};
+__device__ __forceinline__ Item work_item(const ConvK& p, int item) {
+    Item w;
+    w.sp = p.splits > 1 ? fdiv(item, p.fd_num_tiles) : 0;
+    w.tile = item - w.sp * p.num_tiles;
+    w.kb_lo = w.sp * p.kb_split;
+    w.kb_hi = min(w.kb_lo + p.kb_split, p.kb_total);
+    return w;
 }
 
 // PAIR: two CTAs of a cluster (the two SMs of a TPC) work on one 256-pixel x BN tile with tcgen05.mma.cta_group::2:
@@ -225,12 +244,13 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         // compiler wraps every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST sequence (~100 cycles each)
         if (!GATHER) {
             int it = 0;
-            for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
-                const TileCoord tc = tile_coord<false, PAIR>(p, tile, cta_rank);
+            for (int item = first_tile; item < p.num_items; item += tile_step) {
+                const Item wi = work_item(p, item);
+                const TileCoord tc = tile_coord<false, PAIR>(p, wi.tile, cta_rank);
                 // weight image: per (phase, n_tile, k_block) [hi | lo][BN rows][64]; a pair CTA copies rows [rank*BN/2, +BN/2) of each plane
                 const uint8_t* wsrc = p.w_tile + ((size_t)(tc.phase * p.n_tiles + tc.nt) * p.kb_total) * (size_t)(2 * G::B_TILE) + (size_t)cta_rank * G::B_LOCAL;
-                int tap = 0, cblk = 0;
-                for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
+                int tap = wi.kb_lo / p.cb, cblk = wi.kb_lo - tap * p.cb;          // (tap, channel block) of the first k-block of this item
+                for (int kb = wi.kb_lo; kb < wi.kb_hi; ++kb, ++it) {
                     const int s = it % G::STAGES;
                     mbar_wait(empty_bar(s), ((it / G::STAGES) & 1) ^ 1);
                     const uint32_t stage = smem_base + s * G::STAGE;
@@ -339,17 +359,18 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         if (cta_rank == 0) {          // whole warp, warp-uniform values; one elected lane issues (see the TMA producer)
             constexpr uint32_t idesc = f16_idesc(PAIR ? 2 * BM : BM, BN);
             int it = 0, acc_it = 0;                     // k-block and accumulator-stage counters (across tiles)
-            for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+            for (int item = first_tile; item < p.num_items; item += tile_step) {
+                const Item wi = work_item(p, item);
                 // The tensor core truncates (rounds toward zero) when it adds to the fp32 accumulator, a bias that grows
                 // with the length of the chain.  Split mode therefore accumulates at most `chunk` k-blocks per TMEM
                 // stage and lets the epilogue warps add the chunks in registers with round-to-nearest.
-                for (int kb0 = 0; kb0 < p.kb_total; kb0 += p.chunk, ++acc_it) {
+                for (int kb0 = wi.kb_lo; kb0 < wi.kb_hi; kb0 += p.chunk, ++acc_it) {
                     const int a = acc_it & 1;
                     if (PAIR) mbar_wait_cluster(acce_bar(a), ((acc_it >> 1) & 1) ^ 1);
                     else mbar_wait(acce_bar(a), ((acc_it >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
-                    const int kb1 = min(kb0 + p.chunk, p.kb_total);
+                    const int kb1 = min(kb0 + p.chunk, wi.kb_hi);
                     for (int kb = kb0; kb < kb1; ++kb, ++it) {
                         const int s = it % G::STAGES;
                         mbar_wait(full_bar(s), (it / G::STAGES) & 1);
@@ -391,12 +412,14 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         } else if (PAIR && lane == 0) {
             // peer CTA: tell the leader's MMA thread when this CTA's half of a stage has landed
             int it = 0;
-            for (int tile = first_tile; tile < p.num_tiles; tile += tile_step)
-                for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
+            for (int item = first_tile; item < p.num_items; item += tile_step) {
+                const Item wi = work_item(p, item);
+                for (int kb = wi.kb_lo; kb < wi.kb_hi; ++kb, ++it) {
                     const int s = it % G::STAGES;
                     mbar_wait(full_bar(s), (it / G::STAGES) & 1);
                     mbar_arrive_remote(map_to_cta(peer_full_bar(s), 0));
                 }
+            }
         }
     } else {
         // =========================== epilogue (warps 0-7) ===========================
@@ -413,8 +436,9 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         uint32_t slab_it = 0;                         // slabs this group has staged so far (selects the ping-pong buffer)
         uint32_t tile_it = 0;
         const uint32_t acce_remote0 = PAIR ? map_to_cta(acce_bar(0), 0) : 0u;     // the leader's acc_empty barriers, as cluster addresses
-        for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++tile_it) {
-            const TileCoord tc = tile_coord<GATHER, PAIR>(p, tile, cta_rank);
+        for (int item = first_tile; item < p.num_items; item += tile_step, ++tile_it) {
+            const Item wi = work_item(p, item);
+            const TileCoord tc = tile_coord<GATHER, PAIR>(p, wi.tile, cta_rank);
             // This n-tile's scale / shift go through shared memory: every lane needs the same 2*BN values, so the epilogue reads
             // them as broadcast LDS instead of four LDG.128 per 8 channels whose latency sat in front of every FFMA (long-scoreboard
             // stalls were ~20 % of the epilogue warps' samples).  Double buffered by tile parity; the barrier below orders tile i's
@@ -441,12 +465,12 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
             }
             // ---- drain the accumulator chunks of this tile into registers (fp32, round-to-nearest adds) ----
             uint32_t acc[MINE * SLAB];
-            for (int kb0 = 0; kb0 < p.kb_total; kb0 += p.chunk, ++acc_it) {
+            for (int kb0 = wi.kb_lo; kb0 < wi.kb_hi; kb0 += p.chunk, ++acc_it) {
                 const int a = acc_it & 1;
                 mbar_wait(accf_bar(a), (acc_it >> 1) & 1);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN);
-                if (kb0 == 0) {
+                if (kb0 == wi.kb_lo) {
 #pragma unroll
                     for (int j = 0; j < MINE; ++j) {
                         const int cc = group + 2 * j;
@@ -481,6 +505,47 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                 else mbar_arrive(acce_bar(a));        // this thread is done with the TMEM stage
             }
             named_bar_sync(3, EPI_THREADS);           // scale/shift of this tile are staged (all eight epilogue warps)
+            if (p.splits > 1) {
+                // ---- split-K: park this item's partial sums; the CTA whose part arrives last adds all parts (in split order, so the
+                // result does not depend on who is last) and finalizes the tile ----
+                const size_t cta_tile = (size_t)wi.tile * (PAIR ? 2 : 1) + cta_rank;
+                float* wsp = p.sk_ws + (cta_tile * p.splits + wi.sp) * (size_t)(BN * BM);
+#pragma unroll
+                for (int j = 0; j < MINE; ++j) {
+                    const int cc = group + 2 * j;
+                    if (cc < NSLAB) {
+#pragma unroll
+                        for (int i = 0; i < SLAB; ++i) wsp[(size_t)(cc * SLAB + i) * BM + row] = __uint_as_float(acc[j * SLAB + i]);   // lanes = consecutive rows: coalesced
+                    }
+                }
+                __threadfence();
+                named_bar_sync(3, EPI_THREADS);
+                if (threadIdx.x == 0) {
+                    const unsigned old = atomicAdd(p.sk_cnt + cta_tile, 1u);
+                    const unsigned last = old == (unsigned)(p.splits - 1);
+                    if (last) p.sk_cnt[cta_tile] = 0u;                          // every part has arrived: leave the slot clean for the next launch
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(ss_base + (uint32_t)G::SS_BYTES), "r"(last) : "memory");
+                }
+                named_bar_sync(3, EPI_THREADS);
+                uint32_t last;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(ss_base + (uint32_t)G::SS_BYTES));
+                if (!last) continue;                                            // warp-uniform (the whole CTA takes the same way)
+                __threadfence();
+                const float* w0 = p.sk_ws + cta_tile * p.splits * (size_t)(BN * BM);
+#pragma unroll
+                for (int j = 0; j < MINE; ++j) {
+                    const int cc = group + 2 * j;
+                    if (cc < NSLAB) {
+#pragma unroll
+                        for (int i = 0; i < SLAB; ++i) {
+                            const float* q = w0 + (size_t)(cc * SLAB + i) * BM + row;
+                            float v = __ldcg(q);
+                            for (int sp = 1; sp < p.splits; ++sp) v += __ldcg(q + (size_t)sp * (BN * BM));
+                            acc[j * SLAB + i] = __float_as_uint(v);
+                        }
+                    }
+                }
+            }
             // ---- finalize: scale/shift, activation, split, store ----
 #pragma unroll
             for (int j = 0; j < MINE; ++j) {
@@ -608,14 +673,14 @@ static int launch_tc(const ConvK& k, cudaStream_t s) {
         ++na;
     }
     if (PAIR) {
-        // one cluster of two CTAs (the two SMs of a TPC) per tile; k.num_tiles already counts pair tiles
-        const int clusters = k.num_tiles < sms / 2 ? k.num_tiles : sms / 2;
+        // one cluster of two CTAs (the two SMs of a TPC) per work item; k.num_tiles already counts pair tiles
+        const int clusters = k.num_items < sms / 2 ? k.num_items : sms / 2;
         cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(THREADS_TMA);
         attr[na].id = cudaLaunchAttributeClusterDimension;
         attr[na].val.clusterDim.x = 2, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
         ++na;
     } else {
-        cfg.gridDim = dim3(k.num_tiles < sms ? k.num_tiles : sms), cfg.blockDim = dim3(GATHER ? THREADS_GATHER : THREADS_TMA);
+        cfg.gridDim = dim3(k.num_items < sms ? k.num_items : sms), cfg.blockDim = dim3(GATHER ? THREADS_GATHER : THREADS_TMA);
     }
     cfg.dynamicSmemBytes = G::SMEM, cfg.stream = s, cfg.attrs = attr, cfg.numAttrs = na;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, GATHER, PAIR, NBUF>, k);
@@ -867,6 +932,22 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
                "conv2d: epilogue_buffers must be 0/1 or 2 (2: TMA variant with block_n 64 or 128)");
     FT_REQUIRE(!pair || (!gather && BN >= 64), "conv2d: cta_pair needs the TMA variant and block_n >= 64");
     k.num_tiles = k.n_phase * (pair ? (k.m_tiles + 1) / 2 : k.m_tiles) * k.n_tiles;
+    // split-K: `splitk` parts of every tile's K range become separate work items (see work_item / the epilogue)
+    k.splits = 1, k.kb_split = k.kb_total;
+    if (d->splitk > 1) {
+        FT_REQUIRE(!gather, "conv2d: split-K is not available for the FT_K_PACKED (gather) variant");
+        FT_REQUIRE(d->splitk <= 16 && d->splitk <= k.kb_total, "conv2d: splitk %d exceeds 16 or the %d k-blocks of this layer", d->splitk, k.kb_total);
+        k.kb_split = ceil_div(k.kb_total, d->splitk);
+        k.splits = ceil_div(k.kb_total, k.kb_split);
+        const size_t cta_tiles = (size_t)k.num_tiles * (pair ? 2 : 1);
+        FT_REQUIRE(d->splitk_ws && ((uintptr_t)d->splitk_ws & 15) == 0 && d->splitk_counters, "conv2d: split-K needs a 16-byte aligned workspace and a counter array");
+        FT_REQUIRE(d->splitk_ws_bytes >= cta_tiles * k.splits * (size_t)BN * BM * 4 && (size_t)d->splitk_counters_len >= cta_tiles,
+                   "conv2d: split-K workspace too small (need %zu bytes and %zu counters, got %llu / %d)", cta_tiles * k.splits * (size_t)BN * BM * 4, cta_tiles,
+                   (unsigned long long)d->splitk_ws_bytes, d->splitk_counters_len);
+        k.sk_ws = (float*)d->splitk_ws, k.sk_cnt = (unsigned*)d->splitk_counters;
+    }
+    k.num_items = k.num_tiles * k.splits;
+    k.fd_num_tiles = make_fastdiv(k.num_tiles > 0 ? k.num_tiles : 1);
     k.fd_n_tiles = make_fastdiv(k.n_tiles), k.fd_m_units = make_fastdiv(pair ? (k.m_tiles + 1) / 2 : k.m_tiles);
     k.fd_tiles_w = make_fastdiv(k.tiles_w > 0 ? k.tiles_w : 1), k.fd_tiles_h = make_fastdiv(k.tiles_h > 0 ? k.tiles_h : 1);
 

@@ -287,8 +287,17 @@ class ConvLayer:
             return n * ho * wo * self.flops_per_pixel
         return 2 * n * ho * wo * self.cin * self.cout * self.kh * self.kw
 
-    def desc(self, x, out=None, out_f32=None, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05, tiling=None):
-        """`tiling` = (block_n, cta_pair); default: choose_tiling() for this input shape."""
+    def tile_counts(self, n, h, w, bn, pair):
+        """(work tiles, CTA tiles) ft_conv2d_fprop cuts an n x h x w input into with tile width bn (pair: 256-pixel tiles on CTA pairs)."""
+        ho, wo = self.out_hw(h, w)
+        qh, qw = (h, w) if self.kind == _lib.KIND_DECONV else (ho, wo)
+        mt = box_tiles(qw, qh, n)
+        phases, nt = (4 if self.kind == _lib.KIND_DECONV else 1), self.cout_pad // bn
+        return phases * ((mt + 1) // 2 if pair else mt) * nt, phases * (2 * ((mt + 1) // 2) if pair else mt) * nt
+
+    def desc(self, x, out=None, out_f32=None, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05, tiling=None, splitk_ws=None):
+        """`tiling` = (block_n, cta_pair[, epilogue_buffers[, splitk]]); default: choose_tiling() for this input shape.
+        splitk > 1 needs `splitk_ws` = (uint8 workspace tensor, int32 counter tensor) owned by the caller (engine.Plan)."""
         assert x.c == self.cin_p, "input view has %d channels, layer expects %d" % (x.c, self.cin_p)
         assert (res is not None) == self.residual, "layer was packed %s residual blocks" % ("with" if self.residual else "without")
         assert (x.xl, x.xr) == self.in_xpad, "layer expects input rows padded by %s zero columns, view has %s" % (self.in_xpad, (x.xl, x.xr))
@@ -300,6 +309,11 @@ class ConvLayer:
         tiling = tiling if tiling is not None else self.choose_tiling(x.n, x.h, x.w, precision)
         bn, pair = tiling[0], tiling[1]
         d.epilogue_buffers = tiling[2] if len(tiling) > 2 else 1
+        d.splitk = tiling[3] if len(tiling) > 3 else 0
+        if d.splitk > 1:
+            ws, cnt = splitk_ws
+            d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel()
+            d.splitk_counters, d.splitk_counters_len = cnt.data_ptr(), cnt.numel()
         d.w_tile, d.w_gemm = self.tile_image(bn).data_ptr(), self.w_gemm.data_ptr()
         d.scale, d.shift = self.scale.data_ptr(), self.shift.data_ptr()
         d.kind, d.kh, d.kw, d.stride, d.pad = self.kind, self.kh, self.kw, self.stride, self.pad
@@ -491,15 +505,44 @@ class Plan:
         candidates = tile widths {64, 128, 256 (pairs only)} x {single CTA, CTA pair} x {1, 2 epilogue staging buffers}; each candidate is captured as a small CUDA graph of
         `launches` back-to-back launches on the plan's own buffers and timed with CUDA events.  Which shape wins depends on
         how many tiles a layer has against the 148 SMs (wave quantisation) -- layer3/4 of a 64-crop batch, every layer of a
-        2-pair strong-scaling shard -- which a static rule cannot see.  Results are bit-identical across tile shapes (the K
-        order of every accumulation chain is the same); buffers hold whatever the last run left, timing does not depend on it."""
+        2-pair strong-scaling shard -- which a static rule cannot see.  Layers with fewer tiles than SMs and a long K also try
+        split-K (ft_conv_desc.splitk = 2..8).  Results are bit-identical across tile shapes (the K order of every accumulation
+        chain is the same) and deterministic under split-K (parts are added in a fixed order; the chains are cut at other
+        places, so those layers differ from the unsplit result by fp32 rounding, ~1e-7 relative); buffers hold whatever the last
+        run left, timing does not depend on it.  FT_SPLITK=0 keeps split-K out of the candidates."""
         if self.impl != _lib.IMPL_TCGEN05 or torch.device(self.device).type != "cuda":
             return self
         fn = _lib.lib().ft_conv2d_fprop
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         with torch.cuda.device(self.device):
+            # one split-K workspace per plan (its layers run one after the other on one stream), sized for the largest candidate
+            need_ws = need_cnt = 0
+            plans = {}
+            for i, (layer, x, out, out_f32, res) in sorted(self._conv_args.items()):
+                plans[i] = []
+                if layer.k_mode == _lib.K_PACKED or layer.block_n < 64 or os.environ.get("FT_SPLITK", "1") == "0":
+                    continue
+                for bn in (64, 128):
+                    if layer.cout_pad % bn or bn > max(layer.block_n, 64):
+                        continue
+                    kb_total = layer.k_pad // BK + (-(-bn // BK) if layer.residual else 0)
+                    for pair in (0, 1):
+                        items, cta_tiles = layer.tile_counts(x.n, x.h, x.w, bn, pair)
+                        units = sms // 2 if pair else sms
+                        if kb_total < 8 or items >= 2.5 * units:
+                            continue                         # enough tiles to fill the GPU, or too little K to cut
+                        for sk in (2, 3, 4, 6, 8):
+                            if sk * 4 > kb_total or items * sk > 6 * units:
+                                continue
+                            plans[i].append((bn, pair, 1, sk))
+                            need_ws = max(need_ws, cta_tiles * sk * bn * 128 * 4)
+                            need_cnt = max(need_cnt, cta_tiles)
+            if need_ws:
+                self._sk_ws = (torch.empty(need_ws, dtype=torch.uint8, device=self.device), torch.zeros(need_cnt, dtype=torch.int32, device=self.device))
+                self.keep.append(self._sk_ws)
             for i, (layer, x, out, out_f32, res) in sorted(self._conv_args.items()):
                 base = self.calls[i][3]
-                cands = []
+                cands = list(plans[i])
                 for bn in (64, 128, 256):
                     if layer.cout_pad % bn or layer.block_n < 64 or (bn > max(layer.block_n, 64) and not (bn == 256 and layer.cout >= 256)):
                         continue
@@ -512,8 +555,11 @@ class Plan:
                 if len(cands) < 2:
                     continue
                 best = None
-                for bn, pair, nbuf in cands:
-                    d = layer.desc(x, out, out_f32, res, self.precision, self.impl, tiling=(bn, pair, nbuf))
+                sk = 0
+                for cand in cands:
+                    bn, pair, nbuf = cand[:3]
+                    sk = cand[3] if len(cand) > 3 else 0
+                    d = layer.desc(x, out, out_f32, res, self.precision, self.impl, tiling=(bn, pair, nbuf, sk), splitk_ws=getattr(self, "_sk_ws", None))
                     d.tile_order = base.tile_order
                     try:
                         s = stream_ptr()
@@ -539,11 +585,11 @@ class Plan:
                     except RuntimeError:
                         continue
                     if best is None or t < best[0]:
-                        best = (t, bn, pair, nbuf, d)
+                        best = (t, bn, pair, nbuf, sk, d)
                 if best is not None:
-                    t, bn, pair, nbuf, d = best
+                    t, bn, pair, nbuf, sk, d = best
                     self.calls[i] = ("conv2d", fn, (ctypes.byref(d),), d)
-                    self.tuned[i] = (bn, pair, t * 1e3, nbuf)
+                    self.tuned[i] = (bn, pair, t * 1e3, nbuf, sk)
         self.graph = None
         return self
 

@@ -21,7 +21,8 @@ returns it to the host.  Detection (Faster R-CNN) is out of scope: detector boxe
 (`max_det` per frame), exactly where process_frame merges them.
 
 Multi-GPU: videos are independent; each rank owns `shard_pairs(num_streams, rank, world)` of them, runs this
-pipeline on its shard, and `pipeline.gather_keypoints` all-gathers the per-person records once per step.
+pipeline on its shard, and `gather(lane)` all-gathers the step's packed per-person records once per step (one NCCL
+all-gather on its own stream behind the tail).
 """
 import torch
 
@@ -66,11 +67,13 @@ class TrackingPipeline:
                 ln.h_det = torch.zeros(ln.det.shape, dtype=torch.float32, pin_memory=True)
                 ln.h_det_count = torch.zeros(F, dtype=torch.int32, pin_memory=True)
                 ln.d_out, ln.h_out = torch.zeros(self.n_out, **f32), torch.zeros(self.n_out, dtype=torch.float32, pin_memory=True)
-                ln.copied, ln.flow_done, ln.done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+                ln.copied, ln.flow_done, ln.done, ln.gathered = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+                ln.g_out = None
                 ln.gf = ln.gt = None
                 ln.busy = False
                 self.lanes.append(ln)
             self.s_copy, self.s_flow, self.s_tail = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            self.s_comm = torch.cuda.Stream(device=dev)
         self._next = 0
         self.launches_per_step = 0
 
@@ -172,21 +175,41 @@ class TrackingPipeline:
                 ln.flow_done.record(self.s_flow)
             with torch.cuda.stream(self.s_tail):
                 self.s_tail.wait_event(ln.flow_done)
+                self.s_tail.wait_event(ln.gathered)                      # the lane's previous records have left for the other ranks
                 self._run_tail(ln)
                 ln.done.record(self.s_tail)
         self._next = (l + 1) % len(self.lanes)
         return l
 
+    @torch.no_grad()
+    def gather(self, lane, group=None):
+        """The single collective of the path: all-gather of the step's packed records (dets | count | key-points of
+        every person slot, `n_out` floats per rank) over NCCL, on its own stream behind the lane's tail -- it neither delays the
+        next step's kernels nor waits for them.  Returns the [world, n_out] device tensor (valid until the lane's next step), or
+        the local records as [1, n_out] when no process group is initialised."""
+        import torch.distributed as dist
+        ln = self.lanes[lane]
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return ln.d_out.view(1, -1)
+        world = dist.get_world_size(group)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.s_comm):
+            if ln.g_out is None:
+                ln.g_out = torch.empty(world, self.n_out, dtype=torch.float32, device=self.device)
+            self.s_comm.wait_event(ln.done)
+            dist.all_gather_into_tensor(ln.g_out.view(-1), ln.d_out, group=group)
+            ln.gathered.record(self.s_comm)
+        return ln.g_out
+
     def fence_in(self):
         """The pipeline's streams wait for everything enqueued so far on the caller's current stream."""
         cur = torch.cuda.current_stream(self.device)
-        for s in (self.s_copy, self.s_flow, self.s_tail):
+        for s in (self.s_copy, self.s_flow, self.s_tail, self.s_comm):
             s.wait_stream(cur)
 
     def fence_out(self):
         """The caller's current stream waits for everything the pipeline has enqueued."""
         cur = torch.cuda.current_stream(self.device)
-        for s in (self.s_copy, self.s_flow, self.s_tail):
+        for s in (self.s_copy, self.s_flow, self.s_tail, self.s_comm):
             cur.wait_stream(s)
 
     # ---- host-facing step --------------------------------------------------------------------------------
@@ -239,6 +262,7 @@ class TrackingPipeline:
                 ln.flow_done.record(self.s_flow)
             with torch.cuda.stream(self.s_tail):
                 self.s_tail.wait_event(ln.flow_done)
+                self.s_tail.wait_event(ln.gathered)
                 self._run_tail(ln)
                 ln.h_out.copy_(ln.d_out, non_blocking=True)
                 ln.done.record(self.s_tail)

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 14
+#define FT_ABI_VERSION 15
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -123,6 +123,15 @@ typedef struct {
                                the TMA store of its previous slab still reads the other).  2 costs 32 KiB of shared memory =
                                one pipeline stage, and pays on the small-K 1x1 layers whose time is the epilogue's store
                                hand-off chain.  block_n 64 / 128, TMA variants only; engine.Plan.autotune() chooses.        */
+    int32_t splitk;         /* <= 1: off.  n: the K range of every tile is cut into n parts that run as separate work items on
+                               different CTAs (a layer with fewer tiles than SMs -- layer3/4 of a small batch, every layer of a
+                               strong-scaling shard -- then still fills the GPU).  Parts park their fp32 partial sums in
+                               splitk_ws; the CTA whose part arrives last adds them in part order (deterministic) and runs the
+                               normal epilogue.  FT_K_TAP64 / FT_K_ROW only.                                                  */
+    int32_t splitk_counters_len;   /* entries of splitk_counters: >= number of CTA tiles (tiles x 2 for cta_pair)             */
+    void*   splitk_ws;      /* 16-byte aligned scratch, >= CTA tiles x parts x block_n x 128 x 4 bytes                        */
+    uint64_t splitk_ws_bytes;
+    void*   splitk_counters;/* uint32 per CTA tile, zero before the first launch (the kernel leaves them zero)               */
 } ft_conv_desc;
 
 int         ft_abi_version(void);

@@ -19,6 +19,10 @@ m.use_cuda_graph = False
 x = torch.rand(B, 3, 2, 384, 512, device="cuda") * 255
 for i in range(n):
     _lib.reset_launch_count()
+    if i == n - 1:
+        torch.cuda.profiler.start()      # `ncu --profile-from-start off` captures only this last forward (not the warm-up / autotune launches)
     m(x)
     torch.cuda.synchronize()
+    if i == n - 1:
+        torch.cuda.profiler.stop()
 print("launches per forward:", _lib.launch_count())

@@ -26,8 +26,12 @@ m.use_cuda_graph = False
 x = torch.randn(B, 3, 256, 192, device="cuda")
 for i in range(n):
     _lib.reset_launch_count()
+    if i == n - 1:
+        torch.cuda.profiler.start()      # `ncu --profile-from-start off` captures only this last forward (not the warm-up / autotune launches)
     m(x)
     torch.cuda.synchronize()
+    if i == n - 1:
+        torch.cuda.profiler.stop()
 print("launches per forward:", _lib.launch_count())
 plan = list(m._plans.values())[0][0]
 for i, c in enumerate(plan.calls):
