@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libflowtrack_b200.so")
+LIB_PATH = os.environ.get("FT_LIB_PATH") or os.path.join(HERE, "libflowtrack_b200.so")      # FT_LIB_PATH: dev A/B builds (tools/dev)
 
 c_int, c_float, c_void_p, c_ll = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong
 

@@ -61,6 +61,8 @@ struct alignas(64) CorrK {
     float* out;
     int B, H, W, C, kb;
     int a_tiles, num_tiles, parts, num_units;
+    int b_tiles, ncc;   // column tiles of 32 in1' columns; in2' column chunks per row chunk: 1 (W/2 <= 32, chunk = columns 0..31) or 2 (wide
+                        // frames: columns b0-10 .. b0+53 of the tile at b0, so that every lane's 21-wide band lies inside the two chunks)
     float inv;
     int leaky;
     int planar;     // output layout: 0 = fp32 NCHW [B,441,H,W] (the reference's), 1 = parity-planar [B,441,4,ceil(H/2),ceil(W/2)] (see ft_correlation_act)
@@ -370,14 +372,17 @@ struct CorrPairGeo {
 };
 
 struct CorrPairUnit {
-    int n, cls, py, px, a0, H2c, r_lo, c_lo, nch, part;
+    int n, cls, py, px, a0, H2c, r_lo, c_lo, nch, part, b0;
 };
 __device__ __forceinline__ CorrPairUnit corr_pair_unit(const CorrK& p, int unit, int rank) {
     CorrPairUnit t;
     const int ap_tiles = (p.a_tiles + 1) >> 1;
     const int tile = unit / p.parts;
     t.part = unit - tile * p.parts;
-    const int ap = tile % ap_tiles, r = tile / ap_tiles;
+    const int ap = tile % ap_tiles;
+    int r = tile / ap_tiles;
+    t.b0 = (r % p.b_tiles) * CORR_COLS;
+    r /= p.b_tiles;
     t.cls = r & 3, t.n = r >> 2;
     t.py = t.cls >> 1, t.px = t.cls & 1;
     const int A0 = ap * 2 * CORR_ROWS;
@@ -385,11 +390,17 @@ __device__ __forceinline__ CorrPairUnit corr_pair_unit(const CorrK& p, int unit,
     t.H2c = (p.H - t.py + 1) >> 1;
     t.r_lo = max(0, A0 - CD);
     const int r_end = min(t.H2c, A0 + 2 * CORR_ROWS + CD);
-    const int chunks = r_end > t.r_lo ? (r_end - t.r_lo + CORR_ROWS - 1) / CORR_ROWS : 0;
+    const int chunks = (r_end > t.r_lo ? (r_end - t.r_lo + CORR_ROWS - 1) / CORR_ROWS : 0) * p.ncc;    // (row chunk, column chunk) pairs, column fastest
     const int per = (chunks + p.parts - 1) / p.parts;
     t.c_lo = min(chunks, t.part * per);
     t.nch = min(chunks, t.c_lo + per) - t.c_lo;
     return t;
+}
+// chunk c of a unit -> first in2' row of the row chunk and first in2' column of the column chunk
+__device__ __forceinline__ void corr_pair_chunk(const CorrK& p, const CorrPairUnit& t, int c, int& r0, int& c0) {
+    const int j = p.ncc == 2 ? c >> 1 : c, x = p.ncc == 2 ? c & 1 : 0;
+    r0 = t.r_lo + j * CORR_ROWS;
+    c0 = p.ncc == 2 ? t.b0 - CD + CORR_COLS * x : 0;
 }
 
 template <bool SPLIT>
@@ -451,7 +462,9 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_pair_kernel(const __grid
             const CorrPairUnit t = corr_pair_unit(p, unit, rank);
             if (t.nch == 0) continue;
             for (int j = 0; j < t.nch; ++j) {
-                const int r0 = t.r_lo + (t.c_lo + j) * CORR_ROWS + 2 * rank;
+                int r0, c0;
+                corr_pair_chunk(p, t, t.c_lo + j, r0, c0);
+                r0 += 2 * rank;
                 for (int kb = 0; kb < p.kb; ++kb, ++bit) {
                     if (j == 0) {
                         mbar_wait_cluster(aempty_bar(kb), (ut & 1) ^ 1);
@@ -459,8 +472,8 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_pair_kernel(const __grid
                         if (elect_one()) {
                             mbar_arrive_expect_tx(afull_bar(kb), ldA ? (uint32_t)(G::PLANES * CORR_TILE) : 0u);
                             if (ldA) {
-                                tma_load_4d(dst, &p.a_map[t.cls][0], afull_bar(kb), kb * CORR_BK, 0, t.a0, t.n);
-                                if (SPLIT) tma_load_4d(dst + CORR_TILE, &p.a_map[t.cls][1], afull_bar(kb), kb * CORR_BK, 0, t.a0, t.n);
+                                tma_load_4d(dst, &p.a_map[t.cls][0], afull_bar(kb), kb * CORR_BK, t.b0, t.a0, t.n);
+                                if (SPLIT) tma_load_4d(dst + CORR_TILE, &p.a_map[t.cls][1], afull_bar(kb), kb * CORR_BK, t.b0, t.a0, t.n);
                             }
                         }
                         __syncwarp();
@@ -469,9 +482,9 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_pair_kernel(const __grid
                     mbar_wait_cluster(bempty_bar(s), ((bit / G::STAGES) & 1) ^ 1);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(bfull_bar(s), ldB ? (uint32_t)G::STAGE : 0u);
-                        if (ldB) {
-                            tma_load_4d(ring + s * G::STAGE, &p.b2_map[t.cls][0], bfull_bar(s), kb * CORR_BK, 0, r0, t.n);
-                            if (SPLIT) tma_load_4d(ring + s * G::STAGE + CP_HALF, &p.b2_map[t.cls][1], bfull_bar(s), kb * CORR_BK, 0, r0, t.n);
+                        if (ldB) {       // columns left of 0 / right of the sub-image are zero-filled by the TMA unit
+                            tma_load_4d(ring + s * G::STAGE, &p.b2_map[t.cls][0], bfull_bar(s), kb * CORR_BK, c0, r0, t.n);
+                            if (SPLIT) tma_load_4d(ring + s * G::STAGE + CP_HALF, &p.b2_map[t.cls][1], bfull_bar(s), kb * CORR_BK, c0, r0, t.n);
                         }
                     }
                     __syncwarp();
@@ -556,9 +569,10 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_pair_kernel(const __grid
         for (int unit = first_unit; unit < p.num_units; unit += unit_step) {
             const CorrPairUnit t = corr_pair_unit(p, unit, rank);
             const int a = t.a0 + q;
-            const int y = 2 * a + t.py, x = 2 * lane + t.px;
+            const int bcol = t.b0 + lane;                                          // this lane's in1' column
+            const int y = 2 * a + t.py, x = 2 * bcol + t.px;
             const bool valid = y < p.H && x < p.W && !(p.dbg_skip & 8);
-            float* o = p.out + (size_t)t.n * (CDS * CDS) * plane + (p.planar ? ((size_t)t.cls * H2 + a) * W2 + lane : (size_t)y * p.W + x);
+            float* o = p.out + (size_t)t.n * (CDS * CDS) * plane + (p.planar ? ((size_t)t.cls * H2 + a) * W2 + bcol : (size_t)y * p.W + x);
             if (t.part == 0) {
                 for (int tj = -CD; tj <= CD; ++tj) {              // displacement rows outside the image: zeros
                     const int row = a + tj;
@@ -571,7 +585,9 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_pair_kernel(const __grid
             }
             for (int j = 0; j < t.nch; ++j, ++acc_it) {
                 const int as = acc_it % CORR_ACC_STAGES;
-                const int r0 = t.r_lo + (t.c_lo + j) * CORR_ROWS;
+                int r0, c0;
+                corr_pair_chunk(p, t, t.c_lo + j, r0, c0);
+                const int cshift = p.ncc == 2 ? c0 - t.b0 + CD : 0;               // wide: 0 or 32 (the chunk's first band position)
                 mbar_wait_cluster(accf_bar(as), (acc_it / CORR_ACC_STAGES) & 1);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * CORR_BN);
@@ -602,8 +618,13 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_pair_kernel(const __grid
                             float* oc = o + (size_t)((tj + CD) * CDS) * plane;
 #pragma unroll
                             for (int ti = 0; ti < CDS; ++ti) {
-                                const int b2 = lane + ti - CD;
-                                float val = (b2 >= 0 && b2 < 32) ? S[b2 * 34 + lane] : 0.f;
+                                // narrow: chunk column = in2' column, b2 = b + ti - 10 (outside the chunk = outside the image: zero).
+                                // wide: the chunk starts at in2' column b0 - 10 + cshift, so b2 = lane + ti - cshift; a band position
+                                // outside this chunk belongs to the other column chunk of the row and is not written here.
+                                const int b2 = p.ncc == 2 ? lane + ti - cshift : lane + ti - CD;
+                                const bool inside = b2 >= 0 && b2 < 32;
+                                if (p.ncc == 2 && !inside) continue;
+                                float val = inside ? S[b2 * 34 + lane] : 0.f;
                                 val *= p.inv;
                                 if (p.leaky) val = val > 0.f ? val : 0.1f * val;
                                 oc[(size_t)ti * plane] = val;
@@ -629,7 +650,7 @@ static int launch_corr_pair(const CorrK& k0, cudaStream_t s) {
     static bool attr_set[MAX_DEVICES];
     if (ensure_dyn_smem(corr_pair_kernel<SPLIT>, G::SMEM, attr_set, "corr_pair_kernel")) return 1;
     CorrK k = k0;
-    k.num_units = k.B * 4 * ((k.a_tiles + 1) / 2) * k.parts;
+    k.num_units = k.B * 4 * ((k.a_tiles + 1) / 2) * k.b_tiles * k.parts;
     const int max_clusters = device_sms() / 2;
     const int clusters = k.num_units < max_clusters ? k.num_units : max_clusters;
     cudaLaunchConfig_t cfg = {};
@@ -955,8 +976,7 @@ static int check_corr_view(const ft_act& a, const char* name, bool split) {
 using namespace ft;
 
 extern "C" int ft_correlation_tc_supported(int C, int H, int W, int pad, int ksize, int max_disp, int stride1, int stride2) {
-    return pad == 20 && ksize == 1 && max_disp == 20 && stride1 == 1 && stride2 == 2 && C % 64 == 0 && C >= 64 && C <= 256 && H >= 1 && W >= 1 &&
-           (W + 1) / 2 <= CORR_COLS;
+    return pad == 20 && ksize == 1 && max_disp == 20 && stride1 == 1 && stride2 == 2 && C % 64 == 0 && C >= 64 && C <= 256 && H >= 1 && W >= 1;
 }
 
 static int correlation_act_impl(const ft_act* in1, const ft_act* in2, float* out, int fuse_leaky, int precision, int planar, void* stream);
@@ -977,13 +997,15 @@ static int correlation_act_impl(const ft_act* in1, const ft_act* in2, float* out
     if (int e = check_corr_view(*in2, "correlation_act.in2", split)) return e;
     FT_REQUIRE(in1->n == in2->n && in1->h == in2->h && in1->w == in2->w && in1->c == in2->c && in1->n > 0, "correlation_act: the two inputs differ in shape");
     FT_REQUIRE(ft_correlation_tc_supported(in1->c, in1->h, in1->w, 20, 1, 20, 1, 2),
-               "correlation_act: the tensor-core path needs C in {64,128,192,256} and W <= 64 (got C=%d H=%d W=%d)", in1->c, in1->h, in1->w);
+               "correlation_act: the tensor-core path needs C in {64,128,192,256} (got C=%d H=%d W=%d)", in1->c, in1->h, in1->w);
     CorrK k = {};
     k.out = out, k.B = in1->n, k.H = in1->h, k.W = in1->w, k.C = in1->c, k.kb = in1->c / CORR_BK;
     k.inv = 1.f / (float)k.C, k.leaky = fuse_leaky != 0, k.planar = planar;
     k.dbg_skip = dev_knob(FT_DBG_SKIP);
     const int H2 = (k.H + 1) / 2;
     k.a_tiles = ceil_div(H2, CORR_ROWS);
+    const int W2 = (k.W + 1) / 2;
+    k.b_tiles = ceil_div(W2, CORR_COLS), k.ncc = W2 > CORR_COLS ? 2 : 1;
     k.num_tiles = k.B * 4 * k.a_tiles;
     // work units: a tile's chunk list is cut into 3 parts of <= 2 chunks (each part re-loads the tile's A operand through
     // L2): whole tiles (4-6 chunks) leave the last round of the 148 persistent CTAs mostly idle.  Measured on B200 at
@@ -1018,7 +1040,7 @@ static int correlation_act_impl(const ft_act* in1, const ft_act* in2, float* out
     }
     int variant = 4;     // 4 = CTA pairs (default), 2 = single CTA with resident A, 3 = A operand in TMEM (experimental)
     if (const int v = dev_knob(FT_DBG_CORR_VARIANT)) variant = v;
-    if (k.planar) variant = 4;
+    if (k.planar || k.ncc == 2) variant = 4;      // frames wider than 64 px: only the CTA-pair kernel tiles the columns
     if (variant == 4) return split ? launch_corr_pair<true>(k, (cudaStream_t)stream) : launch_corr_pair<false>(k, (cudaStream_t)stream);
     if (variant == 3) return split ? launch_corr3<true>(k, (cudaStream_t)stream) : launch_corr3<false>(k, (cudaStream_t)stream);
     return split ? launch_corr<true>(k, (cudaStream_t)stream) : launch_corr<false>(k, (cudaStream_t)stream);

@@ -156,8 +156,8 @@ int ft_correlation_forward(const float* in1, const float* in2, float* out, int B
                            void* stream);
 /* Tensor-core cost volume (ft_corr.cu) for the FlowNetC geometry (pad 20, kernel 1, max displacement 20, stride1 1,
  * stride2 2; FlowNetC.py:33): the four stride-2 parity classes are independent stride-1 correlations, computed as
- * banded GEMMs by tcgen05 MMAs.  ft_correlation_tc_supported() != 0 when the geometry, C (64..256, multiple of 64)
- * and W (<= 64) fit that kernel.
+ * banded GEMMs by tcgen05 MMAs.  ft_correlation_tc_supported() != 0 when the geometry and C (64..256, multiple of 64)
+ * fit that kernel; maps wider than 64 pixels (frames wider than 512) are tiled in 32-column strips of every parity class.
  *   ft_correlation_act        in1/in2: split-fp16 NHWC activations (the conv stack's layout) -> out: fp32 NCHW
  *                             [B,441,H,W]; precision = FT_PREC_SPLIT (fp32-grade) | FT_PREC_FAST (fp16 operands).
  *   ft_correlation_forward_ws the reference's signature (fp32 NCHW in, like ft_correlation_forward) plus a

@@ -62,8 +62,9 @@ def _corr_ws(a, b, leaky=0, precision=_lib.PREC_SPLIT):
                                    (2, 128, 50, 64),      # H/2 not a multiple of the 4-row tile
                                    (1, 192, 2, 2)])       # one pixel per parity class
 @pytest.mark.parametrize("variant", ["4", "2", "3"], ids=["cta_pair", "single_cta", "a_in_tmem"])
-def test_correlation_tensor_core_vs_oracle(shape, variant, monkeypatch):
-    monkeypatch.setenv("FT_DEV_CORR_VARIANT", variant)       # read by the library at every call
+def test_correlation_tensor_core_vs_oracle(shape, variant, request):
+    L().ft_set_debug(3, int(variant))                        # kernel variant knob (explicit; the library never reads the environment)
+    request.addfinalizer(lambda: L().ft_set_debug(3, 0))
     assert L().ft_correlation_tc_supported(shape[1], shape[2], shape[3], 20, 1, 20, 1, 2) == 1
     g = torch.Generator().manual_seed(7 + sum(shape))
     a, b = torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)
@@ -79,6 +80,34 @@ def test_correlation_tensor_core_vs_oracle(shape, variant, monkeypatch):
     assert (fast - ref).abs().max() < 4e-3 * max(1.0, ref.abs().max().item())
     ol = _corr_ws(a.cuda(), b.cuda(), leaky=1).cpu()
     assert torch.equal(ol, torch.where(out > 0, out, 0.1 * out))
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 24, 128),     # W = 128: two 32-column strips per parity class, four column chunks
+                                   (2, 256, 96, 128),     # FlowNetC at 768x1024 frames
+                                   (1, 64, 21, 100),      # odd H, W/2 = 50: ragged last strip
+                                   (1, 64, 9, 66)])       # just past the single-strip width
+def test_correlation_tensor_core_wide_frames_vs_oracle(shape):
+    """Maps wider than 64 pixels: the CTA-pair kernel tiles every parity class in 32-column strips, each in2' row chunk as two
+    column chunks (columns b0-10 .. b0+53), every band position written by exactly one of them."""
+    assert L().ft_correlation_tc_supported(shape[1], shape[2], shape[3], 20, 1, 20, 1, 2) == 1
+    g = torch.Generator().manual_seed(17 + sum(shape))
+    a, b = torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)
+    ref = ops_oracle.correlation_torch(a, b, 20, 1, 20, 1, 2)
+    nan = torch.full_like(ref, float("nan")).cuda()
+    out = _corr_ws(a.cuda(), b.cuda())
+    assert torch.isfinite(out).all()
+    err = (out.cpu() - ref).abs().max().item()
+    print("tcgen05 correlation (wide) %s: max-abs %.3g (ref abs-max %.3g)" % (shape, err, ref.abs().max().item()))
+    assert err < 1e-5 * max(1.0, ref.abs().max().item())
+    if shape[2] % 2 == 0 and shape[3] % 2 == 0:             # the parity-planar layout FlowNetC consumes
+        aa, ba = gpu_util.pack_nchw(a.cuda()), gpu_util.pack_nchw(b.cuda())
+        B, C, H, W = shape
+        planar = torch.full((B, 441, 4, H // 2, W // 2), float("nan"), device="cuda")
+        _lib.check(L().ft_correlation_act_planar(aa.struct(), ba.struct(), planar.data_ptr(), 0, _lib.PREC_SPLIT, gpu_util.sp()), "corr_planar")
+        torch.cuda.synchronize()
+        want = torch.stack([out[:, :, py::2, px::2] for py in (0, 1) for px in (0, 1)], dim=2)
+        assert torch.equal(planar, want)
+    del nan
 
 
 def test_correlation_tensor_core_full_size_properties():

@@ -1,0 +1,10 @@
+#!/bin/bash
+# A/B of library builds on ONE box, interleaved (box-to-box variance is several per cent): build/ab/lib_<name>.so via FT_LIB_PATH
+mkdir -p gpurun_out
+for round in 1 2; do
+  for name in "$@"; do
+    FT_LIB_PATH=$PWD/build/ab/lib_$name.so python bench.py --steps 40 --warmup 3 --no-kernels --no-reference-gpu --no-cpu-baseline --no-parity > gpurun_out/ab_${name}_$round.json 2>/dev/null
+    python -c "
+import json; d=json.load(open('gpurun_out/ab_${name}_$round.json')); print('$name round $round', round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value']), round(d['roofline']['kernel_ms_per_step'],3), d['clocks']['sm_mhz'])"
+  done
+done
