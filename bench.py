@@ -85,7 +85,7 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 7:
@@ -93,6 +93,7 @@ class ClockSampler:
             try:
                 sm.append(float(c[0]))
                 mx.append(float(c[1]))
+                pw.append(float(c[2]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
@@ -101,7 +102,8 @@ class ClockSampler:
         self.f.close()
         os.unlink(self.f.name)
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_median=statistics.median(pw) if pw else None, power_w_max=max(pw) if pw else None)
         return out
 
 
