@@ -75,7 +75,7 @@ SIGNATURES = {
     "ft_box_propagation": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
-DEBUG_KNOBS = ("FT_DEV_SKIP", "FT_DEV_CHUNK", "FT_DEV_CORR_PARTS", "FT_DEV_CORR_VARIANT", "FT_DEV_NO_PDL")     # ft_set_debug(which = index)
+DEBUG_KNOBS = ("FT_DEV_SKIP", "FT_DEV_CHUNK", "FT_DEV_CORR_PARTS", "FT_DEV_CORR_VARIANT", "FT_DEV_NO_PDL", "FT_DEV_MAX_CTAS")     # ft_set_debug(which = index)
 _lib = None
 
 

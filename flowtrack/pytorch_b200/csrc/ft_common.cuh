@@ -38,7 +38,7 @@ inline int ensure_dyn_smem(F* func, int bytes, bool (&done)[MAX_DEVICES], const 
 
 // Development knobs (profiling experiments of tools/dev): set explicitly through ft_set_debug(), never read from the
 // environment by the library; all zero in production.
-enum { FT_DBG_SKIP = 0, FT_DBG_CHUNK = 1, FT_DBG_CORR_PARTS = 2, FT_DBG_CORR_VARIANT = 3, FT_DBG_NO_PDL = 4, FT_DBG_COUNT = 8 };
+enum { FT_DBG_SKIP = 0, FT_DBG_CHUNK = 1, FT_DBG_CORR_PARTS = 2, FT_DBG_CORR_VARIANT = 3, FT_DBG_NO_PDL = 4, FT_DBG_MAX_CTAS = 5, FT_DBG_COUNT = 8 };
 int dev_knob(int which);
 
 #define FT_REQUIRE(cond, ...)              \

@@ -93,7 +93,8 @@ struct alignas(64) ConvK {
     int bw, bh, bn, lg_bw, lg_bh, tiles_w, tiles_h;
     int act;
     float slope;
-    float act_mul;   // tensor-core epilogue: out = max(v, act_mul * v)
+    float act_mul;   // tensor-core epilogue: out = max(v, min(act_mul * v, act_cap)); act_cap = 0 for ReLU (so that -inf -> 0, not NaN), +inf otherwise
+    float act_cap;
     int8_t tap_dy[4][64];
     int8_t tap_dx[4][64];
     int8_t ph_oy[4];
@@ -565,9 +566,9 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(shv[4]), "=f"(shv[5]), "=f"(shv[6]), "=f"(shv[7]) : "r"(so + 4u * BN + 16u));
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            // branch-free activation: max(v, s*v) with s = 1 (none), 0 (ReLU), slope (LeakyReLU, 0 <= slope <= 1)
+                            // branch-free activation: max(v, min(s*v, cap)) with s = 1 (none), 0 (ReLU, cap 0: inf * 0 = NaN must not leak), slope (LeakyReLU)
                             const float v = fmaf(__uint_as_float(acc[j * SLAB + g8 * 8 + k]), scv[k], shv[k]);
-                            o[g8 * 8 + k] = fmaxf(v, v * p.act_mul);
+                            o[g8 * 8 + k] = fmaxf(v, fminf(v * p.act_mul, p.act_cap));
                         }
                         if (p.out_f32 && valid) {
 #pragma unroll
@@ -663,7 +664,8 @@ static int launch_tc(const ConvK& k, cudaStream_t s) {
     using G = Geo<BN, SPLIT, PAIR, NBUF>;
     static bool attr_set[MAX_DEVICES];   // per instantiation and device
     if (ensure_dyn_smem(conv_tc_kernel<BN, SPLIT, GATHER, PAIR, NBUF>, G::SMEM, attr_set, "conv_tc_kernel")) return 1;
-    const int sms = device_sms();
+    int sms = device_sms();
+    if (const int cap = dev_knob(FT_DBG_MAX_CTAS)) sms = cap < sms ? (cap < 2 ? 2 : cap) : sms;      // dev experiment: persistent grid on part of the GPU
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[2];
     int na = 0;
@@ -822,6 +824,7 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     k.scale = d->scale, k.shift = d->shift, k.act = d->act, k.slope = d->slope;
     FT_REQUIRE(d->act != FT_ACT_LEAKY || (d->slope >= 0.f && d->slope <= 1.f), "conv2d: LeakyReLU slope must lie in [0, 1] (got %g)", (double)d->slope);
     k.act_mul = d->act == FT_ACT_RELU ? 0.f : d->act == FT_ACT_LEAKY ? d->slope : 1.f;
+    k.act_cap = d->act == FT_ACT_RELU ? 0.f : INFINITY;
     k.w_tile = (const uint8_t*)d->w_tile, k.w_gemm = d->w_gemm;
     if (d->out.hi) {
         if (int e = check_view(d->out, "conv2d.out")) return e;

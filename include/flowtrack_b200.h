@@ -142,7 +142,8 @@ const char* ft_last_error(void);
 long long   ft_launch_count(void);
 void        ft_reset_launch_count(void);
 /* Development knobs for the profiling experiments under tools/dev (0 = skip mask of the conv / correlation kernels,
- * 1 = accumulation chunk, 2 = correlation parts, 3 = correlation kernel variant, 4 = no programmatic dependent launch).
+ * 1 = accumulation chunk, 2 = correlation parts, 3 = correlation kernel variant, 4 = no programmatic dependent launch,
+ * 5 = cap on the persistent grid of the conv kernel).
  * All zero by default; the library
  * never reads the environment.  Results under a non-zero skip mask are garbage by design.                          */
 int         ft_set_debug(int which, int value);
