@@ -23,7 +23,8 @@ class FtConvDesc(ctypes.Structure):
                 ("impl", ctypes.c_int32), ("k_mode", ctypes.c_int32), ("in_xpad_l", ctypes.c_int32), ("in_xpad_r", ctypes.c_int32),
                 ("cta_pair", ctypes.c_int32), ("res_blocks", ctypes.c_int32), ("pad_hi", ctypes.c_int32), ("tile_order", ctypes.c_int32),
                 ("epilogue_buffers", ctypes.c_int32), ("splitk", ctypes.c_int32), ("splitk_counters_len", ctypes.c_int32),
-                ("splitk_ws", c_void_p), ("splitk_ws_bytes", ctypes.c_uint64), ("splitk_counters", c_void_p)]
+                ("splitk_ws", c_void_p), ("splitk_ws_bytes", ctypes.c_uint64), ("splitk_counters", c_void_p), ("ctas_per_sm", ctypes.c_int32),
+                ("reserved0", ctypes.c_int32)]
 
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
@@ -31,7 +32,7 @@ KIND_CONV, KIND_DECONV = 0, 1
 PREC_SPLIT, PREC_FAST = 0, 1
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
 K_PACKED, K_TAP64, K_ROW = 0, 1, 2
-ABI_VERSION = 15        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
+ABI_VERSION = 17        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
 
 # name -> (restype, argtypes): every symbol include/flowtrack_b200.h declares
 SIGNATURES = {

@@ -64,6 +64,7 @@ struct alignas(64) ConvK {
     CUtensorMap in_map[4][2];    // [input parity view][hi, lo]   (stride 1: only view 0)
     CUtensorMap out_map[4][2];   // [output phase][hi, lo]        (plain conv: only phase 0)
     CUtensorMap res_map[2];      // residual as an A-operand source
+    CUtensorMap in_map_h[4][2];  // QUAD: the same views with HALF pixel boxes (64 pixels): each CTA loads one half and multicasts it
     const __half* in_hi;
     const __half* in_lo;
     __half* out_hi;
@@ -85,6 +86,8 @@ struct alignas(64) ConvK {
     int rev;        // tile_order: walk the tile list from the end (see ft_conv_desc.tile_order)
     int dbg_skip;   // bring-up/profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no weight loads, 4 = no MMAs, 8 = no TMA stores (results are garbage)
     int M, m_tiles, n_tiles, num_tiles;
+    int n_tiles_w;               // n-tiles of the weight image (= n_tiles, or 2 * n_tiles for QUAD, whose work items span two n-tiles)
+    int half_dx, half_dy, half_dn;   // QUAD: offset of the second half box inside a tile's pixel box
     // split-K (ft_conv_desc.splitk): a work item is (tile, k-split); items = num_tiles * splits, item -> split = item / num_tiles
     int splits, kb_split, num_items;
     FastDiv fd_num_tiles;
@@ -114,7 +117,7 @@ constexpr int THREADS_TMA = (EPI_WARPS + 2) * 32, THREADS_GATHER = (EPI_WARPS + 
 constexpr int ACC_CHUNK = 4;         // split mode: k-blocks (of 64) per tensor-core accumulation chain
 constexpr int SMEM_LIMIT = 232448;   // 227 KiB opt-in maximum per CTA
 
-template <int BN, bool SPLIT, bool PAIR = false, int NBUF = 1>
+template <int BN, bool SPLIT, bool PAIR = false, int NBUF = 1, int OCC = 1>
 struct Geo {
     static constexpr int PLANES = SPLIT ? 2 : 1;
     static constexpr int B_TILE = BN * BK * 2;                     // whole weight k-block of the n-tile (one plane)
@@ -123,14 +126,17 @@ struct Geo {
     // epilogue staging: per warp group NBUF slabs of (SLAB output channels x 128 pixels x 2 planes).  NBUF = 2 lets a group fill
     // one slab while the TMA store of its previous slab is still reading the other (the small-K 1x1 layers are bound by the
     // epilogue's store hand-off chain, not by the tensor pipe); it costs 32 KiB of shared memory, i.e. a pipeline stage.
-    static constexpr int SLAB = BN >= 64 ? 32 : 16;
+    // OCC = 2: two CTAs (two CTA pairs per TPC) share an SM -- half the shared memory each (narrow 16-channel slabs, 2 stages), so one
+    // CTA's epilogue / pipeline-fill latency runs under the other's main loop.  For the layers whose time is the per-tile epilogue
+    // latency chain, not the tensor pipe or HBM: the stems, 64-channel 3x3s and deconvs (epilogue throughput ~2.2 outputs/clk/SM).
+    static constexpr int SLAB = (BN >= 64 && OCC == 1) ? 32 : 16;
     static constexpr int SLAB_PLANE = BM * SLAB * 2;
     static constexpr int GROUP_STAGING = NBUF * 2 * SLAB_PLANE;
     static constexpr int STAGING = 2 * GROUP_STAGING;
     static constexpr int SS_BYTES = 2 * 2 * BN * 4;        // the n-tile's scale | shift, double buffered across tiles (see the epilogue)
     static constexpr int FIXED = 1024 /*align slack*/ + 512 /*barriers*/ + SS_BYTES + 16 /*split-K flag*/ + STAGING;
     static_assert(STAGE % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
-    static constexpr int STAGES_FIT = (SMEM_LIMIT - FIXED) / STAGE;
+    static constexpr int STAGES_FIT = ((OCC == 2 ? SMEM_LIMIT / 2 - 1024 : SMEM_LIMIT) - FIXED) / STAGE;   // OCC 2: 1 KiB per CTA is reserved by the system
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int LAG = STAGES >= 3 ? 2 : 1;       // gather variant: cp.async groups a producer keeps in flight
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
@@ -142,12 +148,13 @@ struct TileCoord {
     int phase, mt, nt;
     int qx0, qy0, n0;    // TMA variant: origin of the pixel box
 };
-template <bool GATHER, bool PAIR = false>
-__device__ __forceinline__ TileCoord tile_coord(const ConvK& p, int tile, int cta_rank = 0) {
+template <bool GATHER, bool PAIR = false, bool QUAD = false>
+__device__ __forceinline__ TileCoord tile_coord(const ConvK& p, int tile, int cta_rank = 0, int pair_id = 0) {
     TileCoord t;
     if (p.rev) tile = p.num_tiles - 1 - tile;
     const int r = fdiv(tile, p.fd_n_tiles);
     t.nt = tile - r * p.n_tiles;           // consecutive CTAs share the A tile (L2 reuse), differ in weights
+    if (QUAD) t.nt = 2 * t.nt + pair_id;   // a quad's two CTA pairs take two neighbouring n-tiles of the same pixels
     // fd_m_units divides by the m-tiles (single CTA) or the m-tile pairs (PAIR: two consecutive m-tiles, one per CTA, x one n-tile)
     t.phase = fdiv(r, p.fd_m_units);
     const int mu = r - t.phase * p.fd_m_units.d;
@@ -184,13 +191,25 @@ __device__ __forceinline__ Item work_item(const ConvK& p, int item) {
 // bytes -- the main loop of the single-CTA variant is bound by shared-memory fill bandwidth (~48 B/clk/SM measured),
 // not by the tensor pipe.  CTA rank 0 (the leader) issues every MMA; the peer's MMA warp only relays "my stage is
 // full" to the leader.
-template <int BN, bool SPLIT, bool GATHER, bool PAIR, int NBUF = 1>
-__global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv_tc_kernel(const __grid_constant__ ConvK p) {
+// QUAD (PAIR only): clusters of FOUR CTAs = two CTA pairs that work on the SAME 256 pixels and two neighbouring n-tiles.  The A
+// operand (the activations: two thirds of a k-block's bytes) is identical for CTA r of both pairs, so each of the two loads one HALF
+// of it (64 pixels) and TMA-multicasts it into both: a k-block costs 32 KiB of L2 -> SM traffic per SM instead of 48 KiB.  ncu
+// shows the conv stack at 10-11 TB/s of L2 -> L1 read traffic on nearly every large layer: that, not the tensor pipe,
+// is the bound this attacks.  A stage may be refilled only when BOTH pairs have consumed it (the refill lands in both CTAs), so the
+// empty barriers count two commits, each multicast to all four CTAs.
+template <int BN, bool SPLIT, bool GATHER, bool PAIR, int NBUF = 1, int OCC = 1, bool QUAD = false>
+__global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, OCC) conv_tc_kernel(const __grid_constant__ ConvK p) {
     static_assert(!(GATHER && PAIR), "the gather variant is single-CTA");
-    using G = Geo<BN, SPLIT, PAIR, NBUF>;
-    const int cta_rank = PAIR ? (int)cluster_ctarank() : 0;
-    const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // pair: a cluster owns a tile
-    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    static_assert(!QUAD || (PAIR && OCC == 1), "QUAD = two CTA pairs per cluster");
+    static_assert(OCC == 1 || (OCC == 2 && !GATHER && NBUF == 1 && 2 * BN <= 256), "two CTAs per SM: TMA variant, half of TMEM each");
+    using G = Geo<BN, SPLIT, PAIR, NBUF, OCC>;
+    constexpr int CL = QUAD ? 4 : (PAIR ? 2 : 1);                                 // CTAs per cluster
+    const int crank = PAIR ? (int)cluster_ctarank() : 0;
+    const int cta_rank = crank & 1;                                               // rank inside the CTA pair
+    const int pair_id = QUAD ? crank >> 1 : 0;
+    const uint32_t leader_rank = (uint32_t)(pair_id * 2);                         // cluster rank of this pair's MMA-issuing CTA
+    const int first_tile = (int)(blockIdx.x / CL);                                // a cluster owns a work item
+    const int tile_step = (int)(gridDim.x / CL);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t staging = smem_base + G::STAGES * G::STAGE;         // 1024-aligned (STAGE is a multiple of 1024)
@@ -209,7 +228,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
     if (threadIdx.x == 0) {
         for (int s = 0; s < G::STAGES; ++s) {
             mbar_init(full_bar(s), GATHER ? 128 + 1 : 1);   // (128 gather arrivals +) 1 arrive.expect_tx for the TMA bytes
-            mbar_init(empty_bar(s), 1);                     // one tcgen05.commit
+            mbar_init(empty_bar(s), QUAD ? 2 : 1);          // one tcgen05.commit (QUAD: one per CTA pair, see above)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(accf_bar(a), 1);
@@ -247,9 +266,9 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
             int it = 0;
             for (int item = first_tile; item < p.num_items; item += tile_step) {
                 const Item wi = work_item(p, item);
-                const TileCoord tc = tile_coord<false, PAIR>(p, wi.tile, cta_rank);
+                const TileCoord tc = tile_coord<false, PAIR, QUAD>(p, wi.tile, cta_rank, pair_id);
                 // weight image: per (phase, n_tile, k_block) [hi | lo][BN rows][64]; a pair CTA copies rows [rank*BN/2, +BN/2) of each plane
-                const uint8_t* wsrc = p.w_tile + ((size_t)(tc.phase * p.n_tiles + tc.nt) * p.kb_total) * (size_t)(2 * G::B_TILE) + (size_t)cta_rank * G::B_LOCAL;
+                const uint8_t* wsrc = p.w_tile + ((size_t)(tc.phase * p.n_tiles_w + tc.nt) * p.kb_total) * (size_t)(2 * G::B_TILE) + (size_t)cta_rank * G::B_LOCAL;
                 int tap = wi.kb_lo / p.cb, cblk = wi.kb_lo - tap * p.cb;          // (tap, channel block) of the first k-block of this item
                 for (int kb = wi.kb_lo; kb < wi.kb_hi; ++kb, ++it) {
                     const int s = it % G::STAGES;
@@ -269,8 +288,18 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                             cx = tc.qx0 + ((dx - px) >> 1);
                             cy = tc.qy0 + ((dy - py) >> 1);
                         }
-                        tma_load_4d(stage, &p.in_map[view][0], full_bar(s), cblk * BK, cx, cy, tc.n0);
-                        if (SPLIT) tma_load_4d(stage + A_TILE, &p.in_map[view][1], full_bar(s), cblk * BK, cx, cy, tc.n0);
+                        if (QUAD) {
+                            // this CTA fetches half `pair_id` (64 pixels) of the A tile and multicasts it to itself and to its twin in the
+                            // other pair (same rank inside the pair): both full barriers receive both halves' bytes
+                            const uint16_t mask = (uint16_t)((1u << cta_rank) | (1u << (2 + cta_rank)));
+                            const uint32_t dst = stage + (uint32_t)pair_id * (A_TILE / 2);
+                            const int hx = cx + pair_id * p.half_dx, hy = cy + pair_id * p.half_dy, hn = tc.n0 + pair_id * p.half_dn;
+                            tma_load_4d_mc(dst, &p.in_map_h[view][0], full_bar(s), cblk * BK, hx, hy, hn, mask);
+                            if (SPLIT) tma_load_4d_mc(dst + A_TILE, &p.in_map_h[view][1], full_bar(s), cblk * BK, hx, hy, hn, mask);
+                        } else {
+                            tma_load_4d(stage, &p.in_map[view][0], full_bar(s), cblk * BK, cx, cy, tc.n0);
+                            if (SPLIT) tma_load_4d(stage + A_TILE, &p.in_map[view][1], full_bar(s), cblk * BK, cx, cy, tc.n0);
+                        }
                     } else {                          // residual k-block: 64 channels of the residual tensor at the output pixels
                         const int c0 = tc.nt * BN + (kb - p.kb_main) * BK;
                         tma_load_4d(stage, &p.res_map[0], full_bar(s), c0, tc.qx0, tc.qy0, tc.n0);
@@ -399,10 +428,12 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                                 }
                             }
                         }
-                        if (PAIR) tc_commit_pair(empty_bar(s));   // smem slot reusable in BOTH CTAs once these MMAs retire
+                        if (QUAD) tc_commit_mc(empty_bar(s), 0xF);     // this pair is done with stage s: tell all four CTAs (their refills land in both pairs)
+                        else if (PAIR) tc_commit_pair(empty_bar(s));   // smem slot reusable in BOTH CTAs once these MMAs retire
                         else tc_commit(empty_bar(s));
                         if (kb == kb1 - 1) {
-                            if (PAIR) tc_commit_pair(accf_bar(a));        // chunk complete -> both CTAs' epilogues
+                            if (QUAD) tc_commit_mc(accf_bar(a), (uint16_t)(3u << leader_rank));   // chunk complete -> the epilogues of this pair's two CTAs
+                            else if (PAIR) tc_commit_pair(accf_bar(a));        // chunk complete -> both CTAs' epilogues
                             else tc_commit(accf_bar(a));
                         }
                         }
@@ -418,7 +449,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
                 for (int kb = wi.kb_lo; kb < wi.kb_hi; ++kb, ++it) {
                     const int s = it % G::STAGES;
                     mbar_wait(full_bar(s), (it / G::STAGES) & 1);
-                    mbar_arrive_remote(map_to_cta(peer_full_bar(s), 0));
+                    mbar_arrive_remote(map_to_cta(peer_full_bar(s), leader_rank));
                 }
             }
         }
@@ -436,10 +467,10 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
         int acc_it = 0;
         uint32_t slab_it = 0;                         // slabs this group has staged so far (selects the ping-pong buffer)
         uint32_t tile_it = 0;
-        const uint32_t acce_remote0 = PAIR ? map_to_cta(acce_bar(0), 0) : 0u;     // the leader's acc_empty barriers, as cluster addresses
+        const uint32_t acce_remote0 = PAIR ? map_to_cta(acce_bar(0), leader_rank) : 0u;     // the pair leader's acc_empty barriers, as cluster addresses
         for (int item = first_tile; item < p.num_items; item += tile_step, ++tile_it) {
             const Item wi = work_item(p, item);
-            const TileCoord tc = tile_coord<GATHER, PAIR>(p, wi.tile, cta_rank);
+            const TileCoord tc = tile_coord<GATHER, PAIR, QUAD>(p, wi.tile, cta_rank, pair_id);
             // This n-tile's scale / shift go through shared memory: every lane needs the same 2*BN values, so the epilogue reads
             // them as broadcast LDS instead of four LDG.128 per 8 channels whose latency sat in front of every FFMA (long-scoreboard
             // stalls were ~20 % of the epilogue warps' samples).  Double buffered by tile parity; the barrier below orders tile i's
@@ -509,7 +540,7 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, 1) conv
             if (p.splits > 1) {
                 // ---- split-K: park this item's partial sums; the CTA whose part arrives last adds all parts (in split order, so the
                 // result does not depend on who is last) and finalizes the tile ----
-                const size_t cta_tile = (size_t)wi.tile * (PAIR ? 2 : 1) + cta_rank;
+                const size_t cta_tile = (size_t)wi.tile * CL + crank;
                 float* wsp = p.sk_ws + (cta_tile * p.splits + wi.sp) * (size_t)(BN * BM);
 #pragma unroll
                 for (int j = 0; j < MINE; ++j) {
@@ -659,12 +690,12 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvK p) {
     }
 }
 
-template <int BN, bool SPLIT, bool GATHER, bool PAIR, int NBUF = 1>
+template <int BN, bool SPLIT, bool GATHER, bool PAIR, int NBUF = 1, int OCC = 1, bool QUAD = false>
 static int launch_tc(const ConvK& k, cudaStream_t s) {
-    using G = Geo<BN, SPLIT, PAIR, NBUF>;
+    using G = Geo<BN, SPLIT, PAIR, NBUF, OCC>;
     static bool attr_set[MAX_DEVICES];   // per instantiation and device
-    if (ensure_dyn_smem(conv_tc_kernel<BN, SPLIT, GATHER, PAIR, NBUF>, G::SMEM, attr_set, "conv_tc_kernel")) return 1;
-    int sms = device_sms();
+    if (ensure_dyn_smem(conv_tc_kernel<BN, SPLIT, GATHER, PAIR, NBUF, OCC, QUAD>, G::SMEM, attr_set, "conv_tc_kernel")) return 1;
+    int sms = device_sms() * OCC;        // OCC = 2: two resident CTAs per SM
     if (const int cap = dev_knob(FT_DBG_MAX_CTAS)) sms = cap < sms ? (cap < 2 ? 2 : cap) : sms;      // dev experiment: persistent grid on part of the GPU
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[2];
@@ -675,17 +706,18 @@ static int launch_tc(const ConvK& k, cudaStream_t s) {
         ++na;
     }
     if (PAIR) {
-        // one cluster of two CTAs (the two SMs of a TPC) per work item; k.num_tiles already counts pair tiles
-        const int clusters = k.num_items < sms / 2 ? k.num_items : sms / 2;
-        cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(THREADS_TMA);
+        // one cluster of two CTAs (the two SMs of a TPC) -- QUAD: four CTAs, two TPCs -- per work item; k.num_tiles already counts cluster tiles
+        constexpr int CL = QUAD ? 4 : 2;
+        const int clusters = k.num_items < sms / CL ? k.num_items : sms / CL;
+        cfg.gridDim = dim3(CL * clusters), cfg.blockDim = dim3(THREADS_TMA);
         attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = 2, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+        attr[na].val.clusterDim.x = CL, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
         ++na;
     } else {
         cfg.gridDim = dim3(k.num_items < sms ? k.num_items : sms), cfg.blockDim = dim3(GATHER ? THREADS_GATHER : THREADS_TMA);
     }
     cfg.dynamicSmemBytes = G::SMEM, cfg.stream = s, cfg.attrs = attr, cfg.numAttrs = na;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, GATHER, PAIR, NBUF>, k);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, GATHER, PAIR, NBUF, OCC, QUAD>, k);
     if (e != cudaSuccess) {
         set_error("conv_tc_kernel<%d,%d,%d,%d>: launch failed: %s", BN, (int)SPLIT, (int)GATHER, (int)PAIR, cudaGetErrorString(e));
         return 1;
@@ -858,7 +890,9 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     FT_REQUIRE(BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256, "conv2d: block_n must be 16, 32, 64, 128 or 256 (got %d)", BN);
     FT_REQUIRE(d->cout_pad % BN == 0, "conv2d: cout_pad %d is not a multiple of block_n %d", d->cout_pad, BN);
     k.n_tiles = d->cout_pad / BN;
+    k.n_tiles_w = k.n_tiles;
     const bool gather = d->k_mode == FT_K_PACKED;
+    const bool quad = d->cta_pair == 2;
     const int res_blocks = d->res.hi ? ceil_div(BN, BK) : 0;
     FT_REQUIRE(d->res_blocks == res_blocks, "conv2d: the weight image carries %d residual k-blocks per tile, this call needs %d (residual %s, block_n %d)",
                d->res_blocks, res_blocks, d->res.hi ? "given" : "absent", BN);
@@ -866,7 +900,7 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     k.dbg_skip = dev_knob(FT_DBG_SKIP);                                      // ft_set_debug(): 0 unless a tools/dev experiment set it
     const int acc_chunk = dev_knob(FT_DBG_CHUNK) > 0 ? dev_knob(FT_DBG_CHUNK) : ACC_CHUNK;
     k.chunk = (split && k.kb_total > acc_chunk) ? acc_chunk : k.kb_total;   // k-blocks accumulated per TMEM stage (see the MMA warp)
-    const int slab = BN >= 64 ? 32 : 16;
+    const int slab = (BN >= 64 && d->ctas_per_sm != 2) ? 32 : 16;      // channels per epilogue staging slab = inner box of the output maps (Geo::SLAB)
 
     if (gather) {
         FT_REQUIRE(d->kind == FT_CONV && !d->res.hi, "conv2d: FT_K_PACKED (gather variant) supports plain convolutions without residual only");
@@ -907,6 +941,16 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
             if (int e = make_map(&k.in_map[view][0], k.in_hi + off, dim, str, abox, 128, "in.hi")) return e;
             if (split)
                 if (int e = make_map(&k.in_map[view][1], k.in_lo + off, dim, str, abox, 128, "in.lo")) return e;
+            if (quad) {      // the same view with half pixel boxes: rows [0,64) and [64,128) of a tile are the two halves of its slowest box dimension
+                int hbox[4] = {BK, k.bw, k.bh, k.bn};
+                k.half_dx = k.half_dy = k.half_dn = 0;
+                if (k.bn > 1) hbox[3] = k.bn / 2, k.half_dn = k.bn / 2;
+                else if (k.bh > 1) hbox[2] = k.bh / 2, k.half_dy = k.bh / 2;
+                else hbox[1] = k.bw / 2, k.half_dx = k.bw / 2;
+                if (int e = make_map(&k.in_map_h[view][0], k.in_hi + off, dim, str, hbox, 128, "in.hi(half)")) return e;
+                if (split)
+                    if (int e = make_map(&k.in_map_h[view][1], k.in_lo + off, dim, str, hbox, 128, "in.lo(half)")) return e;
+            }
         }
         if (k.out_hi) {
             const int mul = k.out_mul;
@@ -934,6 +978,13 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
     FT_REQUIRE(d->epilogue_buffers >= 0 && d->epilogue_buffers <= 2 && (!epi2 || (BN >= 64 && BN <= 128 && !gather)),
                "conv2d: epilogue_buffers must be 0/1 or 2 (2: TMA variant with block_n 64 or 128)");
     FT_REQUIRE(!pair || (!gather && BN >= 64), "conv2d: cta_pair needs the TMA variant and block_n >= 64");
+    FT_REQUIRE(d->cta_pair >= 0 && d->cta_pair <= 2, "conv2d: cta_pair must be 0, 1 or 2");
+    if (quad) {
+        FT_REQUIRE(!k.row_mode && (BN == 64 || BN == 128) && k.n_tiles % 2 == 0 && !epi2 && d->ctas_per_sm != 2 && d->splitk <= 1,
+                   "conv2d: cta_pair = 2 (two CTA pairs sharing the A tile) needs FT_K_TAP64, block_n 64 or 128, an even number of n-tiles (got %d), "
+                   "one staging slab, one CTA per SM and no split-K", k.n_tiles);
+        k.n_tiles /= 2;                 // a work item spans two neighbouring n-tiles
+    }
     k.num_tiles = k.n_phase * (pair ? (k.m_tiles + 1) / 2 : k.m_tiles) * k.n_tiles;
     // split-K: `splitk` parts of every tile's K range become separate work items (see work_item / the epilogue)
     k.splits = 1, k.kb_split = k.kb_total;
@@ -967,6 +1018,15 @@ extern "C" int ft_conv2d_fprop(const ft_conv_desc* d, void* stream) {
         if (pair) return split ? launch_tc<BN_, true, false, true>(k, s) : launch_tc<BN_, false, false, true>(k, s);          \
         if (gather) return split ? launch_tc<BN_, true, true, false>(k, s) : launch_tc<BN_, false, true, false>(k, s);        \
         return split ? launch_tc<BN_, true, false, false>(k, s) : launch_tc<BN_, false, false, false>(k, s);
+    if (quad) {
+        if (BN == 64) return split ? launch_tc<64, true, false, true, 1, 1, true>(k, s) : launch_tc<64, false, false, true, 1, 1, true>(k, s);
+        return split ? launch_tc<128, true, false, true, 1, 1, true>(k, s) : launch_tc<128, false, false, true, 1, 1, true>(k, s);
+    }
+    if (d->ctas_per_sm == 2) {
+        FT_REQUIRE(BN == 64 && pair && !gather && !epi2, "conv2d: ctas_per_sm = 2 is available for block_n 64 on CTA pairs (one staging slab)");
+        return split ? launch_tc<64, true, false, true, 1, 2>(k, s) : launch_tc<64, false, false, true, 1, 2>(k, s);
+    }
+    FT_REQUIRE(d->ctas_per_sm >= 0 && d->ctas_per_sm <= 2, "conv2d: ctas_per_sm must be 0/1 or 2");
     switch (BN) {
         FT_CASE(16)
         FT_CASE(32)

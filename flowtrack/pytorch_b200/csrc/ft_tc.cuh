@@ -164,6 +164,17 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// tcgen05.commit of a CTA pair's MMAs with the arrival multicast to the CTAs of `mask` (cluster ranks; same barrier offset in each)
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+// TMA: 4-D box -> the same shared-memory offset of every CTA in `mask`, completing on the mbarrier at the same offset in each
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` (same offset) in BOTH CTAs of the pair
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }

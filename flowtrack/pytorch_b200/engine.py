@@ -293,6 +293,8 @@ class ConvLayer:
         qh, qw = (h, w) if self.kind == _lib.KIND_DECONV else (ho, wo)
         mt = box_tiles(qw, qh, n)
         phases, nt = (4 if self.kind == _lib.KIND_DECONV else 1), self.cout_pad // bn
+        if pair == 2:                            # clusters of four: a work item = 256 pixels x two n-tiles
+            return phases * ((mt + 1) // 2) * (nt // 2), phases * 2 * ((mt + 1) // 2) * nt
         return phases * ((mt + 1) // 2 if pair else mt) * nt, phases * (2 * ((mt + 1) // 2) if pair else mt) * nt
 
     def desc(self, x, out=None, out_f32=None, res=None, precision=_lib.PREC_SPLIT, impl=_lib.IMPL_TCGEN05, tiling=None, splitk_ws=None):
@@ -310,6 +312,7 @@ class ConvLayer:
         bn, pair = tiling[0], tiling[1]
         d.epilogue_buffers = tiling[2] if len(tiling) > 2 else 1
         d.splitk = tiling[3] if len(tiling) > 3 else 0
+        d.ctas_per_sm = tiling[4] if len(tiling) > 4 else 1
         if d.splitk > 1:
             ws, cnt = splitk_ws
             d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel()
@@ -502,7 +505,8 @@ class Plan:
 
     def autotune(self, launches=4):
         """Pick the tile shape of every tensor-core convolution of the plan by measurement on this GPU and this batch shape:
-        candidates = tile widths {64, 128, 256 (pairs only)} x {single CTA, CTA pair} x {1, 2 epilogue staging buffers}; each candidate is captured as a small CUDA graph of
+        candidates = tile widths {64, 128, 256 (pairs only)} x {single CTA, CTA pair} x {1, 2 epilogue staging buffers}, and two
+        CTAs per SM for 64-wide pair tiles; each candidate is captured as a small CUDA graph of
         `launches` back-to-back launches on the plan's own buffers and timed with CUDA events.  Which shape wins depends on
         how many tiles a layer has against the 148 SMs (wave quantisation) -- layer3/4 of a 64-crop batch, every layer of a
         2-pair strong-scaling shard -- which a static rule cannot see.  Layers with fewer tiles than SMs and a long K also try
@@ -552,6 +556,11 @@ class Plan:
                         cands.append((bn, pair, 1))
                         if layer.k_mode != _lib.K_PACKED and out is not None and bn <= 128:
                             cands.append((bn, pair, 2))      # ping-pong epilogue staging (ft_conv_desc.epilogue_buffers)
+                        if bn == 64 and pair and os.environ.get("FT_OCC2", "1") != "0":
+                            cands.append((bn, pair, 1, 0, 2))    # two CTAs per SM (ft_conv_desc.ctas_per_sm)
+                        if pair and bn <= 128 and layer.k_mode == _lib.K_TAP64 and (layer.cout_pad // bn) % 2 == 0 and os.environ.get("FT_QUAD", "0") != "0":
+                            cands.append((bn, 2, 1))             # two CTA pairs per cluster sharing the A tile by TMA multicast (cta_pair = 2);
+                                                                 # measured slower on every layer (profiles/r02m_autotune_log.txt), so opt-in: FT_QUAD=1
                 if len(cands) < 2:
                     continue
                 best = None
@@ -559,7 +568,8 @@ class Plan:
                 for cand in cands:
                     bn, pair, nbuf = cand[:3]
                     sk = cand[3] if len(cand) > 3 else 0
-                    d = layer.desc(x, out, out_f32, res, self.precision, self.impl, tiling=(bn, pair, nbuf, sk), splitk_ws=getattr(self, "_sk_ws", None))
+                    occ = cand[4] if len(cand) > 4 else 1
+                    d = layer.desc(x, out, out_f32, res, self.precision, self.impl, tiling=(bn, pair, nbuf, sk, occ), splitk_ws=getattr(self, "_sk_ws", None))
                     d.tile_order = base.tile_order
                     try:
                         s = stream_ptr()
@@ -584,12 +594,15 @@ class Plan:
                         t = min(ts)
                     except RuntimeError:
                         continue
+                    if os.environ.get("FT_AUTOTUNE_LOG"):
+                        print("autotune call %3d %s k%d cin %4d cout %4d in %dx%dx%d : bn %3d pair %d nbuf %d splitk %d occ %d -> %7.1f us"
+                              % (i, "deconv" if layer.kind else "conv", layer.kh, layer.cin, layer.cout, x.n, x.h, x.w, bn, pair, nbuf, sk, occ, t * 1e3), flush=True)
                     if best is None or t < best[0]:
-                        best = (t, bn, pair, nbuf, sk, d)
+                        best = (t, bn, pair, nbuf, sk, occ, d)
                 if best is not None:
-                    t, bn, pair, nbuf, sk, d = best
+                    t, bn, pair, nbuf, sk, occ, d = best
                     self.calls[i] = ("conv2d", fn, (ctypes.byref(d),), d)
-                    self.tuned[i] = (bn, pair, t * 1e3, nbuf, sk)
+                    self.tuned[i] = (bn, pair, t * 1e3, nbuf, sk, occ)
         self.graph = None
         return self
 

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 15
+#define FT_ABI_VERSION 17
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -107,8 +107,12 @@ typedef struct {
     int32_t k_mode;         /* FT_K_*: K layout of w_gemm / w_tile                                 */
     int32_t in_xpad_l;      /* the rows of `in` physically start with in_xpad_l and end with in_xpad_r */
     int32_t in_xpad_r;      /* zero pixels: in.w counts them, the image is in.w - l - r wide (0/0 normally) */
-    int32_t cta_pair;       /* != 0: run 256-pixel x block_n tiles on CTA pairs (tcgen05 cta_group::2, clusters of 2);
-                               needs FT_K_TAP64 / FT_K_ROW and block_n >= 64                          */
+    int32_t cta_pair;       /* 1: run 256-pixel x block_n tiles on CTA pairs (tcgen05 cta_group::2, clusters of 2);
+                               needs FT_K_TAP64 / FT_K_ROW and block_n >= 64.
+                               2: clusters of four = two CTA pairs on the same 256 pixels and two neighbouring n-tiles;
+                               the activation (A) tile is fetched once per cluster -- each CTA loads half of it and
+                               TMA-multicasts it to its twin in the other pair -- which cuts the L2 -> SM traffic of a
+                               k-block from 48 to 32 KiB per SM.  FT_K_TAP64, block_n 64 / 128, even n-tile count.   */
     int32_t res_blocks;     /* residual k-blocks appended to every (phase, n_tile) of w_tile:
                                ceil(block_n/64) when the layer is called with a residual, else 0.
                                Block j holds diag(f) for channels [64j, 64j+64) of the tile, where
@@ -132,6 +136,11 @@ typedef struct {
     void*   splitk_ws;      /* 16-byte aligned scratch, >= CTA tiles x parts x block_n x 128 x 4 bytes                        */
     uint64_t splitk_ws_bytes;
     void*   splitk_counters;/* uint32 per CTA tile, zero before the first launch (the kernel leaves them zero)               */
+    int32_t ctas_per_sm;    /* 0 / 1: one persistent CTA per SM.  2: two (half the shared memory each: 2 pipeline stages, 16-channel
+                               staging slabs), so one CTA's epilogue and pipeline fill run under the other's main loop -- for the
+                               layers bound by the per-tile epilogue latency chain (stems, 64-channel 3x3 convolutions and
+                               deconvolutions).  block_n 64 on CTA pairs only; engine.Plan.autotune() chooses.               */
+    int32_t reserved0;
 } ft_conv_desc;
 
 int         ft_abi_version(void);

@@ -261,7 +261,7 @@ def test_autotune_picks_tilings_and_keeps_results_bit_identical(monkeypatch):
     m.refresh()
     b = m(x).clone()
     plan = next(iter(m._plans.values()))[0]
-    assert len(plan.tuned) > 40 and all(bn in (64, 128, 256) and pair in (0, 1) and us > 0 and nbuf in (1, 2) and 0 <= sk <= 8 for bn, pair, us, nbuf, sk in plan.tuned.values())
+    assert len(plan.tuned) > 40 and all(bn in (64, 128, 256) and pair in (0, 1, 2) and us > 0 and nbuf in (1, 2) and 0 <= sk <= 8 and occ in (1, 2) for bn, pair, us, nbuf, sk, occ in plan.tuned.values())
     assert (a - b).abs().max() <= 2e-6 * a.abs().max()             # bit-identical tile shapes; split-K layers differ by fp32 rounding only
 
 
@@ -336,3 +336,69 @@ def test_split_k_matches_unsplit_and_is_deterministic(name, ctor, shape, act, re
     got = outs[0].to_nchw(layer.cout)
     assert (got - ref).abs().max() <= 2e-6 * max(1.0, ref.abs().max().item())
     assert torch.equal(outs[0].hi, outs[1].hi) and torch.equal(outs[0].lo, outs[2].lo)
+
+
+@pytest.mark.parametrize("name,ctor,shape,act,residual", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_two_ctas_per_sm_variant_is_bit_identical(name, ctor, shape, act, residual):
+    """ft_conv_desc.ctas_per_sm = 2 (64-wide pair tiles, two CTA pairs per TPC, 2 stages, 16-channel slabs): same bits as the
+    one-CTA-per-SM kernel on every pair case, and on a many-tile stem-like layer where both resident CTAs wrap their rings."""
+    torch.manual_seed(len(name) * 3)
+    mod = ctor()
+    x = torch.randn(*shape)
+    layer = engine.conv_from_modules(mod, None, act, device="cuda", residual=residual)
+    xa = gpu_util.pack_nchw(x.cuda(), layer.cin_p)
+    ra = gpu_util.pack_nchw(torch.randn(shape[0], layer.cout, *layer.out_hw(shape[2], shape[3])).cuda()) if residual else None
+    a = gpu_util.run_layer(layer, xa, res=ra, tiling=(64, 1, 1, 0, 1))
+    b = gpu_util.run_layer(layer, xa, res=ra, tiling=(64, 1, 1, 0, 2))
+    assert torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)
+
+
+def test_two_ctas_per_sm_many_tiles_and_stem():
+    torch.manual_seed(4)
+    conv = nn.Conv2d(64, 64, 3, 1, 1, bias=False)
+    x = torch.randn(24, 64, 64, 48)                                                  # 576 m-tiles: ~2 tiles per resident CTA
+    layer = engine.conv_from_modules(conv, None, _lib.ACT_RELU, device="cuda")
+    xa = gpu_util.pack_nchw(x.cuda())
+    a = gpu_util.run_layer(layer, xa, tiling=(64, 1, 1, 0, 1))
+    b = gpu_util.run_layer(layer, xa, tiling=(64, 1, 1, 0, 2))
+    assert torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)
+    with torch.no_grad():
+        ref = torch.relu(conv(x))
+    assert (b.to_nchw().cpu() - ref).abs().max() <= 2e-5 * ref.abs().max()
+    stem = nn.Conv2d(6, 64, 7, 2, 3)                                                 # FlowNetS conv1 (FT_K_ROW)
+    xs = torch.randn(2, 6, 128, 192)
+    ls = engine.conv_from_modules(stem, None, _lib.ACT_LEAKY, device="cuda")
+    xsa = gpu_util.pack_nchw(xs.cuda(), ls.cin_p, xpad=ls.in_xpad)
+    a = gpu_util.run_layer(ls, xsa, tiling=(64, 1, 1, 0, 1))
+    b = gpu_util.run_layer(ls, xsa, tiling=(64, 1, 1, 0, 2))
+    assert torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)
+
+
+@pytest.mark.parametrize("name,ctor,shape,act,residual", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+@pytest.mark.parametrize("bn", [64, 128])
+def test_quad_clusters_with_multicast_a_tile_are_bit_identical(name, ctor, shape, act, residual, bn):
+    """ft_conv_desc.cta_pair = 2: clusters of four (two CTA pairs on the same pixels, neighbouring n-tiles), the A tile fetched once
+    per cluster as two multicast halves.  Same bits as plain CTA pairs on every pair case whose n-tile count is even."""
+    torch.manual_seed(len(name) * 5 + bn)
+    mod = ctor()
+    x = torch.randn(*shape)
+    layer = engine.conv_from_modules(mod, None, act, device="cuda", residual=residual)
+    if layer.cout_pad % bn or (layer.cout_pad // bn) % 2:
+        pytest.skip("needs an even number of n-tiles")
+    xa = gpu_util.pack_nchw(x.cuda(), layer.cin_p)
+    ra = gpu_util.pack_nchw(torch.randn(shape[0], layer.cout, *layer.out_hw(shape[2], shape[3])).cuda()) if residual else None
+    a, fa = gpu_util.run_layer(layer, xa, res=ra, tiling=(bn, 1), want_f32=True)
+    b, fb = gpu_util.run_layer(layer, xa, res=ra, tiling=(bn, 2), want_f32=True)
+    assert torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo) and torch.equal(fa, fb)
+
+
+def test_quad_clusters_many_tiles():
+    """Every cluster walks several work items (all stages and both TMEM buffers wrap), 8x6 maps spanning images, stride 2."""
+    torch.manual_seed(9)
+    for conv, shape in ((nn.Conv2d(128, 256, 3, 1, 1), (40, 128, 32, 24)), (nn.Conv2d(256, 512, 1, bias=False), (70, 256, 8, 6)),
+                        (nn.Conv2d(128, 256, 3, 2, 1), (30, 128, 32, 24)), (nn.ConvTranspose2d(256, 256, 4, 2, 1, bias=False), (20, 256, 16, 12))):
+        layer = engine.conv_from_modules(conv, None, _lib.ACT_RELU, device="cuda")
+        xa = gpu_util.pack_nchw(torch.randn(*shape).cuda())
+        a = gpu_util.run_layer(layer, xa, tiling=(128, 1))
+        b = gpu_util.run_layer(layer, xa, tiling=(128, 2))
+        assert torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)

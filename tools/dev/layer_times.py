@@ -34,7 +34,7 @@ def table(name, plan):
             M = d.in_.n * (d.in_.h * d.in_.w if d.kind else ((d.in_.h + 2 * d.pad - d.kh) // d.stride + 1) * ((d.in_.w + 2 * d.pad - d.kw) // d.stride + 1))
             tiles = (4 if d.kind else 1) * ((M + 127) // 128) * (d.cout_pad // d.block_n)
             print("%3d %-6s k%d s%d cin_p=%-4d cout=%-4d in=%3dx%-3d M=%-7d BN=%-3d%-4s kpad=%-5d tiles=%-5d %8.1f us %7.1f TF/s alg (%4.1f%% of peak)"
-                  % (i, "deconv" if d.kind else "conv", d.kh, d.stride, d.in_.c, d.cout, d.in_.h, d.in_.w, M, d.block_n, ("P" if d.cta_pair else " ") + ("2" if d.epilogue_buffers == 2 else " ") + ("k%d" % d.splitk if d.splitk > 1 else ""), d.k_pad, tiles,
+                  % (i, "deconv" if d.kind else "conv", d.kh, d.stride, d.in_.c, d.cout, d.in_.h, d.in_.w, M, d.block_n, ("Q" if d.cta_pair == 2 else "P" if d.cta_pair else " ") + ("2" if d.epilogue_buffers == 2 else " ") + ("k%d" % d.splitk if d.splitk > 1 else "") + ("o2" if d.ctas_per_sm == 2 else ""), d.k_pad, tiles,
                      per[i] * 1e3, fl / per[i] / 1e9, fl / per[i] / 1e9 / PEAK * 100))
         else:
             print("%3d %-40s %8.1f us" % (i, what, per[i] * 1e3))
