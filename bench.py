@@ -385,6 +385,8 @@ def run_ours(args):
             except Exception as e:                        # pragma: no cover
                 per, how = plan.time_calls(reps=3), "un-graphed CUDA-event pairs (graph timing unavailable: %s)" % e
             for i, (what, _fn, _a, _k) in enumerate(plan.calls):
+                if _fn is None:                          # fork / join markers of the plan's branches
+                    continue
                 if what == "conv2d":
                     conv_ms += per[i]
                     conv_flops += plan.flops[i]

@@ -427,6 +427,9 @@ class Plan:
         self.graph = None
         self.taps = {}       # name -> Act / tensor, for layer-by-layer tests
         self.flops = {}      # call index -> algorithmic FLOPs (convolutions only)
+        self._tag, self._ntags = 0, 1   # branch (stream) tag of the calls being added; see branch()
+        self._tags = {}       # call index -> branch tag (absent = 0, the caller's stream)
+        self._streams = {}    # branch tag -> side stream (created lazily)
         self._conv_args = {}  # call index -> (layer, x, out, out_f32, res): what autotune() rebuilds a descriptor from
         self.tuned = {}      # call index -> (block_n, cta_pair, us) chosen by autotune()
         self.alternate_tile_order = os.environ.get("FT_TILE_ORDER", "alternate") == "alternate"
@@ -442,12 +445,41 @@ class Plan:
         self.keep.append(t)
         return t
 
+    def branch(self):
+        """Context manager: the calls added inside form a branch that is independent of the calls added after it until the matching
+        `join()` -- e.g. a FlowNet decoder level's flow head (1x1 conv on a handful of tiles + two tiny kernels) next to its
+        deconvolution, or FlowNetSD next to the FlowNetC -> S -> S chain.  enqueue() issues a branch on a side stream between a fork
+        and a join event, so inside a CUDA graph the branches are parallel paths: kernels that cannot fill the GPU overlap.  The
+        linear order of `calls` stays a valid schedule (time_calls* and the tests use it).  Branches nest."""
+        plan = self
+
+        class _Branch:
+            def __enter__(self_b):
+                self_b.parent, self_b.tag = plan._tag, plan._ntags
+                plan._ntags += 1
+                plan.calls.append(("fork", None, (self_b.tag, self_b.parent), None))
+                plan._tag = self_b.tag
+                return self_b
+
+            def __exit__(self_b, *exc):
+                plan._tag = self_b.parent
+                return False
+
+            def join(self_b):
+                plan.calls.append(("join", None, (self_b.tag, plan._tag), None))
+        return _Branch()
+
+    def _add(self, call):
+        self.calls.append(call)
+        if self._tag:
+            self._tags[len(self.calls) - 1] = self._tag
+
     def conv(self, layer, x, out=None, out_f32=None, res=None, name=None):
         d = layer.desc(x, out, out_f32, res, self.precision, self.impl)
         if self.alternate_tile_order:
             d.tile_order = self._rev
             self._rev ^= 1
-        self.calls.append(("conv2d", _lib.lib().ft_conv2d_fprop, (ctypes.byref(d),), d))
+        self._add(("conv2d", _lib.lib().ft_conv2d_fprop, (ctypes.byref(d),), d))
         self._conv_args[len(self.calls) - 1] = (layer, x, out, out_f32, res)
         self.flops[len(self.calls) - 1] = layer.flops(x.n, x.h, x.w)
         if name:
@@ -455,7 +487,7 @@ class Plan:
         return out if out is not None else out_f32
 
     def call(self, what, fn, *args):
-        self.calls.append((what, fn, args, args))
+        self._add((what, fn, args, args))
 
     def flow_head(self, head, x, out=None, name=None):
         """predict_flow on the split-fp16 view x -> fp32 NCHW flow [B,2,h,w] (a new static tensor unless `out` is given)."""
@@ -481,9 +513,25 @@ class Plan:
         """Issue every call of the plan on the plan device's current stream (also what graph capture records).  The device
         guard makes the launches land on the GPU that owns the plan's buffers whatever the caller's current device is."""
         with torch.cuda.device(self.device):
-            s = stream_ptr()
-            for what, fn, args, _keep in self.calls:
-                _lib.check(fn(*args, s), what)
+            if self._ntags == 1 or os.environ.get("FT_BRANCHES", "1") == "0":
+                s = stream_ptr()
+                for what, fn, args, _keep in self.calls:
+                    if fn is not None:
+                        _lib.check(fn(*args, s), what)
+                return
+            streams = {0: torch.cuda.current_stream()}
+            for i, (what, fn, args, _keep) in enumerate(self.calls):
+                if fn is None:
+                    child, parent = args
+                    if child not in self._streams:
+                        self._streams[child] = torch.cuda.Stream(device=self.device)
+                    streams[child] = self._streams[child]
+                    src, dst = (streams[parent], streams[child]) if what == "fork" else (streams[child], streams[parent])
+                    ev = torch.cuda.Event()
+                    ev.record(src)
+                    dst.wait_event(ev)
+                    continue
+                _lib.check(fn(*args, ctypes.c_void_p(streams[self._tags.get(i, 0)].cuda_stream)), what)
 
     def time_calls(self, reps=3):
         """Per-call device time in ms (CUDA events on the launching stream, averaged over `reps` un-graphed passes).
@@ -496,14 +544,15 @@ class Plan:
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
                 ev[0].record()
                 for i, (what, fn, args, _keep) in enumerate(self.calls):
-                    _lib.check(fn(*args, s), what)
+                    if fn is not None:
+                        _lib.check(fn(*args, s), what)
                     ev[i + 1].record()
                 torch.cuda.synchronize()
                 for i in range(n):
                     tot[i] += ev[i].elapsed_time(ev[i + 1])
         return [t / reps for t in tot]
 
-    def autotune(self, launches=4):
+    def autotune(self, launches=4, hint=None):
         """Pick the tile shape of every tensor-core convolution of the plan by measurement on this GPU and this batch shape:
         candidates = tile widths {64, 128, 256 (pairs only)} x {single CTA, CTA pair} x {1, 2 epilogue staging buffers}, and two
         CTAs per SM for 64-wide pair tiles; each candidate is captured as a small CUDA graph of
@@ -517,10 +566,22 @@ class Plan:
         if self.impl != _lib.IMPL_TCGEN05 or torch.device(self.device).type != "cuda":
             return self
         fn = _lib.lib().ft_conv2d_fprop
+        if hint is not None and all(not (len(v) > 4 and v[4] > 1) for v in hint.values()):
+            # `hint` = the `tuned` record of a plan with the same layers and shapes (e.g. the other lane of a TrackingPipeline):
+            # adopt its choices instead of measuring again (records with split-K need the workspace: those are re-tuned)
+            for i, (bn, pair, us, nbuf, sk, occ) in hint.items():
+                layer, x, out, out_f32, res = self._conv_args[i]
+                d = layer.desc(x, out, out_f32, res, self.precision, self.impl, tiling=(bn, pair, nbuf, 0, occ))
+                d.tile_order = self.calls[i][3].tile_order
+                self.calls[i] = ("conv2d", fn, (ctypes.byref(d),), d)
+                self.tuned[i] = (bn, pair, us, nbuf, 0, occ)
+            self.graph = None
+            return self
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         with torch.cuda.device(self.device):
-            # one split-K workspace per plan (its layers run one after the other on one stream), sized for the largest candidate
-            need_ws = need_cnt = 0
+            # one split-K workspace per branch of the plan (the layers of a branch run one after the other on one stream; branches
+            # run concurrently and must not share it), sized for the branch's largest candidate
+            need = {}
             plans = {}
             for i, (layer, x, out, out_f32, res) in sorted(self._conv_args.items()):
                 plans[i] = []
@@ -539,11 +600,11 @@ class Plan:
                             if sk * 4 > kb_total or items * sk > 6 * units:
                                 continue
                             plans[i].append((bn, pair, 1, sk))
-                            need_ws = max(need_ws, cta_tiles * sk * bn * 128 * 4)
-                            need_cnt = max(need_cnt, cta_tiles)
-            if need_ws:
-                self._sk_ws = (torch.empty(need_ws, dtype=torch.uint8, device=self.device), torch.zeros(need_cnt, dtype=torch.int32, device=self.device))
-                self.keep.append(self._sk_ws)
+                            w, c = need.get(self._tags.get(i, 0), (0, 0))
+                            need[self._tags.get(i, 0)] = (max(w, cta_tiles * sk * bn * 128 * 4), max(c, cta_tiles))
+            self._sk_ws = {tag: (torch.empty(w, dtype=torch.uint8, device=self.device), torch.zeros(c, dtype=torch.int32, device=self.device))
+                           for tag, (w, c) in need.items()}
+            self.keep.append(self._sk_ws)
             for i, (layer, x, out, out_f32, res) in sorted(self._conv_args.items()):
                 base = self.calls[i][3]
                 cands = list(plans[i])
@@ -569,7 +630,7 @@ class Plan:
                     bn, pair, nbuf = cand[:3]
                     sk = cand[3] if len(cand) > 3 else 0
                     occ = cand[4] if len(cand) > 4 else 1
-                    d = layer.desc(x, out, out_f32, res, self.precision, self.impl, tiling=(bn, pair, nbuf, sk, occ), splitk_ws=getattr(self, "_sk_ws", None))
+                    d = layer.desc(x, out, out_f32, res, self.precision, self.impl, tiling=(bn, pair, nbuf, sk, occ), splitk_ws=getattr(self, "_sk_ws", {}).get(self._tags.get(i, 0)))
                     d.tile_order = base.tile_order
                     try:
                         s = stream_ptr()
@@ -614,7 +675,7 @@ class Plan:
         overlap across them: a call's figure here is its full, un-overlapped duration."""
         with torch.cuda.device(self.device):
             n = len(self.calls)
-            self.enqueue()                                        # warm-up outside the capture
+            self.enqueue()                                        # warm-up outside the capture (timed below in linear order, branches serialised)
             torch.cuda.synchronize()
             ev = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(n + 1)]
             g = torch.cuda.CUDAGraph()
@@ -622,7 +683,8 @@ class Plan:
                 s = stream_ptr()
                 ev[0].record()
                 for i, (what, fn, args, _keep) in enumerate(self.calls):
-                    _lib.check(fn(*args, s), what)
+                    if fn is not None:
+                        _lib.check(fn(*args, s), what)
                     ev[i + 1].record()
             tot = [0.0] * n
             g.replay()

@@ -88,7 +88,9 @@ class _FlowBase(nn.Module):
                 pair = p.f32(B, 3, 2, H, W)
             out = self._build(p, self._layers, pair, B, H, W)
             if os.environ.get("FT_AUTOTUNE", "1") != "0":
-                p.autotune()                         # per-layer tile shape by measurement (engine.Plan.autotune)
+                # per-layer tile shape by measurement (engine.Plan.autotune); a plan of the same shape (another lane) lends its choices
+                twin = next((v[0].tuned for k, v in self._plans.items() if k[:-1] == key[:-1] and v[0].tuned), None)
+                p.autotune(hint=twin)
             self._plans[key] = (p, pair, out)
         return self._plans[key]
 
@@ -192,10 +194,16 @@ class _Stacked(_FlowBase):
     def _subnets(self):
         return {n: m for n, m in self.named_children() if n.startswith("flownet")}
 
-    def _c_then_s1(self, p, L, pair, B, H, W):
-        """FlowNetC -> warp -> FlowNetS_1 (models.py:121-135); returns x (fp32), x (act) and the 2nd full-res flow."""
+    def _c_then_s1(self, p, L, pair, B, H, W, sd_branch=False):
+        """FlowNetC -> warp -> FlowNetS_1 (models.py:121-135); returns x (fp32), x (act) and the 2nd full-res flow.
+        sd_branch (FlowNet2): FlowNetSD only needs the normalised pair, so it is added here as a branch of the plan that runs
+        next to the whole C -> S1 -> S2 chain (joined before the fusion network)."""
         p.rgb_max = self.rgb_max
         xf, xa = _normalise(p, pair, B, H, W, True, True, xpad=L["flownets_d"]["conv0"].in_xpad if "flownets_d" in L else (0, 0))
+        if sd_branch:
+            with p.branch() as br:
+                self._sd_flow = _up4(p, FlowNetSD.build(p, L["flownets_d"], xa, B, "sd_"), B, 1.0 / self.div_flow, "nearest")
+            self._sd_branch = br
         flow = _up4(p, FlowNetC.build(p, L["flownetc"], _frames(p, xf, B, H, W, L["flownetc"]["conv1"].in_xpad), B, "c_"), B, self.div_flow, "bilinear")
         p.taps["flownetc_flow"] = flow
         cat = _warp_concat(p, xf, flow, B, H, W, self.div_flow)
@@ -259,10 +267,11 @@ class FlowNet2(_Stacked):
 
     def _build(self, p, L, pair, B, H, W):
         lib = _lib.lib()
-        xf, xa, flow = self._c_then_s1(p, L, pair, B, H, W)
+        xf, xa, flow = self._c_then_s1(p, L, pair, B, H, W, sd_branch=True)
         cat = _warp_concat(p, xf, flow, B, H, W, self.div_flow)
         s2 = _up4(p, FlowNetS.build(p, L["flownets_2"], cat, B, "s2_"), B, self.div_flow, "nearest")            # models.py:146-147
-        sd = _up4(p, FlowNetSD.build(p, L["flownets_d"], xa, B, "sd_"), B, 1.0 / self.div_flow, "nearest")      # models.py:159-160 ('/')
+        sd = self._sd_flow                                                                                       # models.py:159-160 ('/'), built as a branch
+        self._sd_branch.join()
         p.taps["flownets2_flow"], p.taps["flownetsd_flow"] = s2, sd
         fcat = p.act(B, H, W, 11)
         p.call("fusion_concat", lib.ft_fusion_concat, xf.data_ptr(), sd.data_ptr(), s2.data_ptr(), B, H, W, fcat.struct())

@@ -73,16 +73,22 @@ def alloc_concats(p, B, H, W):
 
 def decoder(p, L, cat, c6, B, inter, tag=""):
     """Adds the ladder to plan `p`; returns the fp32 NCHW flow2 tensor [B,2,H/4,W/4]."""
-    f = p.flow_head(L["predict_flow6"], c6)
-    p.flow_up(L["upsampled_flow6_to_5"], f, cat[5].view(1024, 2))
+    # at every level the flow head (an 18-output 1x1 convolution on a handful of tiles + two tiny kernels) and the deconvolution read
+    # the same concat buffer and write disjoint slices of the next one: two branches of the plan (parallel paths of the CUDA graph)
+    with p.branch() as br:
+        f = p.flow_head(L["predict_flow6"], c6)
+        p.flow_up(L["upsampled_flow6_to_5"], f, cat[5].view(1024, 2))
     p.conv(L["deconv5"], c6, cat[5].view(512, 512))
+    br.join()
     for lvl in (5, 4, 3):
         src = cat[lvl]
         s, d = SKIP[lvl - 1]
-        head_in = p.conv(L["inter_conv%d" % lvl], src, p.act(B, src.h, src.w, L["inter_conv%d" % lvl].cout)) if inter else src
-        f = p.flow_head(L["predict_flow%d" % lvl], head_in)
-        p.flow_up(L["upsampled_flow%d_to_%d" % (lvl, lvl - 1)], f, cat[lvl - 1].view(s + d, 2))
+        with p.branch() as br:
+            head_in = p.conv(L["inter_conv%d" % lvl], src, p.act(B, src.h, src.w, L["inter_conv%d" % lvl].cout)) if inter else src
+            f = p.flow_head(L["predict_flow%d" % lvl], head_in)
+            p.flow_up(L["upsampled_flow%d_to_%d" % (lvl, lvl - 1)], f, cat[lvl - 1].view(s + d, 2))
         p.conv(L["deconv%d" % (lvl - 1)], src, cat[lvl - 1].view(s, d))
+        br.join()
     src = cat[2]
     head_in = p.conv(L["inter_conv2"], src, p.act(B, src.h, src.w, L["inter_conv2"].cout)) if inter else src
     return p.flow_head(L["predict_flow2"], head_in, name=tag + "flow2")

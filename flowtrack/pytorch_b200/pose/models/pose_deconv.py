@@ -146,10 +146,17 @@ class DeconvResnet(nn.Module):
         p.taps["pool"] = pooled
         cur = pooled
         for i, blk in enumerate(L["blocks"]):
-            t1 = p.conv(blk["c1"], cur, p.act(B, cur.h, cur.w, blk["c1"].cout))
             h2, w2 = blk["c2"].out_hw(cur.h, cur.w)
+            br = None
+            if blk["down"] is not None:           # the projection shortcut only needs the block input: a branch next to conv1 -> conv2
+                with p.branch() as br:
+                    res = p.conv(blk["down"], cur, p.act(B, h2, w2, blk["down"].cout))
+            else:
+                res = cur
+            t1 = p.conv(blk["c1"], cur, p.act(B, cur.h, cur.w, blk["c1"].cout))
             t2 = p.conv(blk["c2"], t1, p.act(B, h2, w2, blk["c2"].cout))
-            res = cur if blk["down"] is None else p.conv(blk["down"], cur, p.act(B, h2, w2, blk["down"].cout))
+            if br is not None:
+                br.join()
             cur = p.conv(blk["c3"], t2, p.act(B, h2, w2, blk["c3"].cout), res=res, name="block%d" % i)
         for i, dl in enumerate(L["deconv"]):
             cur = p.conv(dl, cur, p.act(B, 2 * cur.h, 2 * cur.w, 256), name="deconv%d" % i)

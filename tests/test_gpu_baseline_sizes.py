@@ -85,3 +85,17 @@ def test_cfg5_pose_resnet152_batch4_384x288():
 
 def test_cfg5_flownet2_full_stack_384x512():
     _check_flow("FlowNet2", 1, seed=24)
+
+
+def test_cfg5_flownet2_autotuned_plan_with_concurrent_branches(monkeypatch):
+    """The production configuration of BASELINE config 5's flow network: per-layer autotuning on (split-K is chosen for most
+    layers at one pair) and the plan's branches (FlowNetSD next to the C -> S -> S chain, flow heads next to the deconvolutions)
+    running as parallel graph paths -- each branch owns its split-K workspace.  Same oracle gate, and stable over replays."""
+    monkeypatch.setenv("FT_AUTOTUNE", "1")
+    m = _check_flow("FlowNet2", 1, seed=24)
+    plan = next(iter(m._plans.values()))[0]
+    assert plan._ntags > 5 and len(plan.tuned) > 60
+    x = recipes.flow_input(1, (384, 512), seed=24).cuda()
+    a = m(x).clone()
+    for _ in range(5):
+        assert torch.equal(m(x), a)

@@ -27,6 +27,8 @@ def table(name, plan):
     tot_fl = 0.0
     print("== %s (%s): %d calls, %.3f ms summed" % (name, prec, len(per), tot))
     for i, (what, _fn, _a, keep) in enumerate(plan.calls):
+        if _fn is None:
+            continue
         if what == "conv2d":
             d = keep
             fl = plan.flops[i]
