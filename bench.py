@@ -488,7 +488,7 @@ def parity_check(torch, cfg, pipe, pose, flow, video, state):
     ln = pipe.lanes[(pipe._next - 1) % len(pipe.lanes)]
     g_flow = ln.flow[0].cpu().numpy()
     g_hm = pipe.heatmaps[:PEOPLE].cpu()
-    g_crops = pipe.crops[:PEOPLE].cpu()
+    g_crops = pipe.person_crops((pipe._next - 1) % len(pipe.lanes))[:PEOPLE].cpu()
     w_dets, w_kps, w_flow = track_oracle.process_frame(o_pose, o_flow, frames[0, 0], frames[0, 1], dets[0], kps.reshape(pipe.F, PEOPLE, 17, 3)[0], None,
                                                        inp_res=cfg["crop_hw"], thresh=0.3, max_people=PEOPLE)
     with torch.no_grad():

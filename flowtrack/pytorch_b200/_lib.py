@@ -32,7 +32,7 @@ KIND_CONV, KIND_DECONV = 0, 1
 PREC_SPLIT, PREC_FAST = 0, 1
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
 K_PACKED, K_TAP64, K_ROW = 0, 1, 2
-ABI_VERSION = 17        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
+ABI_VERSION = 18        # FT_ABI_VERSION of include/flowtrack_b200.h this binding was written against
 
 # name -> (restype, argtypes): every symbol include/flowtrack_b200.h declares
 SIGNATURES = {
@@ -68,6 +68,7 @@ SIGNATURES = {
     "ft_track_merge": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p, c_void_p, c_void_p]),
     "ft_track_select": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p] * 6),
     "ft_crop_affine": (c_int, [c_void_p, c_int] + [c_ll] * 4 + [c_int] * 3 + [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_void_p]),
+    "ft_crop_affine_s2d": (c_int, [c_void_p, c_int] + [c_ll] * 4 + [c_int] * 3 + [c_void_p] * 3 + [c_int] * 4 + [ctypes.POINTER(FtAct), c_int, c_int, c_void_p]),
     "ft_flip_w": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "ft_flip_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ft_nms_oks": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),

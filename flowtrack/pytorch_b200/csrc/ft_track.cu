@@ -26,48 +26,98 @@ struct CropSrc {
     int H, W, C, is_u8;
 };
 
+// inverse of get_transform(center, scale, (oh, ow)) as cv::warpAffine inverts it: src = (M0*x + M1*y + M2, M3*x + M4*y + M5)
+struct CropMap {
+    double M0, M1, M2, M3, M4, M5;
+};
+__device__ __forceinline__ CropMap crop_map(double cx, double cy, double scale, int oh, int ow) {
+    CropMap m;
+    m.M0 = (double)oh / scale, m.M1 = 0.0, m.M3 = 0.0, m.M4 = (double)oh / scale;
+    m.M2 = -(double)oh * cx / scale + 0.5 * ow, m.M5 = -(double)oh * cy / scale + 0.5 * oh;
+    double D = m.M0 * m.M4 - m.M1 * m.M3;
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = m.M4 * D, A22 = m.M0 * D;
+    m.M0 = A11, m.M1 *= -D, m.M3 *= -D, m.M4 = A22;
+    const double b1 = -m.M0 * m.M2 - m.M1 * m.M5, b2 = -m.M3 * m.M2 - m.M4 * m.M5;
+    m.M2 = b1, m.M5 = b2;
+    return m;
+}
+// the C channel values of output pixel (x, y) of a crop (fixed-point bilinear taps as described above)
+template <int MAXC>
+__device__ __forceinline__ void crop_pixel(const CropSrc& src, const CropMap& m, long long f, int x, int y, float (&v)[MAXC]) {
+    const int X = (__double2int_rn(m.M0 * x * 1024.0) + __double2int_rn((m.M1 * y + m.M2) * 1024.0) + 16) >> 5;
+    const int Y = (__double2int_rn(m.M3 * x * 1024.0) + __double2int_rn((m.M4 * y + m.M5) * 1024.0) + 16) >> 5;
+    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+    const int fx = X & 31, fy = Y & 31;
+    const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy), w10 = (32 - fx) * fy, w11 = fx * fy;
+    const bool x0 = sx >= 0 && sx < src.W, x1 = sx + 1 >= 0 && sx + 1 < src.W;
+    const bool y0 = sy >= 0 && sy < src.H, y1 = sy + 1 >= 0 && sy + 1 < src.H;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        if (c >= src.C) break;
+        const long long b = f * src.sn + (long long)c * src.sc;
+        const long long o00 = b + sy * src.sh + sx * src.sw, o01 = o00 + src.sw, o10 = o00 + src.sh, o11 = o10 + src.sw;
+        if (src.is_u8) {
+            const uint8_t* p = (const uint8_t*)src.base;
+            const int s = w00 * (y0 && x0 ? (int)p[o00] : 0) + w01 * (y0 && x1 ? (int)p[o01] : 0) + w10 * (y1 && x0 ? (int)p[o10] : 0) +
+                          w11 * (y1 && x1 ? (int)p[o11] : 0);
+            v[c] = (float)((s + 512) >> 10);
+        } else {
+            const float* p = (const float*)src.base;
+            const float k = 1.f / 1024.f;
+            v[c] = (y0 && x0 ? __ldg(p + o00) : 0.f) * (w00 * k) + (y0 && x1 ? __ldg(p + o01) : 0.f) * (w01 * k) + (y1 && x0 ? __ldg(p + o10) : 0.f) * (w10 * k) +
+                   (y1 && x1 ? __ldg(p + o11) : 0.f) * (w11 * k);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) crop_affine_kernel(CropSrc src, const float* __restrict__ centers, const float* __restrict__ scales,
                                                           const int32_t* __restrict__ frame_of, int N, int oh, int ow, int reverse_c,
                                                           float* __restrict__ out) {
     const int n = blockIdx.z;
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= ow || y >= oh) return;
-    const double cx = centers[2 * n], cy = centers[2 * n + 1], scale = scales[n];
-    double M0 = (double)oh / scale, M1 = 0.0, M3 = 0.0, M4 = (double)oh / scale;
-    double M2 = -(double)oh * cx / scale + 0.5 * ow, M5 = -(double)oh * cy / scale + 0.5 * oh;
-    {   // cv::warpAffine: invert the forward map
-        double D = M0 * M4 - M1 * M3;
-        D = D != 0 ? 1. / D : 0;
-        const double A11 = M4 * D, A22 = M0 * D;
-        M0 = A11, M1 *= -D, M3 *= -D, M4 = A22;
-        const double b1 = -M0 * M2 - M1 * M5, b2 = -M3 * M2 - M4 * M5;
-        M2 = b1, M5 = b2;
-    }
-    const int X = (__double2int_rn(M0 * x * 1024.0) + __double2int_rn((M1 * y + M2) * 1024.0) + 16) >> 5;
-    const int Y = (__double2int_rn(M3 * x * 1024.0) + __double2int_rn((M4 * y + M5) * 1024.0) + 16) >> 5;
-    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
-    const int fx = X & 31, fy = Y & 31;
-    const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy), w10 = (32 - fx) * fy, w11 = fx * fy;
-    const bool x0 = sx >= 0 && sx < src.W, x1 = sx + 1 >= 0 && sx + 1 < src.W;
-    const bool y0 = sy >= 0 && sy < src.H, y1 = sy + 1 >= 0 && sy + 1 < src.H;
-    const long long f = frame_of ? frame_of[n] : 0;
+    const CropMap m = crop_map(centers[2 * n], centers[2 * n + 1], scales[n], oh, ow);
+    float v[4];
+    crop_pixel<4>(src, m, frame_of ? frame_of[n] : 0, x, y, v);
     for (int c = 0; c < src.C; ++c) {
-        const long long b = f * src.sn + (long long)c * src.sc;
-        const long long o00 = b + sy * src.sh + sx * src.sw, o01 = o00 + src.sw, o10 = o00 + src.sh, o11 = o10 + src.sw;
-        float v;
-        if (src.is_u8) {
-            const uint8_t* p = (const uint8_t*)src.base;
-            const int s = w00 * (y0 && x0 ? (int)p[o00] : 0) + w01 * (y0 && x1 ? (int)p[o01] : 0) + w10 * (y1 && x0 ? (int)p[o10] : 0) +
-                          w11 * (y1 && x1 ? (int)p[o11] : 0);
-            v = (float)((s + 512) >> 10);
-        } else {
-            const float* p = (const float*)src.base;
-            const float k = 1.f / 1024.f;
-            v = (y0 && x0 ? __ldg(p + o00) : 0.f) * (w00 * k) + (y0 && x1 ? __ldg(p + o01) : 0.f) * (w01 * k) + (y1 && x0 ? __ldg(p + o10) : 0.f) * (w10 * k) +
-                (y1 && x1 ? __ldg(p + o11) : 0.f) * (w11 * k);
-        }
         const int co = reverse_c ? src.C - 1 - c : c;
-        out[(((size_t)n * src.C + co) * oh + y) * ow + x] = v;
+        out[(((size_t)n * src.C + co) * oh + y) * ow + x] = v[c];
+    }
+}
+
+// The same crops written straight into the space-to-depth split-fp16 layout the PoseResNet stem reads (ft_pack_image_s2d):
+// dst [N, oh/2, xl + ow/2 + xr, 16], channel (py*2+px)*4 + c = crop[c, 2Y+py, 2X+px], 4th channel of every sub-pixel zero.
+// One thread per s2d pixel: 4 crop pixels x 3 channels; the fp32 crops never touch HBM (38 MB written + read per 64 crops).
+__global__ void __launch_bounds__(256) crop_affine_s2d_kernel(CropSrc src, const float* __restrict__ centers, const float* __restrict__ scales,
+                                                              const int32_t* __restrict__ frame_of, int N, int oh, int ow, int reverse_c, ft_act d, int xl) {
+    const int n = blockIdx.z;
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (X >= (ow >> 1) || Y >= (oh >> 1)) return;
+    const CropMap m = crop_map(centers[2 * n], centers[2 * n + 1], scales[n], oh, ow);
+    const long long f = frame_of ? frame_of[n] : 0;
+    float o[16];
+#pragma unroll
+    for (int sp = 0; sp < 4; ++sp) {
+        float v[3];
+        crop_pixel<3>(src, m, f, 2 * X + (sp & 1), 2 * Y + (sp >> 1), v);
+        o[sp * 4 + 0] = reverse_c ? v[2] : v[0], o[sp * 4 + 1] = v[1], o[sp * 4 + 2] = reverse_c ? v[0] : v[2], o[sp * 4 + 3] = 0.f;
+    }
+    const size_t pix = ((size_t)n * d.h + Y) * d.w + X + xl;
+    __half* hi = reinterpret_cast<__half*>(d.hi) + pix * d.ld + d.coff;
+    __half* lo = d.lo ? reinterpret_cast<__half*>(d.lo) + pix * d.ld + d.coff : nullptr;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        Half8 h8, l8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __half h0, l0, h1, l1;
+            split_f32(o[g * 8 + 2 * k], h0, l0);
+            split_f32(o[g * 8 + 2 * k + 1], h1, l1);
+            h8.v[k] = __halves2half2(h0, h1), l8.v[k] = __halves2half2(l0, l1);
+        }
+        *reinterpret_cast<Half8*>(hi + g * 8) = h8;
+        if (lo) *reinterpret_cast<Half8*>(lo + g * 8) = l8;
     }
 }
 
@@ -425,6 +475,22 @@ extern "C" int ft_crop_affine(const void* frames, int is_u8, long long sn, long 
     crop_affine_kernel<<<dim3(ceil_div(out_w, 32), ceil_div(out_h, 8), N), 256, 0, (cudaStream_t)stream>>>(s, centers, scales, frame_of, N, out_h, out_w,
                                                                                                             reverse_channels != 0, out);
     return check_launch("crop_affine_kernel");
+}
+
+extern "C" int ft_crop_affine_s2d(const void* frames, int is_u8, long long sn, long long sc, long long sh, long long sw, int H, int W, int C,
+                                  const float* centers, const float* scales, const int32_t* frame_of, int N, int out_h, int out_w, int reverse_channels,
+                                  const ft_act* dst, int xpad_l, int xpad_r, void* stream) {
+    FT_REQUIRE(H > 0 && W > 0 && C == 3 && out_h > 0 && out_w > 0 && out_h % 2 == 0 && out_w % 2 == 0 && N >= 0, "crop_affine_s2d: bad shape (3 channels, even crop size)");
+    if (N == 0) return 0;
+    FT_REQUIRE(frames && centers && scales && dst && dst->hi, "crop_affine_s2d: null pointer");
+    FT_REQUIRE(N <= 65535, "crop_affine_s2d: at most 65535 crops per call");
+    FT_REQUIRE(dst->c == 16 && dst->ld % 8 == 0 && dst->coff % 8 == 0 && dst->coff + 16 <= dst->ld && dst->n == N && dst->h == out_h / 2 &&
+                   dst->w == xpad_l + out_w / 2 + xpad_r && xpad_l >= 0 && xpad_r >= 0,
+               "crop_affine_s2d: dst must be a 16-channel view of [%d, %d, %d + %d + %d]", N, out_h / 2, xpad_l, out_w / 2, xpad_r);
+    CropSrc s = {frames, sn, sc, sh, sw, H, W, C, is_u8 != 0};
+    crop_affine_s2d_kernel<<<dim3(ceil_div(out_w / 2, 32), ceil_div(out_h / 2, 8), N), 256, 0, (cudaStream_t)stream>>>(s, centers, scales, frame_of, N, out_h, out_w,
+                                                                                                                    reverse_channels != 0, *dst, xpad_l);
+    return check_launch("crop_affine_s2d_kernel");
 }
 
 extern "C" int ft_nms(const float* dets, const int32_t* counts, int frames, int N, float thresh, int inclusive, int32_t* keep, int32_t* num_keep,

@@ -509,18 +509,21 @@ class Plan:
         self.keep.append(up)
         return dst
 
-    def enqueue(self):
-        """Issue every call of the plan on the plan device's current stream (also what graph capture records).  The device
-        guard makes the launches land on the GPU that owns the plan's buffers whatever the caller's current device is."""
+    def enqueue(self, start=0):
+        """Issue every call of the plan (from call index `start`: a caller that fills the plan's packed input itself skips the
+        packing calls) on the plan device's current stream (also what graph capture records).  The device guard makes the
+        launches land on the GPU that owns the plan's buffers whatever the caller's current device is."""
         with torch.cuda.device(self.device):
             if self._ntags == 1 or os.environ.get("FT_BRANCHES", "1") == "0":
                 s = stream_ptr()
-                for what, fn, args, _keep in self.calls:
+                for what, fn, args, _keep in self.calls[start:]:
                     if fn is not None:
                         _lib.check(fn(*args, s), what)
                 return
             streams = {0: torch.cuda.current_stream()}
             for i, (what, fn, args, _keep) in enumerate(self.calls):
+                if i < start:
+                    continue
                 if fn is None:
                     child, parent = args
                     if child not in self._streams:

@@ -133,6 +133,7 @@ class DeconvResnet(nn.Module):
         if L["stem"].cin_p == 16:                               # space-to-depth stem: [B, H/2, W/2, 16], rows zero-padded for FT_K_ROW
             x = p.act(B, H // 2, W // 2, 16, xpad=L["stem"].in_xpad)
             p.call("pack_image_s2d", _lib.lib().ft_pack_image_s2d, src.data_ptr(), B, H, W, x.struct(), x.xl, x.xr)
+            p.taps["input_s2d"] = x                             # a caller may fill this itself (ft_crop_affine_s2d) and enqueue(start=1)
             h, w = L["stem"].out_hw(H // 2, W // 2)
         else:
             x = p.act(B, H, W, 8, xpad=L["stem"].in_xpad)       # packed input, 3 -> 8 channels, rows zero-padded for the FT_K_ROW stem

@@ -103,13 +103,28 @@ class TrackingPipeline:
                                      self.dets.data_ptr(), self.count.data_ptr(), self.centers.data_ptr(), self.scales.data_ptr(), self.valid.data_ptr(), s()),
                    "track_select")
         # person crops out of the uint8 BGR current frame of every pair (frames[:, 1]), as pose_est cuts them (net_utils.py:52-57)
-        net_utils.crop_boxes_cuda(ln.frames[:, 1], self.centers, self.scales, self.frame_of, self.crop_hw, reverse_channels=False, out=self.crops)
-        self.pose_plan.enqueue()
+        xs = self.pose_plan.taps.get("input_s2d")
+        if xs is not None and self.pose_plan.calls[0][0] == "pack_image_s2d":
+            # ... written straight into the stem's space-to-depth split-fp16 input (ft_crop_affine_s2d): the fp32 crops never exist
+            fr = ln.frames[:, 1]
+            sn, sh, sw, sc = fr.stride()
+            _lib.check(L.ft_crop_affine_s2d(fr.data_ptr(), 1, sn, sc, sh, sw, H, W, 3, self.centers.data_ptr(), self.scales.data_ptr(), self.frame_of.data_ptr(),
+                                            n, self.crop_hw[0], self.crop_hw[1], 0, xs.struct(), xs.xl, xs.xr, s()), "crop_affine_s2d")
+            self.pose_plan.enqueue(start=1)
+        else:
+            net_utils.crop_boxes_cuda(ln.frames[:, 1], self.centers, self.scales, self.frame_of, self.crop_hw, reverse_channels=False, out=self.crops)
+            self.pose_plan.enqueue()
         net_utils.final_preds_cuda(self.heatmaps, self.centers, self.scales, True, out=self.keypoints, valid=self.valid)
         o, a, b = ln.d_out, F * P * 5, F * P * 5 + F
         o[:a].copy_(self.dets.view(-1))
         o[a:b].copy_(self.count)
         o[b:].copy_(self.keypoints.view(-1))
+
+    def person_crops(self, lane):
+        """The fp32 crops [F*P,3,h,w] of the lane's last step, recomputed from the state it left (centres / scales of the selected
+        boxes, the lane's current frames) -- the fused path never materialises them; tests and the bench's parity leg use this."""
+        ln = self.lanes[lane]
+        return net_utils.crop_boxes_cuda(ln.frames[:, 1], self.centers, self.scales, self.frame_of, self.crop_hw, reverse_channels=False)
 
     def capture(self):
         with torch.cuda.device(self.device):

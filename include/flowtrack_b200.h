@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define FT_ABI_VERSION 17
+#define FT_ABI_VERSION 18
 
 /* ---- activations ------------------------------------------------------------------------------
  * Inter-layer activations live in HBM as "split-fp16" NHWC planes: value = float(hi) + float(lo),
@@ -267,6 +267,12 @@ int ft_box_propagation(const float* kps, const int32_t* frame_of, int N, int K, 
 int ft_crop_affine(const void* frames, int is_u8, long long sn, long long sc, long long sh, long long sw,
                    int H, int W, int C, const float* centers, const float* scales, const int32_t* frame_of,
                    int N, int out_h, int out_w, int reverse_channels, float* out, void* stream);
+/* The same crops (3-channel frames, even crop size) written straight into the space-to-depth split-fp16 layout of the PoseResNet
+ * stem (see ft_pack_image_s2d): dst [N, out_h/2, xpad_l + out_w/2 + xpad_r, 16].  The fp32 crops never touch HBM.          */
+int ft_crop_affine_s2d(const void* frames, int is_u8, long long sn, long long sc, long long sh, long long sw,
+                       int H, int W, int C, const float* centers, const float* scales, const int32_t* frame_of,
+                       int N, int out_h, int out_w, int reverse_channels, const ft_act* dst, int xpad_l, int xpad_r,
+                       void* stream);
 /* Flip test (tools/pose/main.py:289-299; swaplr_image, lib/pose/utils/transforms.py:140-170).
  * ft_flip_w mirrors the last axis: src/dst [rows, W] fp32 (a [B,C,H,W] batch is rows = B*C*H).
  * ft_flip_merge: out[n,c,y,x] = 0.5 * (hm[n,c,y,x] + hm_flipped[n, perm[c], y, W-1-x]); perm [C] int32 is the left/right

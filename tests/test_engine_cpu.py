@@ -134,7 +134,7 @@ def test_library_exports_every_declared_symbol():
     declared -= {"ft_act", "ft_conv_desc"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     l = _lib.lib()                                         # loads the .so and resolves every symbol
-    assert l.ft_abi_version() == _lib.ABI_VERSION == 17
+    assert l.ft_abi_version() == _lib.ABI_VERSION == 18
     assert l.ft_sizeof(0) == ctypes.sizeof(_lib.FtAct) == 40 and l.ft_sizeof(1) == ctypes.sizeof(_lib.FtConvDesc)
 
 

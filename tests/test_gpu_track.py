@@ -5,7 +5,9 @@ import numpy as np
 import pytest
 import torch
 
+from flowtrack.pytorch_b200 import _lib
 from flowtrack.pytorch_b200.tracking import net_utils
+from tests import gpu_util
 from oracle import track_oracle
 from tests.golden import recipes
 
@@ -200,3 +202,55 @@ def test_nms_oks_matches_reference_outputs():
             p["score"] = float(1.0 - i / (2.0 * n))
         assert evaluation.nms_oks(p2, 0.4, recipes.COCO_DELTA, 0.3) == track_oracle.nms_oks(p2, 0.4, recipes.COCO_DELTA, 0.3)
     assert evaluation.nms_oks([], 0.5, recipes.COCO_DELTA) == []
+
+
+def test_crop_affine_s2d_equals_crop_then_pack():
+    """ft_crop_affine_s2d (the tracker's fused path) == ft_crop_affine followed by ft_pack_image_s2d, bit for bit, from uint8 BGR
+    frames addressed by strides (the current frame of every pair) and from float frames with reversed channels."""
+    from flowtrack.pytorch_b200 import engine
+    from flowtrack.pytorch_b200.tracking import net_utils
+    rng = np.random.default_rng(11)
+    F_, H, W, oh, ow, P = 3, 96, 128, 64, 48, 2
+    pairs = torch.from_numpy(rng.integers(0, 255, (F_, 2, H, W, 3), dtype=np.uint8)).cuda()
+    n = F_ * P
+    centers = torch.tensor(rng.uniform(20, 100, (n, 2)), dtype=torch.float32).cuda()
+    scales = torch.tensor(rng.uniform(40, 140, n), dtype=torch.float32).cuda()
+    frame_of = (torch.arange(n, dtype=torch.int32) // P).cuda()
+    L = _lib.lib()
+    for frames, is_u8, rev in ((pairs[:, 1], 1, 0), (pairs[:, 1].permute(0, 3, 1, 2).float().contiguous(), 0, 1)):
+        crops = net_utils.crop_boxes_cuda(frames, centers, scales, frame_of, (oh, ow), reverse_channels=bool(rev))
+        want = engine.Act(n, oh // 2, ow // 2, 16, "cuda", xpad=(4, 4))
+        _lib.check(L.ft_pack_image_s2d(crops.data_ptr(), n, oh, ow, want.struct(), 4, 4, gpu_util.sp()), "pack_s2d")
+        got = engine.Act(n, oh // 2, ow // 2, 16, "cuda", xpad=(4, 4))
+        if is_u8:
+            sn, sh, sw, sc = frames.stride()
+        else:
+            sn, sc, sh, sw = frames.stride()
+        _lib.check(L.ft_crop_affine_s2d(frames.data_ptr(), is_u8, sn, sc, sh, sw, H, W, 3, centers.data_ptr(), scales.data_ptr(), frame_of.data_ptr(), n, oh, ow,
+                                        rev, got.struct(), 4, 4, gpu_util.sp()), "crop_s2d")
+        torch.cuda.synchronize()
+        assert torch.equal(got.hi, want.hi) and torch.equal(got.lo, want.lo)
+        assert got.hi[:, :, :4].abs().max() == 0 and got.hi[:, :, -4:].abs().max() == 0          # the zero columns stay untouched
+
+
+def test_pack_pair_u8_equals_float_pack():
+    """ft_pack_pair_u8 (uint8 BGR frames) == ft_pack_pair on the same pair as float RGB [B,3,2,H,W]: the x_f32 output within float
+    rounding of the mean (exact integer sums vs a float reduction), the split-fp16 view likewise; zero columns untouched."""
+    from flowtrack.pytorch_b200 import engine
+    rng = np.random.default_rng(5)
+    B, H, W = 3, 64, 128
+    u8 = torch.from_numpy(rng.integers(0, 255, (B, 2, H, W, 3), dtype=np.uint8)).cuda()
+    pair = u8.flip(4).permute(0, 4, 1, 2, 3).float().contiguous()                               # [B,3(RGB),2,H,W]
+    L = _lib.lib()
+    xf_a, xf_b = torch.empty(B, 6, H, W, device="cuda"), torch.empty(B, 6, H, W, device="cuda")
+    a, b = engine.Act(B, H, W, 6, "cuda", xpad=(4, 8)), engine.Act(B, H, W, 6, "cuda", xpad=(4, 8))
+    ws = torch.zeros(L.ft_pack_pair_ws_floats(B), device="cuda")
+    _lib.check(L.ft_pack_pair(pair.data_ptr(), B, H, W, 255.0, ws.data_ptr(), xf_a.data_ptr(), a.struct(), 4, 8, gpu_util.sp()), "pack_pair")
+    sums = torch.zeros(B * 3, dtype=torch.int64, device="cuda")
+    _lib.check(L.ft_pack_pair_u8(u8.data_ptr(), B, H, W, 1, 255.0, sums.data_ptr(), xf_b.data_ptr(), b.struct(), 4, 8, gpu_util.sp()), "pack_pair_u8")
+    torch.cuda.synchronize()
+    ref = (pair - pair.reshape(B, 3, -1).mean(-1).view(B, 3, 1, 1, 1)) / 255.0
+    ref = torch.cat((ref[:, :, 0], ref[:, :, 1]), dim=1)
+    assert (xf_b - ref).abs().max() < 1e-6 and (xf_a - xf_b).abs().max() < 1e-6
+    assert (a.to_nchw(6) - b.to_nchw(6)).abs().max() < 1e-6 and (b.to_nchw(6) - ref).abs().max() < 1e-6
+    assert b.hi[:, :, :4].abs().max() == 0 and b.hi[:, :, -8:].abs().max() == 0 and b.to_nchw()[:, 6:].abs().max() == 0
