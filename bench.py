@@ -320,12 +320,14 @@ def run_ours(args):
                 p.collect(pending.pop(0))
         return device_step, host_step, host_drain
 
-    def timed(p, fn, steps, warmup, drain=None):
+    def timed(p, fn, steps, warmup, drain=None, profile=False):
         for _ in range(warmup):
             fn()
         if drain:
             drain()
         barrier()
+        if profile:                                      # ncu --profile-from-start off: the launch list is exactly the timed steps
+            torch.cuda.profiler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         p.fence_in()                                     # the pipeline's streams start after e0 ...
@@ -336,6 +338,8 @@ def run_ours(args):
         p.fence_out()                                    # ... and e1 waits for all of them
         e1.record()
         barrier()
+        if profile:
+            torch.cuda.profiler.stop()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -351,7 +355,7 @@ def run_ours(args):
         for _ in range(10):
             pipe.step_device()
         torch.cuda.synchronize()
-    ms = timed(pipe, device_step, args.steps, args.warmup)
+    ms = timed(pipe, device_step, args.steps, args.warmup, profile=args.profile_range)
     ms_e2e = timed(pipe, host_step, args.steps, max(1, args.warmup // 2), drain=host_drain)
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
@@ -661,6 +665,7 @@ def main():
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
+    ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed device steps (for ncu --profile-from-start off)")
     ap.add_argument("--preroll", type=float, default=0.6, help="seconds of untimed steps while nvidia-smi starts sampling")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -91,7 +91,7 @@ struct alignas(64) ConvK {
     // split-K (ft_conv_desc.splitk): a work item is (tile, k-split); items = num_tiles * splits, item -> split = item / num_tiles
     int splits, kb_split, num_items;
     FastDiv fd_num_tiles;
-    float* sk_ws;            // partial accumulators [cta tile][split][BN columns][128 rows] fp32
+    float* sk_ws;            // partial accumulators [cta tile][split][BN / 4 column quads][128 rows][4] fp32
     unsigned* sk_cnt;        // arrivals per cta tile (zero between launches: the last arriver resets its slot)
     int bw, bh, bn, lg_bw, lg_bh, tiles_w, tiles_h;
     int act;
@@ -541,13 +541,16 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, OCC) co
                 // ---- split-K: park this item's partial sums; the CTA whose part arrives last adds all parts (in split order, so the
                 // result does not depend on who is last) and finalizes the tile ----
                 const size_t cta_tile = (size_t)wi.tile * CL + crank;
-                float* wsp = p.sk_ws + (cta_tile * p.splits + wi.sp) * (size_t)(BN * BM);
+                // workspace layout per (cta tile, part): [BN / 4 column quads][128 rows] float4 -- a thread's 16-byte accesses, lanes =
+                // consecutive rows: every warp access is 512 contiguous bytes
+                uint4* wsp = reinterpret_cast<uint4*>(p.sk_ws + (cta_tile * p.splits + wi.sp) * (size_t)(BN * BM)) + row;
 #pragma unroll
                 for (int j = 0; j < MINE; ++j) {
                     const int cc = group + 2 * j;
                     if (cc < NSLAB) {
 #pragma unroll
-                        for (int i = 0; i < SLAB; ++i) wsp[(size_t)(cc * SLAB + i) * BM + row] = __uint_as_float(acc[j * SLAB + i]);   // lanes = consecutive rows: coalesced
+                        for (int i = 0; i < SLAB / 4; ++i)
+                            wsp[(size_t)(cc * (SLAB / 4) + i) * BM] = make_uint4(acc[j * SLAB + 4 * i], acc[j * SLAB + 4 * i + 1], acc[j * SLAB + 4 * i + 2], acc[j * SLAB + 4 * i + 3]);
                     }
                 }
                 __threadfence();
@@ -563,17 +566,37 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, OCC) co
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(ss_base + (uint32_t)G::SS_BYTES));
                 if (!last) continue;                                            // warp-uniform (the whole CTA takes the same way)
                 __threadfence();
-                const float* w0 = p.sk_ws + cta_tile * p.splits * (size_t)(BN * BM);
+                // all of a part's loads are issued before the first add (MINE * SLAB / 4 independent 16-byte loads in flight per thread):
+                // the reduction costs about one L2 round trip per part, not one per element
+                const uint4* w0 = reinterpret_cast<const uint4*>(p.sk_ws + cta_tile * p.splits * (size_t)(BN * BM)) + row;
+                for (int sp = 0; sp < p.splits; ++sp) {
+                    const uint4* q = w0 + (size_t)sp * (BN * BM / 4);
+                    uint4 v[MINE * (SLAB / 4)];
 #pragma unroll
-                for (int j = 0; j < MINE; ++j) {
-                    const int cc = group + 2 * j;
-                    if (cc < NSLAB) {
+                    for (int j = 0; j < MINE; ++j) {
+                        const int cc = group + 2 * j;
+                        if (cc < NSLAB) {
 #pragma unroll
-                        for (int i = 0; i < SLAB; ++i) {
-                            const float* q = w0 + (size_t)(cc * SLAB + i) * BM + row;
-                            float v = __ldcg(q);
-                            for (int sp = 1; sp < p.splits; ++sp) v += __ldcg(q + (size_t)sp * (BN * BM));
-                            acc[j * SLAB + i] = __float_as_uint(v);
+                            for (int i = 0; i < SLAB / 4; ++i) v[j * (SLAB / 4) + i] = __ldcg(q + (size_t)(cc * (SLAB / 4) + i) * BM);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < MINE; ++j) {
+                        const int cc = group + 2 * j;
+                        if (cc < NSLAB) {
+#pragma unroll
+                            for (int i = 0; i < SLAB / 4; ++i) {
+                                const uint4 t = v[j * (SLAB / 4) + i];
+                                uint32_t* a4 = acc + j * SLAB + 4 * i;
+                                if (sp == 0) {
+                                    a4[0] = t.x, a4[1] = t.y, a4[2] = t.z, a4[3] = t.w;
+                                } else {
+                                    a4[0] = __float_as_uint(__uint_as_float(a4[0]) + __uint_as_float(t.x));
+                                    a4[1] = __float_as_uint(__uint_as_float(a4[1]) + __uint_as_float(t.y));
+                                    a4[2] = __float_as_uint(__uint_as_float(a4[2]) + __uint_as_float(t.z));
+                                    a4[3] = __float_as_uint(__uint_as_float(a4[3]) + __uint_as_float(t.w));
+                                }
+                            }
                         }
                     }
                 }

@@ -295,39 +295,43 @@ __global__ void pack_image_s2d_kernel(const float* __restrict__ src, int B, int 
     }
 }
 
-__global__ void maxpool3x3s2_kernel(ft_act in, ft_act out) {
+// grid: x = (output column, 8-channel group) pairs, y = output rows, z = images -- no 64-bit index arithmetic per element (the
+// grid-stride form spent most of its instructions on size_t divisions)
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(ft_act in, ft_act out) {
     const int groups = out.c / 8;
-    const size_t total = (size_t)out.n * out.h * out.w * groups;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ox = t / groups, g = t - ox * groups;
+    if (ox >= out.w) return;
     const __half* ih = reinterpret_cast<const __half*>(in.hi);
     const __half* il = reinterpret_cast<const __half*>(in.lo);
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i % groups);
-        const size_t pix = i / groups;
-        const int ox = (int)(pix % out.w), oy = (int)((pix / out.w) % out.h), b = (int)(pix / ((size_t)out.w * out.h));
-        float best[8];
+    for (int b = blockIdx.z; b < out.n; b += gridDim.z)
+        for (int oy = blockIdx.y; oy < out.h; oy += gridDim.y) {
+            float best[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) best[k] = -INFINITY;
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int iy = oy * 2 + dy, ix = ox * 2 + dx;
-                if (iy < 0 || iy >= in.h || ix < 0 || ix >= in.w) continue;
-                const size_t off = (((size_t)b * in.h + iy) * in.w + ix) * in.ld + in.coff + g * 8;
-                const Half8 h = *reinterpret_cast<const Half8*>(ih + off);
-                Half8 l;
-                if (il) l = *reinterpret_cast<const Half8*>(il + off);
+            for (int k = 0; k < 8; ++k) best[k] = -INFINITY;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float2 f = __half22float2(h.v[k]);
-                    if (il) {
-                        const float2 fl = __half22float2(l.v[k]);
-                        f.x += fl.x, f.y += fl.y;
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int iy = oy * 2 + dy, ix = ox * 2 + dx;
+                    if (iy < 0 || iy >= in.h || ix < 0 || ix >= in.w) continue;
+                    const size_t off = (((size_t)b * in.h + iy) * in.w + ix) * in.ld + in.coff + g * 8;
+                    const Half8 h = *reinterpret_cast<const Half8*>(ih + off);
+                    Half8 l;
+                    if (il) l = *reinterpret_cast<const Half8*>(il + off);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float2 f = __half22float2(h.v[k]);
+                        if (il) {
+                            const float2 fl = __half22float2(l.v[k]);
+                            f.x += fl.x, f.y += fl.y;
+                        }
+                        best[2 * k] = fmaxf(best[2 * k], f.x);
+                        best[2 * k + 1] = fmaxf(best[2 * k + 1], f.y);
                     }
-                    best[2 * k] = fmaxf(best[2 * k], f.x);
-                    best[2 * k + 1] = fmaxf(best[2 * k + 1], f.y);
                 }
-            }
-        store8(out, pix, g * 8, best);
-    }
+            store8(out, ((size_t)b * out.h + oy) * out.w + ox, g * 8, best);
+        }
 }
 
 #define PAIR_MEAN_CHUNKS 64
@@ -389,75 +393,116 @@ __global__ void pack_pair_kernel(const float* __restrict__ pair, const float* __
 
 // ---- uint8 frame pairs (the reference's cv2 frames, net_utils.py:83-87): frames [B,2,H,W,3] uint8, channel order BGR (cv2) or RGB ----
 // per (b, memory channel) sums over both frames: exact integer arithmetic, one atomicAdd per block and channel
-__global__ void pair_u8_sum_kernel(const uint8_t* __restrict__ frames, size_t bytes_per_pair, unsigned long long* __restrict__ sums) {
+__global__ void __launch_bounds__(256) pair_u8_sum_kernel(const uint8_t* __restrict__ frames, size_t bytes_per_pair, unsigned long long* __restrict__ sums) {
     const int b = blockIdx.y;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(frames + (size_t)b * bytes_per_pair);
-    const size_t groups = bytes_per_pair / 12;                      // 12 bytes = 4 pixels: the channel of every byte lane is fixed per thread
+    const uint32_t groups = (uint32_t)(bytes_per_pair / 12);        // 12 bytes = 4 pixels: the channel of every byte lane is fixed per word
     uint32_t s0 = 0, s1 = 0, s2 = 0;
-    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
         const uint32_t a = __ldg(w + 3 * g), c = __ldg(w + 3 * g + 1), d = __ldg(w + 3 * g + 2);
-        // bytes: a = c0 c1 c2 c0 | c = c1 c2 c0 c1 | d = c2 c0 c1 c2
-        s0 += (a & 255u) + (a >> 24) + ((c >> 16) & 255u) + ((d >> 8) & 255u);
-        s1 += ((a >> 8) & 255u) + (c & 255u) + (c >> 24) + ((d >> 16) & 255u);
-        s2 += ((a >> 16) & 255u) + ((c >> 8) & 255u) + (d & 255u) + (d >> 24);
+        // bytes: a = c0 c1 c2 c0 | c = c1 c2 c0 c1 | d = c2 c0 c1 c2  -> byte-select dot products
+        s0 = __dp4a(a, 0x01000001u, s0), s0 = __dp4a(c, 0x00010000u, s0), s0 = __dp4a(d, 0x00000100u, s0);
+        s1 = __dp4a(a, 0x00000100u, s1), s1 = __dp4a(c, 0x01000001u, s1), s1 = __dp4a(d, 0x00010000u, s1);
+        s2 = __dp4a(a, 0x00010000u, s2), s2 = __dp4a(c, 0x00000100u, s2), s2 = __dp4a(d, 0x01000001u, s2);
     }
     for (int o = 16; o > 0; o >>= 1) {
         s0 += __shfl_xor_sync(0xffffffffu, s0, o), s1 += __shfl_xor_sync(0xffffffffu, s1, o), s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(sums + b * 3 + 0, (unsigned long long)s0);
-        atomicAdd(sums + b * 3 + 1, (unsigned long long)s1);
-        atomicAdd(sums + b * 3 + 2, (unsigned long long)s2);
+    // one atomicAdd per block and channel (integers: the result does not depend on the order)
+    __shared__ uint32_t sh[3][8];
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) sh[0][warp] = s0, sh[1][warp] = s1, sh[2][warp] = s2;
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned long long t = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sh[threadIdx.x][k];
+        atomicAdd(sums + b * 3 + threadIdx.x, t);
     }
 }
 
-__global__ void pack_pair_u8_kernel(const uint8_t* __restrict__ frames, const unsigned long long* __restrict__ sums, int B, int H, int W, int bgr,
-                                    float rgb_max, float* __restrict__ x_f32, ft_act d, int has_dst, int xl) {
+// one thread per 4 consecutive pixels of a row (W % 4 == 0): 12 bytes per frame as three 32-bit loads, 4 x 16-byte stores per plane;
+// grid: x = pixel quads of a row, y = rows, z = pairs
+__global__ void __launch_bounds__(128) pack_pair_u8_kernel(const uint8_t* __restrict__ frames, const unsigned long long* __restrict__ sums, int B, int H, int W, int bgr,
+                                                           float rgb_max, float* __restrict__ x_f32, ft_act d, int has_dst, int xl) {
+    const int xq = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xq * 4 >= W) return;
     const size_t plane = (size_t)H * W;
-    const size_t total = (size_t)B * plane;
     const double inv_n = 1.0 / (2.0 * (double)plane);
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = i / plane, p = i % plane;
-        float v[8];
+    for (int b = blockIdx.z; b < B; b += gridDim.z) {
+        float mean[3];                                                               // of memory channel mc (models.py:112: per sample and colour, both frames)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int mc = bgr ? 2 - c : c;                                       // memory channel holding colour c of the RGB flow input
-            const float mean = (float)((double)sums[b * 3 + mc] * inv_n);         // models.py:112 (per sample and colour, both frames)
+        for (int mc = 0; mc < 3; ++mc) mean[mc] = (float)((double)sums[b * 3 + mc] * inv_n);
+        for (int y = blockIdx.y; y < H; y += gridDim.y) {
+            const size_t p0 = (size_t)y * W + 4 * xq;
+            float v[4][8];
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
-                const float t = ((float)frames[((b * 2 + f) * plane + p) * 3 + mc] - mean) / rgb_max;      // x channel = f*3 + c (models.py:116-119)
-                v[f * 3 + c] = t;
-                if (x_f32) x_f32[(b * 6 + f * 3 + c) * plane + p] = t;
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(frames + (((size_t)b * 2 + f) * plane + p0) * 3);
+                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+                const uint32_t by[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24, w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
+                                         w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+#pragma unroll
+                for (int px = 0; px < 4; ++px)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int mc = bgr ? 2 - c : c;                               // memory channel holding colour c of the RGB flow input
+                        v[px][f * 3 + c] = ((float)by[px * 3 + mc] - mean[mc]) / rgb_max;   // x channel = f*3 + c (models.py:116-119)
+                    }
             }
-        }
-        v[6] = v[7] = 0.f;
-        if (has_dst) {
-            const size_t dpix = (b * H + p / W) * d.w + p % W + xl;
-            store8(d, dpix, 0, v);
-            const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int g = 1; g < d.c / 8; ++g) store8(d, dpix, g * 8, z);
+            if (x_f32) {
+#pragma unroll
+                for (int ch = 0; ch < 6; ++ch)
+                    *reinterpret_cast<float4*>(x_f32 + ((size_t)b * 6 + ch) * plane + p0) = make_float4(v[0][ch], v[1][ch], v[2][ch], v[3][ch]);
+            }
+            if (has_dst) {
+                const size_t dpix = ((size_t)b * H + y) * d.w + 4 * xq + xl;        // d.w = physical row pitch (W + zero columns)
+                const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+                for (int px = 0; px < 4; ++px) {
+                    v[px][6] = v[px][7] = 0.f;
+                    store8(d, dpix + px, 0, v[px]);
+                    for (int g = 1; g < d.c / 8; ++g) store8(d, dpix + px, g * 8, z);
+                }
+            }
         }
     }
 }
 
-__global__ void upsample4x_kernel(const float* __restrict__ src, float* __restrict__ dst, int BC, int h, int w, float mul, int mode) {
+// ---------------- upsample4x ----------------
+// one thread per SOURCE column: the four output columns 4x .. 4x+3 of one output row (a 16-byte store when dst allows it);
+// grid: x = source columns, y = output rows, z = planes.  Same arithmetic per element as a one-thread-per-output kernel.
+template <int MODE>
+__global__ void __launch_bounds__(128) upsample4x_kernel(const float* __restrict__ src, float* __restrict__ dst, int BC, int h, int w, float mul, int vec) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
     const int H = 4 * h, W = 4 * w;
-    const size_t total = (size_t)BC * H * W;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int X = (int)(i % W), Y = (int)((i / W) % H);
-        const float* p = src + (i / ((size_t)H * W)) * h * w;
-        float v;
-        if (mode == 1) {
-            v = p[(Y >> 2) * w + (X >> 2)];
-        } else {
-            // align_corners=False: src = (dst + 0.5)/4 - 0.5, clamped below at 0 (ATen area_pixel_compute_source_index)
-            const float sy = fmaxf((Y + 0.5f) * 0.25f - 0.5f, 0.f), sx = fmaxf((X + 0.5f) * 0.25f - 0.5f, 0.f);
-            const int y0 = (int)sy, x0 = (int)sx;
-            const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-            const float ly = sy - y0, lx = sx - x0;
-            v = (1.f - ly) * ((1.f - lx) * p[y0 * w + x0] + lx * p[y0 * w + x1]) + ly * ((1.f - lx) * p[y1 * w + x0] + lx * p[y1 * w + x1]);
+    for (int bc = blockIdx.z; bc < BC; bc += gridDim.z) {
+        const float* p = src + (size_t)bc * h * w;
+        for (int Y = blockIdx.y; Y < H; Y += gridDim.y) {
+            float o[4];
+            if (MODE == 1) {
+                o[0] = o[1] = o[2] = o[3] = p[(Y >> 2) * w + x] * mul;
+            } else {
+                // align_corners=False: src = (dst + 0.5)/4 - 0.5, clamped below at 0 (ATen area_pixel_compute_source_index)
+                const float sy = fmaxf((Y + 0.5f) * 0.25f - 0.5f, 0.f);
+                const int y0 = (int)sy, y1 = min(y0 + 1, h - 1);
+                const float ly = sy - y0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float sx = fmaxf((4 * x + k + 0.5f) * 0.25f - 0.5f, 0.f);
+                    const int x0 = (int)sx, x1 = min(x0 + 1, w - 1);
+                    const float lx = sx - x0;
+                    const float v = (1.f - ly) * ((1.f - lx) * p[y0 * w + x0] + lx * p[y0 * w + x1]) + ly * ((1.f - lx) * p[y1 * w + x0] + lx * p[y1 * w + x1]);
+                    o[k] = v * mul;
+                }
+            }
+            float* q = dst + ((size_t)bc * H + Y) * W + 4 * x;
+            if (vec) {
+                *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+                q[0] = o[0], q[1] = o[1], q[2] = o[2], q[3] = o[3];
+            }
         }
-        dst[i] = v * mul;
     }
 }
 
@@ -527,60 +572,63 @@ __global__ void fusion_concat_kernel(const float* __restrict__ x6, const float* 
 // (the input is read once) and this kernel finishes the convolution by the shifted sum
 //   flow[n, c, y, x] = bias[c] + sum_t part[n, t*2 + c, y + r - 1, x + s - 1]   (zero outside the map).
 // =====================================================================================================
-__global__ void flow_head_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ flow, int B, int H, int W) {
+// grid: x = columns, y = rows, z = images
+__global__ void __launch_bounds__(128) flow_head_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ flow, int B, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
     const size_t plane = (size_t)H * W;
-    const size_t total = (size_t)B * plane;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = i / plane, p = i % plane;
-        const int x = (int)(p % W), y = (int)(p / W);
-        float u = bias ? bias[0] : 0.f, v = bias ? bias[1] : 0.f;
+    for (int b = blockIdx.z; b < B; b += gridDim.z)
+        for (int y = blockIdx.y; y < H; y += gridDim.y) {
+            float u = bias ? bias[0] : 0.f, v = bias ? bias[1] : 0.f;
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int yy = y + r - 1, xx = x + s - 1;
-                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                const float* q = part + ((b * 18 + (r * 3 + s) * 2) * H + yy) * W + xx;
-                u += q[0];
-                v += q[plane];
-            }
-        flow[(b * 2) * plane + p] = u;
-        flow[(b * 2 + 1) * plane + p] = v;
-    }
+                for (int s = 0; s < 3; ++s) {
+                    const int yy = y + r - 1, xx = x + s - 1;
+                    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                    const float* q = part + (((size_t)b * 18 + (r * 3 + s) * 2) * H + yy) * W + xx;
+                    u += q[0];
+                    v += q[plane];
+                }
+            const size_t p = (size_t)y * W + x;
+            flow[((size_t)b * 2) * plane + p] = u;
+            flow[((size_t)b * 2 + 1) * plane + p] = v;
+        }
 }
 
 // upsampled_flow*_to_*: ConvTranspose2d(2, 2, 4, 2, 1) of the fp32 flow (FlowNetS.py:41-44), written as split-fp16
 // NHWC channels [0,2) (+6 zeros) of a slice of the next level's concat buffer.  w is the module's [2(in)][2(out)][4][4].
-__global__ void flow_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ w, const float* __restrict__ bias,
-                                     int B, int h, int wd, ft_act d) {
+// grid: x = output columns, y = output rows, z = images
+__global__ void __launch_bounds__(128) flow_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ w, const float* __restrict__ bias,
+                                                            int B, int h, int wd, ft_act d) {
     __shared__ float sw[64];
     if (threadIdx.x < 64) sw[threadIdx.x] = w[threadIdx.x];
     __syncthreads();
     const int Ho = 2 * h, Wo = 2 * wd;
-    const size_t total = (size_t)B * Ho * Wo;
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ox >= Wo) return;
     const size_t plane = (size_t)h * wd;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
-        const size_t b = i / ((size_t)Wo * Ho);
-        float o[8] = {bias ? bias[0] : 0.f, bias ? bias[1] : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        // oy = 2*iy - 1 + ky  ->  ky = oy + 1 - 2*iy in [0,4)
+    for (int b = blockIdx.z; b < B; b += gridDim.z)
+        for (int oy = blockIdx.y; oy < Ho; oy += gridDim.y) {
+            float o[8] = {bias ? bias[0] : 0.f, bias ? bias[1] : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            // oy = 2*iy - 1 + ky  ->  ky = oy + 1 - 2*iy in [0,4)
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            const int iy = (oy + 1) / 2 - a, ky = oy + 1 - 2 * iy;
-            if (iy < 0 || iy >= h) continue;
+            for (int a = 0; a < 2; ++a) {
+                const int iy = (oy + 1) / 2 - a, ky = oy + 1 - 2 * iy;
+                if (iy < 0 || iy >= h) continue;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int ix = (ox + 1) / 2 - c, kx = ox + 1 - 2 * ix;
-                if (ix < 0 || ix >= wd) continue;
-                const float f0 = flow[(b * 2) * plane + (size_t)iy * wd + ix], f1 = flow[(b * 2 + 1) * plane + (size_t)iy * wd + ix];
-                o[0] = fmaf(f0, sw[(0 * 2 + 0) * 16 + ky * 4 + kx], o[0]);
-                o[0] = fmaf(f1, sw[(1 * 2 + 0) * 16 + ky * 4 + kx], o[0]);
-                o[1] = fmaf(f0, sw[(0 * 2 + 1) * 16 + ky * 4 + kx], o[1]);
-                o[1] = fmaf(f1, sw[(1 * 2 + 1) * 16 + ky * 4 + kx], o[1]);
+                for (int c = 0; c < 2; ++c) {
+                    const int ix = (ox + 1) / 2 - c, kx = ox + 1 - 2 * ix;
+                    if (ix < 0 || ix >= wd) continue;
+                    const float f0 = flow[((size_t)b * 2) * plane + (size_t)iy * wd + ix], f1 = flow[((size_t)b * 2 + 1) * plane + (size_t)iy * wd + ix];
+                    o[0] = fmaf(f0, sw[(0 * 2 + 0) * 16 + ky * 4 + kx], o[0]);
+                    o[0] = fmaf(f1, sw[(1 * 2 + 0) * 16 + ky * 4 + kx], o[0]);
+                    o[1] = fmaf(f0, sw[(0 * 2 + 1) * 16 + ky * 4 + kx], o[1]);
+                    o[1] = fmaf(f1, sw[(1 * 2 + 1) * 16 + ky * 4 + kx], o[1]);
+                }
             }
+            store8(d, ((size_t)b * Ho + oy) * Wo + ox, 0, o);
         }
-        store8(d, i, 0, o);
-    }
 }
 
 // =====================================================================================================
@@ -744,7 +792,7 @@ int ft_maxpool3x3s2(const ft_act* in, const ft_act* out, void* stream) {
     if (int e = check_act(in, "maxpool.in", false)) return e;
     if (int e = check_act(out, "maxpool.out", false)) return e;
     FT_REQUIRE(out->h == (in->h + 1) / 2 && out->w == (in->w + 1) / 2 && out->n == in->n && out->c == in->c, "maxpool: shape mismatch");
-    maxpool3x3s2_kernel<<<grid_for((size_t)out->n * out->h * out->w * (out->c / 8), 256), 256, 0, (cudaStream_t)stream>>>(*in, *out);
+    maxpool3x3s2_kernel<<<dim3(ceil_div(out->w * (out->c / 8), 256), min(out->h, 65535), min(out->n, 65535)), 256, 0, (cudaStream_t)stream>>>(*in, *out);
     return check_launch("maxpool3x3s2_kernel");
 }
 
@@ -794,7 +842,8 @@ int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* m
 int ft_pack_pair_u8(const uint8_t* frames, int B, int H, int W, int bgr, float rgb_max, void* sum_ws, float* x_f32, const ft_act* dst, int xpad_l,
                     int xpad_r, void* stream) {
     FT_REQUIRE(frames && sum_ws && B > 0 && H > 0 && W > 0, "pack_pair_u8: bad arguments");
-    FT_REQUIRE(((size_t)H * W) % 4 == 0 && ((uintptr_t)frames & 3) == 0, "pack_pair_u8: H*W must be a multiple of 4 and the frames 4-byte aligned");
+    FT_REQUIRE(W % 4 == 0 && ((uintptr_t)frames & 3) == 0, "pack_pair_u8: W must be a multiple of 4 and the frames 4-byte aligned");
+    FT_REQUIRE(!x_f32 || ((uintptr_t)x_f32 & 15) == 0, "pack_pair_u8: x_f32 must be 16-byte aligned");
     FT_REQUIRE(B <= 65535 && ((uintptr_t)sum_ws & 7) == 0, "pack_pair_u8: at most 65535 pairs; the workspace must be 8-byte aligned");
     ft_act d = {};
     if (dst) {
@@ -812,14 +861,17 @@ int ft_pack_pair_u8(const uint8_t* frames, int B, int H, int W, int bgr, float r
     const int bx = min(ceil_div((int)(bytes_per_pair / 12), 256), max(1, device_sms() * 8 / B));
     pair_u8_sum_kernel<<<dim3(bx, B), 256, 0, s>>>(frames, bytes_per_pair, (unsigned long long*)sum_ws);
     if (check_launch("pair_u8_sum_kernel")) return 1;
-    pack_pair_u8_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, s>>>(frames, (const unsigned long long*)sum_ws, B, H, W, bgr != 0, rgb_max, x_f32, d,
-                                                                          dst != nullptr, xpad_l);
+    pack_pair_u8_kernel<<<dim3(ceil_div(W / 4, 128), min(H, 65535), B), 128, 0, s>>>(frames, (const unsigned long long*)sum_ws, B, H, W, bgr != 0, rgb_max, x_f32, d,
+                                                                                      dst != nullptr, xpad_l);
     return check_launch("pack_pair_u8_kernel");
 }
 
 int ft_upsample4x(const float* src, float* dst, int B, int C, int h, int w, float mul, int mode, void* stream) {
     FT_REQUIRE(src && dst && B > 0 && C > 0 && h > 0 && w > 0 && (mode == 0 || mode == 1), "upsample4x: bad arguments");
-    upsample4x_kernel<<<grid_for((size_t)B * C * h * w * 16, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, B * C, h, w, mul, mode);
+    const dim3 grid(ceil_div(w, 128), min(4 * h, 65535), min(B * C, 65535));
+    const int vec = ((uintptr_t)dst & 15) == 0;
+    if (mode == 1) upsample4x_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(src, dst, B * C, h, w, mul, vec);
+    else upsample4x_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(src, dst, B * C, h, w, mul, vec);
     return check_launch("upsample4x_kernel");
 }
 
@@ -839,7 +891,7 @@ int ft_fusion_concat(const float* x6, const float* flow_sd, const float* flow_s2
 
 int ft_flow_head(const float* part, const float* bias, float* flow, int B, int H, int W, void* stream) {
     FT_REQUIRE(part && flow && B > 0 && H > 0 && W > 0, "flow_head: bad arguments");
-    flow_head_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(part, bias, flow, B, H, W);
+    flow_head_kernel<<<dim3(ceil_div(W, 128), min(H, 65535), min(B, 65535)), 128, 0, (cudaStream_t)stream>>>(part, bias, flow, B, H, W);
     return check_launch("flow_head_kernel");
 }
 
@@ -847,7 +899,7 @@ int ft_flow_upsample(const float* flow, const float* w, const float* bias, int B
     if (int e = check_act(dst, "flow_upsample.dst", false)) return e;
     FT_REQUIRE(flow && w && B > 0 && h > 0 && wd > 0, "flow_upsample: bad arguments");
     FT_REQUIRE(dst->c == 8 && dst->n == B && dst->h == 2 * h && dst->w == 2 * wd, "flow_upsample: dst must be an 8-channel view of a [%d,%d,%d] map", B, 2 * h, 2 * wd);
-    flow_upsample_kernel<<<grid_for((size_t)B * h * wd * 4, 256), 256, 0, (cudaStream_t)stream>>>(flow, w, bias, B, h, wd, *dst);
+    flow_upsample_kernel<<<dim3(ceil_div(2 * wd, 128), min(2 * h, 65535), min(B, 65535)), 128, 0, (cudaStream_t)stream>>>(flow, w, bias, B, h, wd, *dst);
     return check_launch("flow_upsample_kernel");
 }
 
