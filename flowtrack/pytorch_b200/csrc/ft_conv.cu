@@ -84,7 +84,8 @@ struct alignas(64) ConvK {
     int n_phase, taps, cb, kb_main, kb_total, k_pad, chunk;
     FastDiv fd_n_tiles, fd_m_units, fd_tiles_w, fd_tiles_h;
     int rev;        // tile_order: walk the tile list from the end (see ft_conv_desc.tile_order)
-    int dbg_skip;   // bring-up/profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no weight loads, 4 = no MMAs, 8 = no TMA stores (results are garbage)
+    int dbg_skip;   // bring-up/profiling knob (FT_DEV_SKIP): 1 = no A loads, 2 = no weight loads, 4 = no MMAs, 8 = no TMA stores; split-K: 16 = no partial-sum
+                    // stores, 32 = every thread fences (the old protocol), 128 = the last arriver reads part 0 only (results are garbage)
     int M, m_tiles, n_tiles, num_tiles;
     int n_tiles_w;               // n-tiles of the weight image (= n_tiles, or 2 * n_tiles for QUAD, whose work items span two n-tiles)
     int half_dx, half_dy, half_dn;   // QUAD: offset of the second half box inside a tile's pixel box
@@ -544,32 +545,40 @@ __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS_TMA, OCC) co
                 // workspace layout per (cta tile, part): [BN / 4 column quads][128 rows] float4 -- a thread's 16-byte accesses, lanes =
                 // consecutive rows: every warp access is 512 contiguous bytes
                 uint4* wsp = reinterpret_cast<uint4*>(p.sk_ws + (cta_tile * p.splits + wi.sp) * (size_t)(BN * BM)) + row;
+                if (!(p.dbg_skip & 16)) {
 #pragma unroll
-                for (int j = 0; j < MINE; ++j) {
-                    const int cc = group + 2 * j;
-                    if (cc < NSLAB) {
+                    for (int j = 0; j < MINE; ++j) {
+                        const int cc = group + 2 * j;
+                        if (cc < NSLAB) {
 #pragma unroll
-                        for (int i = 0; i < SLAB / 4; ++i)
-                            wsp[(size_t)(cc * (SLAB / 4) + i) * BM] = make_uint4(acc[j * SLAB + 4 * i], acc[j * SLAB + 4 * i + 1], acc[j * SLAB + 4 * i + 2], acc[j * SLAB + 4 * i + 3]);
+                            for (int i = 0; i < SLAB / 4; ++i)
+                                wsp[(size_t)(cc * (SLAB / 4) + i) * BM] = make_uint4(acc[j * SLAB + 4 * i], acc[j * SLAB + 4 * i + 1], acc[j * SLAB + 4 * i + 2], acc[j * SLAB + 4 * i + 3]);
+                        }
                     }
                 }
-                __threadfence();
+                // release / acquire through ONE thread (the cooperative-groups grid-barrier pattern): the named barrier orders every
+                // epilogue thread's partial-sum stores before thread 0's fence + counter increment; on the way back thread 0's fence
+                // after the increment orders the other parts' stores before the loads the whole CTA issues behind the second barrier.
+                // (256 threads each executing MEMBAR.SC.GPU with their stores in flight cost several microseconds per work item.)
+                if (p.dbg_skip & 32) __threadfence();
                 named_bar_sync(3, EPI_THREADS);
                 if (threadIdx.x == 0) {
+                    __threadfence();
                     const unsigned old = atomicAdd(p.sk_cnt + cta_tile, 1u);
                     const unsigned last = old == (unsigned)(p.splits - 1);
                     if (last) p.sk_cnt[cta_tile] = 0u;                          // every part has arrived: leave the slot clean for the next launch
+                    __threadfence();
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(ss_base + (uint32_t)G::SS_BYTES), "r"(last) : "memory");
                 }
                 named_bar_sync(3, EPI_THREADS);
                 uint32_t last;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(ss_base + (uint32_t)G::SS_BYTES));
                 if (!last) continue;                                            // warp-uniform (the whole CTA takes the same way)
-                __threadfence();
+                if (p.dbg_skip & 32) __threadfence();
                 // all of a part's loads are issued before the first add (MINE * SLAB / 4 independent 16-byte loads in flight per thread):
                 // the reduction costs about one L2 round trip per part, not one per element
                 const uint4* w0 = reinterpret_cast<const uint4*>(p.sk_ws + cta_tile * p.splits * (size_t)(BN * BM)) + row;
-                for (int sp = 0; sp < p.splits; ++sp) {
+                for (int sp = 0; sp < ((p.dbg_skip & 128) ? 1 : p.splits); ++sp) {
                     const uint4* q = w0 + (size_t)sp * (BN * BM / 4);
                     uint4 v[MINE * (SLAB / 4)];
 #pragma unroll
