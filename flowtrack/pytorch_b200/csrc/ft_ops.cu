@@ -207,31 +207,37 @@ __device__ __forceinline__ float bilin_sample(const float* __restrict__ p, const
     return v;
 }
 
-__global__ void resample2d_kernel(const float* __restrict__ img, const float* __restrict__ flow, float* __restrict__ out,
-                                  int B, int C, int H, int W) {
+// Per-pixel kernels: x from blockIdx.x / threadIdx.x, rows from blockIdx.y, images from blockIdx.z (the latter two grid-strided past
+// 65535) -- no 64-bit division per element (the grid-stride-over-a-linear-index form spent most of its instructions on them).
+#define FT_FOR_PIXELS(B_, H_, W_, bvar_, yvar_, xvar_)                         \
+    const int xvar_ = blockIdx.x * blockDim.x + threadIdx.x;                   \
+    if (xvar_ < (W_))                                                          \
+        for (int bvar_ = blockIdx.z; bvar_ < (B_); bvar_ += gridDim.z)         \
+            for (int yvar_ = blockIdx.y; yvar_ < (H_); yvar_ += gridDim.y)
+constexpr int PIX_THREADS = 128;
+
+__global__ void __launch_bounds__(PIX_THREADS) resample2d_kernel(const float* __restrict__ img, const float* __restrict__ flow, float* __restrict__ out,
+                                                                 int B, int C, int H, int W) {
     const size_t plane = (size_t)H * W;
-    const size_t total = (size_t)B * plane;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / plane);
-        const float dx = flow[((size_t)b * 2) * plane + (size_t)y * W + x];
-        const float dy = flow[((size_t)b * 2 + 1) * plane + (size_t)y * W + x];
+    FT_FOR_PIXELS(B, H, W, b, y, x) {
+        const size_t p = (size_t)y * W + x;
+        const float dx = flow[((size_t)b * 2) * plane + p];
+        const float dy = flow[((size_t)b * 2 + 1) * plane + p];
         const Bilin s = bilin_setup((float)x + dx, (float)y + dy, W, H);
-        for (int c = 0; c < C; ++c)
-            out[((size_t)b * C + c) * plane + (size_t)y * W + x] = bilin_sample(img + ((size_t)b * C + c) * plane, s, W);
+        for (int c = 0; c < C; ++c) out[((size_t)b * C + c) * plane + p] = bilin_sample(img + ((size_t)b * C + c) * plane, s, W);
     }
 }
 
-__global__ void channelnorm_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C, int H, int W) {
+__global__ void __launch_bounds__(PIX_THREADS) channelnorm_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C, int H, int W) {
     const size_t plane = (size_t)H * W;
-    const size_t total = (size_t)B * plane;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = i / plane, p = i % plane;
+    FT_FOR_PIXELS(B, H, W, b, y, px) {
+        const size_t p = (size_t)y * W + px;
         float r = 0.f;
         for (int c = 0; c < C; ++c) {
-            const float v = x[(b * C + c) * plane + p];
+            const float v = x[((size_t)b * C + c) * plane + p];
             r = fmaf(v, v, r);
         }
-        out[i] = sqrtf(r);
+        out[(size_t)b * plane + p] = sqrtf(r);
     }
 }
 
@@ -275,12 +281,10 @@ __global__ void pack_image_kernel(const float* __restrict__ src, long long sb, l
 }
 
 // space-to-depth packing of a 3-channel image (see ft_pack_image_s2d): one thread per s2d pixel = 16 channels
-__global__ void pack_image_s2d_kernel(const float* __restrict__ src, int B, int H, int W, ft_act d, int xl) {
+__global__ void __launch_bounds__(PIX_THREADS) pack_image_s2d_kernel(const float* __restrict__ src, int B, int H, int W, ft_act d, int xl) {
     const int H2 = H >> 1, W2 = W >> 1;
-    const size_t total = (size_t)B * H2 * W2;
     const size_t plane = (size_t)H * W;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int X = (int)(i % W2), Y = (int)((i / W2) % H2), b = (int)(i / ((size_t)W2 * H2));
+    FT_FOR_PIXELS(B, H2, W2, b, Y, X) {
         const float* s = src + (size_t)b * 3 * plane + (size_t)(2 * Y) * W + 2 * X;
         float v[16];
 #pragma unroll
@@ -365,25 +369,24 @@ __global__ void pair_mean_final_kernel(const double* __restrict__ partial, int H
     if (threadIdx.x == 0) mean[blockIdx.x] = (float)(s / (double)HW2);
 }
 
-__global__ void pack_pair_kernel(const float* __restrict__ pair, const float* __restrict__ mean, int B, int H, int W,
-                                 float rgb_max, float* __restrict__ x_f32, ft_act d, int has_dst, int xl) {
+__global__ void __launch_bounds__(PIX_THREADS) pack_pair_kernel(const float* __restrict__ pair, const float* __restrict__ mean, int B, int H, int W,
+                                                                float rgb_max, float* __restrict__ x_f32, ft_act d, int has_dst, int xl) {
     const size_t plane = (size_t)H * W;
-    const size_t total = (size_t)B * plane;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = i / plane, p = i % plane;
+    FT_FOR_PIXELS(B, H, W, b, y, x) {
+        const size_t p = (size_t)y * W + x;
         float v[8];
 #pragma unroll
         for (int f = 0; f < 2; ++f)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 // pair is [B,3,2,H,W]; x channel = f*3 + c  (models.py:116-119)
-                const float t = (pair[((b * 3 + c) * 2 + f) * plane + p] - mean[b * 3 + c]) / rgb_max;
+                const float t = (pair[(((size_t)b * 3 + c) * 2 + f) * plane + p] - mean[b * 3 + c]) / rgb_max;
                 v[f * 3 + c] = t;
-                if (x_f32) x_f32[(b * 6 + f * 3 + c) * plane + p] = t;
+                if (x_f32) x_f32[((size_t)b * 6 + f * 3 + c) * plane + p] = t;
             }
         v[6] = v[7] = 0.f;
         if (has_dst) {
-            const size_t dpix = (b * H + p / W) * d.w + p % W + xl;       // d.w = physical row pitch (W + zero columns)
+            const size_t dpix = ((size_t)b * H + y) * d.w + x + xl;       // d.w = physical row pitch (W + zero columns)
             store8(d, dpix, 0, v);
             const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int g = 1; g < d.c / 8; ++g) store8(d, dpix, g * 8, z);
@@ -506,61 +509,57 @@ __global__ void __launch_bounds__(128) upsample4x_kernel(const float* __restrict
     }
 }
 
-__global__ void warp_concat_kernel(const float* __restrict__ x6, const float* __restrict__ flow, float div_flow, int B, int H, int W, ft_act d) {
+__global__ void __launch_bounds__(PIX_THREADS) warp_concat_kernel(const float* __restrict__ x6, const float* __restrict__ flow, float div_flow, int B, int H, int W, ft_act d) {
     const size_t plane = (size_t)H * W;
-    const size_t total = (size_t)B * plane;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = i / plane, p = i % plane;
-        const int x = (int)(p % W), y = (int)(p / W);
-        const float u = flow[(b * 2) * plane + p], v = flow[(b * 2 + 1) * plane + p];
+    FT_FOR_PIXELS(B, H, W, b, y, x) {
+        const size_t p = (size_t)y * W + x;
+        const float u = flow[((size_t)b * 2) * plane + p], v = flow[((size_t)b * 2 + 1) * plane + p];
         const Bilin s = bilin_setup((float)x + u, (float)y + v, W, H);
         float o[16];
         float e = 0.f;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) o[c] = x6[(b * 6 + c) * plane + p];
+        for (int c = 0; c < 6; ++c) o[c] = x6[((size_t)b * 6 + c) * plane + p];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            o[6 + c] = bilin_sample(x6 + (b * 6 + 3 + c) * plane, s, W);
+            o[6 + c] = bilin_sample(x6 + ((size_t)b * 6 + 3 + c) * plane, s, W);
             const float df = o[c] - o[6 + c];
             e = fmaf(df, df, e);
         }
         o[9] = u / div_flow, o[10] = v / div_flow, o[11] = sqrtf(e);
         o[12] = o[13] = o[14] = o[15] = 0.f;
-        store8(d, i, 0, o);
-        store8(d, i, 8, o + 8);
+        store8(d, (size_t)b * plane + p, 0, o);
+        store8(d, (size_t)b * plane + p, 8, o + 8);
     }
 }
 
-__global__ void fusion_concat_kernel(const float* __restrict__ x6, const float* __restrict__ fsd, const float* __restrict__ fs2,
-                                     int B, int H, int W, ft_act d) {
+__global__ void __launch_bounds__(PIX_THREADS) fusion_concat_kernel(const float* __restrict__ x6, const float* __restrict__ fsd, const float* __restrict__ fs2,
+                                                                    int B, int H, int W, ft_act d) {
     const size_t plane = (size_t)H * W;
-    const size_t total = (size_t)B * plane;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = i / plane, p = i % plane;
-        const int x = (int)(p % W), y = (int)(p / W);
+    FT_FOR_PIXELS(B, H, W, b, y, x) {
+        const size_t p = (size_t)y * W + x;
         float o[16];
         float err[2];
         const float* fl[2] = {fsd, fs2};
 #pragma unroll
-        for (int c = 0; c < 3; ++c) o[c] = x6[(b * 6 + c) * plane + p];
+        for (int c = 0; c < 3; ++c) o[c] = x6[((size_t)b * 6 + c) * plane + p];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const float u = fl[k][(b * 2) * plane + p], v = fl[k][(b * 2 + 1) * plane + p];
+            const float u = fl[k][((size_t)b * 2) * plane + p], v = fl[k][((size_t)b * 2 + 1) * plane + p];
             o[3 + 2 * k] = u, o[4 + 2 * k] = v;
             o[7 + k] = sqrtf(fmaf(u, u, v * v));
             const Bilin s = bilin_setup((float)x + u, (float)y + v, W, H);
             float e = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float df = o[c] - bilin_sample(x6 + (b * 6 + 3 + c) * plane, s, W);
+                const float df = o[c] - bilin_sample(x6 + ((size_t)b * 6 + 3 + c) * plane, s, W);
                 e = fmaf(df, df, e);
             }
             err[k] = sqrtf(e);
         }
         o[9] = err[0], o[10] = err[1];
         o[11] = o[12] = o[13] = o[14] = o[15] = 0.f;
-        store8(d, i, 0, o);
-        store8(d, i, 8, o + 8);
+        store8(d, (size_t)b * plane + p, 0, o);
+        store8(d, (size_t)b * plane + p, 8, o + 8);
     }
 }
 
@@ -778,13 +777,13 @@ int ft_correlation_forward(const float* in1, const float* in2, float* out, int B
 
 int ft_resample2d_forward(const float* img, const float* flow, float* out, int B, int C, int H, int W, void* stream) {
     FT_REQUIRE(img && flow && out && B > 0 && C > 0 && H > 0 && W > 0, "resample2d: bad arguments");
-    resample2d_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(img, flow, out, B, C, H, W);
+    resample2d_kernel<<<dim3(ceil_div(W, PIX_THREADS), min(H, 65535), min(B, 65535)), PIX_THREADS, 0, (cudaStream_t)stream>>>(img, flow, out, B, C, H, W);
     return check_launch("resample2d_kernel");
 }
 
 int ft_channelnorm_forward(const float* x, float* out, int B, int C, int H, int W, void* stream) {
     FT_REQUIRE(x && out && B > 0 && C > 0 && H > 0 && W > 0, "channelnorm: bad arguments");
-    channelnorm_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, C, H, W);
+    channelnorm_kernel<<<dim3(ceil_div(W, PIX_THREADS), min(H, 65535), min(B, 65535)), PIX_THREADS, 0, (cudaStream_t)stream>>>(x, out, B, C, H, W);
     return check_launch("channelnorm_kernel");
 }
 
@@ -812,7 +811,7 @@ int ft_pack_image_s2d(const float* src, int B, int H, int W, const ft_act* dst, 
     FT_REQUIRE(((uintptr_t)src & 7) == 0, "pack_image_s2d: src must be 8-byte aligned");
     FT_REQUIRE(dst->c == 16 && dst->n == B && dst->h == H / 2 && xpad_l >= 0 && xpad_r >= 0 && dst->w == W / 2 + xpad_l + xpad_r,
                "pack_image_s2d: destination must be [B, H/2, xpad_l + W/2 + xpad_r, 16] (got n=%d h=%d w=%d c=%d)", dst->n, dst->h, dst->w, dst->c);
-    pack_image_s2d_kernel<<<grid_for((size_t)B * (H / 2) * (W / 2), 256), 256, 0, (cudaStream_t)stream>>>(src, B, H, W, *dst, xpad_l);
+    pack_image_s2d_kernel<<<dim3(ceil_div(W / 2, PIX_THREADS), min(H / 2, 65535), min(B, 65535)), PIX_THREADS, 0, (cudaStream_t)stream>>>(src, B, H, W, *dst, xpad_l);
     return check_launch("pack_image_s2d_kernel");
 }
 
@@ -835,7 +834,7 @@ int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* m
     if (check_launch("pair_mean_partial_kernel")) return 1;
     pair_mean_final_kernel<<<B * 3, 32, 0, (cudaStream_t)stream>>>(partial, 2 * H * W, mean);
     if (check_launch("pair_mean_final_kernel")) return 1;
-    pack_pair_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(pair, mean, B, H, W, rgb_max, x_f32, d, dst != nullptr, xpad_l);
+    pack_pair_kernel<<<dim3(ceil_div(W, PIX_THREADS), min(H, 65535), min(B, 65535)), PIX_THREADS, 0, (cudaStream_t)stream>>>(pair, mean, B, H, W, rgb_max, x_f32, d, dst != nullptr, xpad_l);
     return check_launch("pack_pair_kernel");
 }
 
@@ -878,14 +877,14 @@ int ft_upsample4x(const float* src, float* dst, int B, int C, int h, int w, floa
 int ft_warp_concat(const float* x6, const float* flow, float div_flow, int B, int H, int W, const ft_act* dst, void* stream) {
     if (int e = check_act(dst, "warp_concat.dst", false)) return e;
     FT_REQUIRE(x6 && flow && dst->c == 16 && dst->n == B && dst->h == H && dst->w == W, "warp_concat: bad arguments");
-    warp_concat_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x6, flow, div_flow, B, H, W, *dst);
+    warp_concat_kernel<<<dim3(ceil_div(W, PIX_THREADS), min(H, 65535), min(B, 65535)), PIX_THREADS, 0, (cudaStream_t)stream>>>(x6, flow, div_flow, B, H, W, *dst);
     return check_launch("warp_concat_kernel");
 }
 
 int ft_fusion_concat(const float* x6, const float* flow_sd, const float* flow_s2, int B, int H, int W, const ft_act* dst, void* stream) {
     if (int e = check_act(dst, "fusion_concat.dst", false)) return e;
     FT_REQUIRE(x6 && flow_sd && flow_s2 && dst->c == 16 && dst->n == B && dst->h == H && dst->w == W, "fusion_concat: bad arguments");
-    fusion_concat_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x6, flow_sd, flow_s2, B, H, W, *dst);
+    fusion_concat_kernel<<<dim3(ceil_div(W, PIX_THREADS), min(H, 65535), min(B, 65535)), PIX_THREADS, 0, (cudaStream_t)stream>>>(x6, flow_sd, flow_s2, B, H, W, *dst);
     return check_launch("fusion_concat_kernel");
 }
 

@@ -76,8 +76,11 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(CropSrc src, const flo
                                                           float* __restrict__ out) {
     const int n = blockIdx.z;
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    __shared__ CropMap sm;                      // one double-precision inversion per block instead of one per thread
+    if (threadIdx.x == 0) sm = crop_map(centers[2 * n], centers[2 * n + 1], scales[n], oh, ow);
+    __syncthreads();
     if (x >= ow || y >= oh) return;
-    const CropMap m = crop_map(centers[2 * n], centers[2 * n + 1], scales[n], oh, ow);
+    const CropMap m = sm;
     float v[4];
     crop_pixel<4>(src, m, frame_of ? frame_of[n] : 0, x, y, v);
     for (int c = 0; c < src.C; ++c) {
@@ -93,8 +96,11 @@ __global__ void __launch_bounds__(256) crop_affine_s2d_kernel(CropSrc src, const
                                                               const int32_t* __restrict__ frame_of, int N, int oh, int ow, int reverse_c, ft_act d, int xl) {
     const int n = blockIdx.z;
     const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    __shared__ CropMap sm;                      // one double-precision inversion per block instead of one per thread
+    if (threadIdx.x == 0) sm = crop_map(centers[2 * n], centers[2 * n + 1], scales[n], oh, ow);
+    __syncthreads();
     if (X >= (ow >> 1) || Y >= (oh >> 1)) return;
-    const CropMap m = crop_map(centers[2 * n], centers[2 * n + 1], scales[n], oh, ow);
+    const CropMap m = sm;
     const long long f = frame_of ? frame_of[n] : 0;
     float o[16];
 #pragma unroll

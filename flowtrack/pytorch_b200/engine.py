@@ -16,6 +16,7 @@ from . import _lib
 from ._lib import FtAct, FtConvDesc
 
 BK = 64  # k-block (fp16 elements) = one 128-byte swizzle row
+AUTOTUNE_MARGIN = 0.015  # Plan.autotune(): a candidate tiling replaces the static choice only if it is more than this fraction faster
 
 
 def round_up(a, b):
@@ -627,7 +628,8 @@ class Plan:
                                                                  # measured slower on every layer (profiles/r02m_autotune_log.txt), so opt-in: FT_QUAD=1
                 if len(cands) < 2:
                     continue
-                best = None
+                best = t_dflt = None
+                dflt = tuple(layer.choose_tiling(x.n, x.h, x.w, self.precision)) + (1, 0, 1)
                 sk = 0
                 for cand in cands:
                     bn, pair, nbuf = cand[:3]
@@ -663,6 +665,10 @@ class Plan:
                               % (i, "deconv" if layer.kind else "conv", layer.kh, layer.cin, layer.cout, x.n, x.h, x.w, bn, pair, nbuf, sk, occ, t * 1e3), flush=True)
                     if best is None or t < best[0]:
                         best = (t, bn, pair, nbuf, sk, occ, d)
+                    if (bn, pair, nbuf, sk, occ) == dflt:
+                        t_dflt = (t, bn, pair, nbuf, sk, occ, d)
+                if best is not None and t_dflt is not None and best[0] > t_dflt[0] * (1.0 - AUTOTUNE_MARGIN):
+                    best = t_dflt                            # within the measurement noise of the static choice: keep that
                 if best is not None:
                     t, bn, pair, nbuf, sk, occ, d = best
                     self.calls[i] = ("conv2d", fn, (ctypes.byref(d),), d)
