@@ -458,17 +458,20 @@ def build_record():
 
 def read_traffic_capture(_lib):
     """DRAM bytes per conv launch from the committed `ncu --set full` capture of the same plans (profiles/r02_conv_traffic.json;
-    produced by tools/dev/ncu_conv_traffic.py).  The capture records the SHA-256 of the kernel sources it was taken with; a
-    capture of other sources is refused (traffic = null) instead of being reported against today's kernels."""
+    produced by tools/dev/jobs/evidence.sh + tools/dev/ncu_summary.py).  The capture records the SHA-256 of conv_tc_kernel's
+    translation unit and headers (build.kernel_hash(CONV_SOURCES)); a capture of other conv sources, or a library that was not built
+    from the sources in the tree, is refused (traffic = null) instead of being reported against today's kernels."""
     try:
         from flowtrack.pytorch_b200 import build as ft_build
         with open(os.path.join(ROOT, "profiles", "r02_conv_traffic.json")) as f:
             tr = json.load(f)
-        if tr.get("source_sha256") != ft_build.source_hash():
-            return None, {"refused": "profiles/r02_conv_traffic.json was captured with other kernel sources (%s...), not the ones built here"
-                          % str(tr.get("source_sha256"))[:12]}
+        if ft_build.read_info().get("source_sha256") != ft_build.source_hash():
+            return None, {"refused": "libflowtrack_b200.so was not built from the sources in this tree"}
+        if tr.get("kernel_sources_sha256") != ft_build.kernel_hash(ft_build.CONV_SOURCES):
+            return None, {"refused": "profiles/r02_conv_traffic.json was captured with other conv kernel sources (%s...), not the ones built here"
+                          % str(tr.get("kernel_sources_sha256"))[:12]}
         return tr["dram_bytes_per_launch"], {"tensor_pipe_active_pct_time_weighted": tr.get("tensor_pipe_active_pct_time_weighted"), "source": tr.get("source"),
-                                              "source_sha256": tr.get("source_sha256")}
+                                              "kernel_sources": tr.get("kernel_sources"), "kernel_sources_sha256": tr.get("kernel_sources_sha256")}
     except Exception:
         return None, None
 

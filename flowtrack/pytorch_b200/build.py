@@ -36,6 +36,20 @@ def source_hash():
     return h.hexdigest()
 
 
+def kernel_hash(names):
+    """SHA-256 over the compile flags and the named files of csrc/ (a kernel's own translation unit plus the headers it includes):
+    what an ncu capture of ONE kernel is stamped with, so that a change to an unrelated source file does not void it."""
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    for f in sorted(names):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
+CONV_SOURCES = ("ft_conv.cu", "ft_tc.cuh", "ft_common.cuh")     # conv_tc_kernel
+CORR_SOURCES = ("ft_corr.cu", "ft_tc.cuh", "ft_common.cuh")     # corr_pair_kernel
+
+
 def read_info():
     try:
         with open(INFO) as f:

@@ -423,50 +423,32 @@ __global__ void __launch_bounds__(256) pair_u8_sum_kernel(const uint8_t* __restr
     }
 }
 
-// one thread per 4 consecutive pixels of a row (W % 4 == 0): 12 bytes per frame as three 32-bit loads, 4 x 16-byte stores per plane;
-// grid: x = pixel quads of a row, y = rows, z = pairs
-__global__ void __launch_bounds__(128) pack_pair_u8_kernel(const uint8_t* __restrict__ frames, const unsigned long long* __restrict__ sums, int B, int H, int W, int bgr,
+// one thread per pixel (a warp's two 16-byte stores per plane are 512 contiguous bytes; a 4-pixels-per-thread variant with wider
+// loads measured 2.4x slower on its strided stores); grid: x = columns, y = rows, z = pairs
+__global__ void __launch_bounds__(256) pack_pair_u8_kernel(const uint8_t* __restrict__ frames, const unsigned long long* __restrict__ sums, int B, int H, int W, int bgr,
                                                            float rgb_max, float* __restrict__ x_f32, ft_act d, int has_dst, int xl) {
-    const int xq = blockIdx.x * blockDim.x + threadIdx.x;
-    if (xq * 4 >= W) return;
     const size_t plane = (size_t)H * W;
     const double inv_n = 1.0 / (2.0 * (double)plane);
-    for (int b = blockIdx.z; b < B; b += gridDim.z) {
-        float mean[3];                                                               // of memory channel mc (models.py:112: per sample and colour, both frames)
+    FT_FOR_PIXELS(B, H, W, b, y, x) {
+        const size_t p = (size_t)y * W + x;
+        float v[8];
 #pragma unroll
-        for (int mc = 0; mc < 3; ++mc) mean[mc] = (float)((double)sums[b * 3 + mc] * inv_n);
-        for (int y = blockIdx.y; y < H; y += gridDim.y) {
-            const size_t p0 = (size_t)y * W + 4 * xq;
-            float v[4][8];
+        for (int c = 0; c < 3; ++c) {
+            const int mc = bgr ? 2 - c : c;                                       // memory channel holding colour c of the RGB flow input
+            const float mean = (float)((double)sums[b * 3 + mc] * inv_n);         // models.py:112 (per sample and colour, both frames)
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
-                const uint32_t* q = reinterpret_cast<const uint32_t*>(frames + (((size_t)b * 2 + f) * plane + p0) * 3);
-                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
-                const uint32_t by[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24, w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
-                                         w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
-#pragma unroll
-                for (int px = 0; px < 4; ++px)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const int mc = bgr ? 2 - c : c;                               // memory channel holding colour c of the RGB flow input
-                        v[px][f * 3 + c] = ((float)by[px * 3 + mc] - mean[mc]) / rgb_max;   // x channel = f*3 + c (models.py:116-119)
-                    }
+                const float t = ((float)__ldg(frames + (((size_t)b * 2 + f) * plane + p) * 3 + mc) - mean) / rgb_max;      // x channel = f*3 + c (models.py:116-119)
+                v[f * 3 + c] = t;
+                if (x_f32) x_f32[((size_t)b * 6 + f * 3 + c) * plane + p] = t;
             }
-            if (x_f32) {
-#pragma unroll
-                for (int ch = 0; ch < 6; ++ch)
-                    *reinterpret_cast<float4*>(x_f32 + ((size_t)b * 6 + ch) * plane + p0) = make_float4(v[0][ch], v[1][ch], v[2][ch], v[3][ch]);
-            }
-            if (has_dst) {
-                const size_t dpix = ((size_t)b * H + y) * d.w + 4 * xq + xl;        // d.w = physical row pitch (W + zero columns)
-                const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-                for (int px = 0; px < 4; ++px) {
-                    v[px][6] = v[px][7] = 0.f;
-                    store8(d, dpix + px, 0, v[px]);
-                    for (int g = 1; g < d.c / 8; ++g) store8(d, dpix + px, g * 8, z);
-                }
-            }
+        }
+        v[6] = v[7] = 0.f;
+        if (has_dst) {
+            const size_t dpix = ((size_t)b * H + y) * d.w + x + xl;               // d.w = physical row pitch (W + zero columns)
+            store8(d, dpix, 0, v);
+            const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int g = 1; g < d.c / 8; ++g) store8(d, dpix, g * 8, z);
         }
     }
 }
@@ -841,8 +823,7 @@ int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* m
 int ft_pack_pair_u8(const uint8_t* frames, int B, int H, int W, int bgr, float rgb_max, void* sum_ws, float* x_f32, const ft_act* dst, int xpad_l,
                     int xpad_r, void* stream) {
     FT_REQUIRE(frames && sum_ws && B > 0 && H > 0 && W > 0, "pack_pair_u8: bad arguments");
-    FT_REQUIRE(W % 4 == 0 && ((uintptr_t)frames & 3) == 0, "pack_pair_u8: W must be a multiple of 4 and the frames 4-byte aligned");
-    FT_REQUIRE(!x_f32 || ((uintptr_t)x_f32 & 15) == 0, "pack_pair_u8: x_f32 must be 16-byte aligned");
+    FT_REQUIRE(((size_t)H * W) % 4 == 0 && ((uintptr_t)frames & 3) == 0, "pack_pair_u8: H*W must be a multiple of 4 and the frames 4-byte aligned");
     FT_REQUIRE(B <= 65535 && ((uintptr_t)sum_ws & 7) == 0, "pack_pair_u8: at most 65535 pairs; the workspace must be 8-byte aligned");
     ft_act d = {};
     if (dst) {
@@ -860,8 +841,8 @@ int ft_pack_pair_u8(const uint8_t* frames, int B, int H, int W, int bgr, float r
     const int bx = min(ceil_div((int)(bytes_per_pair / 12), 256), max(1, device_sms() * 8 / B));
     pair_u8_sum_kernel<<<dim3(bx, B), 256, 0, s>>>(frames, bytes_per_pair, (unsigned long long*)sum_ws);
     if (check_launch("pair_u8_sum_kernel")) return 1;
-    pack_pair_u8_kernel<<<dim3(ceil_div(W / 4, 128), min(H, 65535), B), 128, 0, s>>>(frames, (const unsigned long long*)sum_ws, B, H, W, bgr != 0, rgb_max, x_f32, d,
-                                                                                      dst != nullptr, xpad_l);
+    pack_pair_u8_kernel<<<dim3(ceil_div(W, 256), min(H, 65535), B), 256, 0, s>>>(frames, (const unsigned long long*)sum_ws, B, H, W, bgr != 0, rgb_max, x_f32, d,
+                                                                                  dst != nullptr, xpad_l);
     return check_launch("pack_pair_u8_kernel");
 }
 

@@ -216,8 +216,7 @@ int ft_pack_pair(const float* pair, int B, int H, int W, float rgb_max, float* m
 /* The same from uint8 frames as the reference's callers hold them (cv2 frames, lib/tracking/net_utils.py:83-87): frames
  * [B,2,H,W,3] uint8, memory channel order BGR (bgr != 0, cv2) or RGB; the BGR->RGB flip, the float conversion, the per-sample
  * colour mean over both frames (exact integer sums) and the division by rgb_max happen in the packing pass, so a frame pair
- * crosses PCIe as 6 bytes per pixel instead of 24.  sum_ws: B*3 x 8 bytes of scratch (cleared by a memset node).  W must be a
- * multiple of 4 (FlowNet frames are multiples of 64), frames 4-byte and x_f32 16-byte aligned.                              */
+ * crosses PCIe as 6 bytes per pixel instead of 24.  sum_ws: B*3 x 8 bytes of scratch (cleared by a memset node).          */
 int ft_pack_pair_u8(const uint8_t* frames, int B, int H, int W, int bgr, float rgb_max, void* sum_ws, float* x_f32,
                     const ft_act* dst, int xpad_l, int xpad_r, void* stream);
 /* src: [B,C,h,w] fp32 -> dst: [B,C,4h,4w] fp32 times `mul`.  mode 0 = bilinear (align_corners=False),

@@ -3,8 +3,9 @@
     python tools/dev/ncu_summary.py conv  <pose_raw.csv> <flow_raw.csv> <out.json>   # per-launch DRAM bytes, tensor-pipe %, time
     python tools/dev/ncu_summary.py corr  <corr_raw.csv> <out.json>
 
-The JSON records the SHA-256 of the kernel sources the capture was taken with (flowtrack/pytorch_b200/build.py:source_hash);
-bench.py refuses a capture whose hash differs from the library it runs."""
+The JSON records the SHA-256 of the profiled kernel's own translation unit + csrc headers (flowtrack/pytorch_b200/build.py:
+kernel_hash); bench.py refuses a capture whose kernel hash differs from
+the sources the library it runs was built from.  Run it on the tree the capture was taken with."""
 import csv
 import json
 import os
@@ -49,7 +50,7 @@ def conv(pose_csv, flow_csv, out):
         tw += sum(d["gpu__time_duration.sum"] * d["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"] for d in k)
     rec = {"source": "ncu --set full --clock-control none over every conv_tc_kernel launch of one PoseResNet-50 B=64 forward and one FlowNet2S B=16 forward "
                      "(tools/dev/jobs/evidence.sh; raw pages: %s, %s)" % (os.path.basename(pose_csv), os.path.basename(flow_csv)),
-           "source_sha256": ft_build.source_hash(), "launches": n, "dram_bytes_per_launch": dram / n, "time_us_per_launch_under_ncu": t / n * 1e6,
+           "kernel_sources": list(ft_build.CONV_SOURCES), "kernel_sources_sha256": ft_build.kernel_hash(ft_build.CONV_SOURCES), "launches": n, "dram_bytes_per_launch": dram / n, "time_us_per_launch_under_ncu": t / n * 1e6,
            "tensor_pipe_active_pct_time_weighted": tw / t, "per_net": per_net}
     json.dump(rec, open(out, "w"), indent=1)
     print(json.dumps(rec, indent=1))
@@ -65,7 +66,7 @@ def corr(corr_csv, out):
                      "dram_throughput_pct": d.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
                      "l1tex_xbar_read_bytes": d.get("l1tex__m_xbar2l1tex_read_bytes.sum"), "l1tex2xbar_write_bytes": d.get("l1tex__m_l1tex2xbar_write_bytes.sum")})
     rec = {"source": "ncu --set full --clock-control none, corr_pair_kernel at [32,256,48,64] (tools/dev/jobs/evidence.sh; raw page %s)" % os.path.basename(corr_csv),
-           "source_sha256": ft_build.source_hash(), "launches": recs}
+           "kernel_sources": list(ft_build.CORR_SOURCES), "kernel_sources_sha256": ft_build.kernel_hash(ft_build.CORR_SOURCES), "launches": recs}
     json.dump(rec, open(out, "w"), indent=1)
     print(json.dumps(rec, indent=1))
 
