@@ -7,6 +7,8 @@ k4 s2 p1 transposed convolution split into its four output-parity 2x2 sub-convol
 7.3 item 5), and every forward step is a kernel launch in libflowtrack_b200.so.
 """
 import ctypes
+import hashlib
+import json
 import os
 
 import numpy as np
@@ -570,17 +572,22 @@ class Plan:
         if self.impl != _lib.IMPL_TCGEN05 or torch.device(self.device).type != "cuda":
             return self
         fn = _lib.lib().ft_conv2d_fprop
-        if hint is not None and all(not (len(v) > 4 and v[4] > 1) for v in hint.values()):
+        if hint is not None:
             # `hint` = the `tuned` record of a plan with the same layers and shapes (e.g. the other lane of a TrackingPipeline):
-            # adopt its choices instead of measuring again (records with split-K need the workspace: those are re-tuned)
-            for i, (bn, pair, us, nbuf, sk, occ) in hint.items():
-                layer, x, out, out_f32, res = self._conv_args[i]
-                d = layer.desc(x, out, out_f32, res, self.precision, self.impl, tiling=(bn, pair, nbuf, 0, occ))
-                d.tile_order = self.calls[i][3].tile_order
-                self.calls[i] = ("conv2d", fn, (ctypes.byref(d),), d)
-                self.tuned[i] = (bn, pair, us, nbuf, 0, occ)
-            self.graph = None
-            return self
+            # adopt its choices instead of measuring again
+            return self._apply_tuned(hint)
+        cache_path, sig = os.environ.get("FT_AUTOTUNE_CACHE"), None
+        if cache_path:
+            # choices measured by an earlier process on the same GPU model, kernel sources and plan (tools/dev/jobs/evidence.sh tunes
+            # once outside the profiler and lets the runs under ncu load the result, so they profile the production tiling)
+            sig = self.signature()
+            try:
+                with open(cache_path) as f:
+                    rec = json.load(f).get(sig)
+            except (OSError, ValueError):
+                rec = None
+            if rec is not None:
+                return self._apply_tuned({int(i): tuple(v) for i, v in rec.items()})
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         with torch.cuda.device(self.device):
             # one split-K workspace per branch of the plan (the layers of a branch run one after the other on one stream; branches
@@ -673,6 +680,48 @@ class Plan:
                     t, bn, pair, nbuf, sk, occ, d = best
                     self.calls[i] = ("conv2d", fn, (ctypes.byref(d),), d)
                     self.tuned[i] = (bn, pair, t * 1e3, nbuf, sk, occ)
+        self.graph = None
+        if cache_path:
+            try:
+                with open(cache_path) as f:
+                    cache = json.load(f)
+            except (OSError, ValueError):
+                cache = {}
+            cache[sig] = {str(i): list(v) for i, v in self.tuned.items()}
+            with open(cache_path, "w") as f:
+                json.dump(cache, f, indent=0)
+        return self
+
+    def signature(self):
+        """Identifies (GPU model, conv kernel sources, precision, every convolution's layer and input shape) for FT_AUTOTUNE_CACHE."""
+        from . import build as ft_build
+        h = hashlib.sha256((torch.cuda.get_device_name(self.device) + ft_build.kernel_hash(ft_build.CONV_SOURCES) + str(self.precision)).encode())
+        for i, (layer, x, out, out_f32, res) in sorted(self._conv_args.items()):
+            h.update(repr((i, layer.kind, layer.kh, layer.kw, layer.cin, layer.cout, layer.stride, layer.pad, layer.k_mode, layer.residual, x.n, x.h, x.w,
+                           out is None, self._tags.get(i, 0))).encode())
+        return h.hexdigest()
+
+    def _apply_tuned(self, choices):
+        """Rebuild the convolution descriptors from `choices` = {call index: (block_n, cta_pair, us, epilogue_buffers, splitk, ctas_per_sm)}
+        (a `tuned` record); split-K choices get one workspace per branch of the plan, sized for the branch's largest user."""
+        fn = _lib.lib().ft_conv2d_fprop
+        with torch.cuda.device(self.device):
+            need = {}
+            for i, (bn, pair, us, nbuf, sk, occ) in choices.items():
+                if sk > 1:
+                    layer, x, out, out_f32, res = self._conv_args[i]
+                    _items, cta_tiles = layer.tile_counts(x.n, x.h, x.w, bn, pair)
+                    w, c = need.get(self._tags.get(i, 0), (0, 0))
+                    need[self._tags.get(i, 0)] = (max(w, cta_tiles * sk * bn * 128 * 4), max(c, cta_tiles))
+            self._sk_ws = {tag: (torch.empty(w, dtype=torch.uint8, device=self.device), torch.zeros(c, dtype=torch.int32, device=self.device))
+                           for tag, (w, c) in need.items()}
+            self.keep.append(self._sk_ws)
+            for i, (bn, pair, us, nbuf, sk, occ) in choices.items():
+                layer, x, out, out_f32, res = self._conv_args[i]
+                d = layer.desc(x, out, out_f32, res, self.precision, self.impl, tiling=(bn, pair, nbuf, sk, occ), splitk_ws=self._sk_ws.get(self._tags.get(i, 0)))
+                d.tile_order = self.calls[i][3].tile_order
+                self.calls[i] = ("conv2d", fn, (ctypes.byref(d),), d)
+                self.tuned[i] = (bn, pair, us, nbuf, sk, occ)
         self.graph = None
         return self
 

@@ -265,6 +265,32 @@ def test_autotune_picks_tilings_and_keeps_results_bit_identical(monkeypatch):
     assert (a - b).abs().max() <= 2e-6 * a.abs().max()             # bit-identical tile shapes; split-K layers differ by fp32 rounding only
 
 
+def test_autotune_cache_round_trip(monkeypatch, tmp_path):
+    """FT_AUTOTUNE_CACHE: the first plan of a shape measures and records its choices (split-K included), a second plan of the same
+    shape loads them without measuring and computes the same bits."""
+    import json
+    from flowtrack.pytorch_b200.pose import models as pose_models
+    from flowtrack.pytorch_b200.tracking import synthetic
+    cache = tmp_path / "tuned.json"
+    monkeypatch.setenv("FT_AUTOTUNE", "1")
+    monkeypatch.setenv("FT_AUTOTUNE_CACHE", str(cache))
+    torch.manual_seed(0)
+    m = synthetic.condition_pose_weights(pose_models.deconv("resnet50", 17, False), 0).cuda()
+    x = torch.randn(2, 3, 128, 96, generator=torch.Generator().manual_seed(5)).cuda()
+    a = m(x).clone()
+    plan_a = next(iter(m._plans.values()))[0]
+    rec = json.loads(cache.read_text())
+    assert list(rec) == [plan_a.signature()] and len(rec[plan_a.signature()]) == len(plan_a.tuned)
+    assert any(v[4] > 1 for v in plan_a.tuned.values())            # a 2-crop batch has fewer tiles than SMs: some layers split K
+    monkeypatch.setattr(torch.cuda.CUDAGraph, "replay", None)      # a second measurement would have to replay candidate graphs
+    m.use_cuda_graph = False
+    m.refresh()
+    b = m(x).clone()
+    plan_b = next(iter(m._plans.values()))[0]
+    assert plan_b is not plan_a and plan_b.tuned == plan_a.tuned
+    assert torch.equal(a, b)
+
+
 def test_pdl_off_gives_identical_results():
     """Programmatic dependent launch only changes when a kernel's prologue runs: FT_DBG_NO_PDL (ft_set_debug(4, 1)) is bit-identical."""
     from flowtrack.pytorch_b200.pose import models as pose_models
