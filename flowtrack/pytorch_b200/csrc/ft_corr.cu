@@ -33,6 +33,15 @@
 
 namespace ft {
 
+// "This thread has read its part of a TMEM accumulator stage": a pure signal -- the reads are complete when tcgen05.wait::ld
+// returns and no generic-proxy data is handed over -- so the arrive is RELAXED.  The default (.release) makes the thread wait until
+// every global store it has in flight (the previous rows of the band, 21-42 STG per warp) is performed; B200 boxes on driver
+// 580.178 take ~3 us for that, where the 580.159 boxes took ~0.4 us: the same binary went from 105 us to 255 us at [32,256,48,64].
+__device__ __forceinline__ void tmem_stage_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+
 constexpr int CD = 10;                 // displacement radius in parity-class pixels (max_displacement 20 / stride2 2)
 constexpr int CDS = 2 * CD + 1;        // 21
 constexpr int CORR_BM = 128, CORR_BN = 128, CORR_BK = 64;
@@ -242,14 +251,16 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_c
         // =========================== epilogue (warps 0-3) ===========================
         const int q = warp;                                       // TMEM lane quarter = in1' row a0 + q; lane = column b
         float* S = reinterpret_cast<float*>(smem_raw + (slabs - smem_u32(smem_raw))) + warp * (32 * 34);
-        const size_t plane = (size_t)p.H * p.W;
+        // NCHW: lane b writes column 2b+px of row 2a+py; parity-planar: class plane [H2, W2], lane b writes column b (see the pair kernel)
+        const int H2 = (p.H + 1) >> 1, W2 = (p.W + 1) >> 1;
+        const size_t plane = p.planar ? (size_t)4 * H2 * W2 : (size_t)p.H * p.W;
         int acc_it = 0;
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
             const CorrUnit t = corr_unit(p, unit);
             const int a = t.a0 + q;
             const int y = 2 * a + t.py, x = 2 * lane + t.px;
             const bool valid = y < p.H && x < p.W && !(p.dbg_skip & 8);
-            float* o = p.out + (size_t)t.n * (CDS * CDS) * plane + (size_t)y * p.W + x;
+            float* o = p.out + (size_t)t.n * (CDS * CDS) * plane + (p.planar ? ((size_t)t.cls * H2 + a) * W2 + lane : (size_t)y * p.W + x);
             if (t.part == 0) {
                 // displacement rows that fall outside the image: the correlation is zero there (never visited by a chunk)
                 for (int tj = -CD; tj <= CD; ++tj) {
@@ -279,7 +290,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_tc_kernel(const __grid_c
                     if (use0 || use1) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (h == 1) {
                         tc_fence_before();
-                        mbar_arrive(acce_bar(as));              // this thread is done with the TMEM stage
+                        tmem_stage_release(map_to_cta(acce_bar(as), 0));   // this thread is done with the TMEM stage (own CTA = cluster rank 0)
                     }
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {
@@ -603,7 +614,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) corr_pair_kernel(const __grid
                     if (use0 || use1) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (h == 1) {
                         tc_fence_before();
-                        mbar_arrive_remote(acce_remote0 + 8u * as);      // the leader's barrier counts both CTAs' epilogue threads
+                        tmem_stage_release(acce_remote0 + 8u * as);      // the leader's barrier counts both CTAs' epilogue threads
                     }
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {
@@ -869,7 +880,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) corr_tc3_kernel(const __grid_co
                 if (use1) TMEM_LD_32(t_row + (2 * h + 1) * 32, v1);
                 if (use0 || use1) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
-                mbar_arrive(acce_bar(as));                  // this thread is done with the TMEM stage
+                tmem_stage_release(map_to_cta(acce_bar(as), 0));   // this thread is done with the TMEM stage (own CTA = cluster rank 0)
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const bool use = rr ? use1 : use0;
@@ -1038,9 +1049,16 @@ static int correlation_act_impl(const ft_act* in1, const ft_act* in2, float* out
             }
         }
     }
-    int variant = 4;     // 4 = CTA pairs (default), 2 = single CTA with resident A, 3 = A operand in TMEM (experimental)
+    // 2 = single CTA with resident A (default), 4 = CTA pairs (cta_group::2; the only kernel that tiles maps wider than 64 px),
+    // 3 = A operand in TMEM (experimental).  The pair kernel was the default while it was the fastest (105 vs 116 us at
+    // [32,256,48,64] on B200 boxes with driver 580.159); on the 580.178 boxes the plain global stores (STG) of a CLUSTER-launched
+    // kernel run ~6x slower -- the same pair binary takes 255 us there, 81 us with its stores switched off, while the single-CTA
+    // kernel (no cluster) measures 116 us on both (profiles/r02x_corr_cluster_store_regression.txt) -- so the default is the
+    // kernel that does not depend on it.  The convolution kernels are not affected: their cluster variants store through TMA.
+    int variant = 2;
     if (const int v = dev_knob(FT_DBG_CORR_VARIANT)) variant = v;
-    if (k.planar || k.ncc == 2) variant = 4;      // frames wider than 64 px: only the CTA-pair kernel tiles the columns
+    if (k.ncc == 2) variant = 4;                  // frames wider than 64 px: only the CTA-pair kernel tiles the columns
+    if (k.planar && variant == 3) variant = 2;    // the TMEM-operand experiment writes NCHW only
     if (variant == 4) return split ? launch_corr_pair<true>(k, (cudaStream_t)stream) : launch_corr_pair<false>(k, (cudaStream_t)stream);
     if (variant == 3) return split ? launch_corr3<true>(k, (cudaStream_t)stream) : launch_corr3<false>(k, (cudaStream_t)stream);
     return split ? launch_corr<true>(k, (cudaStream_t)stream) : launch_corr<false>(k, (cudaStream_t)stream);

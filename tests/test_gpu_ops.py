@@ -129,9 +129,13 @@ def test_correlation_tensor_core_full_size_properties():
 
 
 @pytest.mark.parametrize("shape", [(2, 256, 48, 64), (3, 128, 16, 24), (1, 64, 6, 2)])
-def test_correlation_planar_layout_and_pack(shape):
-    """ft_correlation_act_planar (parity-planar fp32 [B,441,4,H/2,W/2]) == the NCHW result re-indexed, and
-    ft_pack_corr_planar lands it in channels [32, 473) of a 480-channel NHWC merge buffer like ft_pack_image does."""
+@pytest.mark.parametrize("variant", ["2", "4"], ids=["single_cta", "cta_pair"])
+def test_correlation_planar_layout_and_pack(shape, variant, request):
+    """ft_correlation_act_planar (parity-planar fp32 [B,441,4,H/2,W/2]) == the NCHW result re-indexed -- from the single-CTA kernel
+    (the default) and from the CTA-pair kernel -- and ft_pack_corr_planar lands it in channels [32, 473) of a 480-channel NHWC
+    merge buffer like ft_pack_image does."""
+    L().ft_set_debug(3, int(variant))
+    request.addfinalizer(lambda: L().ft_set_debug(3, 0))
     B, C, H, W = shape
     g = torch.Generator().manual_seed(3 + sum(shape))
     a, b = torch.randn(*shape, generator=g).cuda(), torch.randn(*shape, generator=g).cuda()

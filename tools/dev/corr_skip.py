@@ -19,7 +19,12 @@ for i in range(2):
     st = t.stride()
     _lib.check(L.ft_pack_image(t.data_ptr(), st[0], st[1], st[2], st[3], C, 1.0, act.struct(), 0, 0, 0), "pack")
     acts.append(act)
-o = torch.empty(B, 441, H, W, device="cuda")
+if os.environ.get("OUT_ALLOC") == "big":      # the output as a 2 MiB-aligned slice of one 2 GiB allocation (page-size / TLB experiments)
+    pool = torch.empty(2 << 30, dtype=torch.uint8, device="cuda")
+    off = (-pool.data_ptr()) % (2 << 20)
+    o = pool[off:off + B * 441 * H * W * 4].view(torch.float32).view(B, 441, H, W)
+else:
+    o = torch.empty(B, 441, H, W, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 flush2 = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
 clean = os.environ.get("FLUSH_CLEAN", "0") == "1"
@@ -30,7 +35,10 @@ for i in range(8):
         flush2.sum()      # read 256 MB: L2 ends up holding clean lines instead of the memset's dirty ones
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    _lib.check(L.ft_correlation_act(acts[0].struct(), acts[1].struct(), o.data_ptr(), 1, prec, 0), "corr")
+    if os.environ.get("CORR_PLANAR") == "1":
+        _lib.check(L.ft_correlation_act_planar(acts[0].struct(), acts[1].struct(), o.data_ptr(), 1, prec, 0), "corr")
+    else:
+        _lib.check(L.ft_correlation_act(acts[0].struct(), acts[1].struct(), o.data_ptr(), 1, prec, 0), "corr")
     e1.record()
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))

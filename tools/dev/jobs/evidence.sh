@@ -4,7 +4,7 @@
 #      at the bench shape (16 pairs + 64 crops)                              -> gpurun_out/r02_bench_launches.csv
 #      and at a strong-scaling shard (2 pairs + 8 crops = 1/8 of the batch)   -> gpurun_out/r02_bench_launches_p2.csv
 #   2. ncu --set full over every conv launch of one pose / flow forward     -> gpurun_out/r02_{pose,flow}_full_raw.csv
-#   3. ncu --set full of corr_pair_kernel at BASELINE config 3              -> gpurun_out/r02_corr_raw.csv
+#   3. ncu --set full of corr_tc_kernel (the default correlation kernel) at BASELINE config 3              -> gpurun_out/r02_corr_raw.csv
 #   4. compute-sanitizer memcheck over the split-K conv tests and the elementwise / tracking kernels -> gpurun_out/r02_sanitizer.txt
 # tools/dev/ncu_summary.py (run here, no GPU needed) turns 2-3 into profiles/r02_conv_traffic.json / r02_corr_ncu.json.
 # usage: evidence.sh [all|lists]   (lists = only step 1)
@@ -26,7 +26,7 @@ timeout 900 ncu --set full --clock-control none --profile-from-start off -k rege
 ncu -i gpurun_out/pose_full.ncu-rep --page raw --csv --metrics $M > gpurun_out/r02_pose_full_raw.csv 2>&1
 timeout 900 ncu --set full --clock-control none --profile-from-start off -k regex:conv_tc -o gpurun_out/flow_full python tools/dev/flow_once.py 16 split 2 > gpurun_out/r02_ncu_flow.log 2>&1
 ncu -i gpurun_out/flow_full.ncu-rep --page raw --csv --metrics $M > gpurun_out/r02_flow_full_raw.csv 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:corr_pair -c 4 -o gpurun_out/corr_full python tools/dev/corr_bench.py > gpurun_out/r02_ncu_corr.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:corr_tc_kernel -c 4 -o gpurun_out/corr_full python tools/dev/corr_bench.py > gpurun_out/r02_ncu_corr.log 2>&1
 ncu -i gpurun_out/corr_full.ncu-rep --page raw --csv --metrics $M > gpurun_out/r02_corr_raw.csv 2>&1
 rm -f gpurun_out/pose_full.ncu-rep gpurun_out/flow_full.ncu-rep gpurun_out/corr_full.ncu-rep
 FT_AUTOTUNE=0 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_conv.py tests/test_gpu_track.py tests/test_gpu_ops.py -m gpu -q -x -k "splitk or pack_pair or maxpool or upsample or flow_head or crop or nms or decode or boxprop" > gpurun_out/r02_sanitizer.txt 2>&1; echo "sanitizer rc=$?"

@@ -57,7 +57,7 @@ def conv(pose_csv, flow_csv, out):
 
 
 def corr(corr_csv, out):
-    k = [d for d in rows(corr_csv) if "corr_pair_kernel" in str(d.get("Kernel Name", ""))]
+    k = [d for d in rows(corr_csv) if "corr_tc_kernel" in str(d.get("Kernel Name", "")) or "corr_pair_kernel" in str(d.get("Kernel Name", ""))]
     recs = []
     for d in k:
         recs.append({"kernel": d["Kernel Name"], "time_us_under_ncu": d["gpu__time_duration.sum"] * 1e6,
@@ -65,7 +65,7 @@ def corr(corr_csv, out):
                      "tensor_pipe_active_pct": d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
                      "dram_throughput_pct": d.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
                      "l1tex_xbar_read_bytes": d.get("l1tex__m_xbar2l1tex_read_bytes.sum"), "l1tex2xbar_write_bytes": d.get("l1tex__m_l1tex2xbar_write_bytes.sum")})
-    rec = {"source": "ncu --set full --clock-control none, corr_pair_kernel at [32,256,48,64] (tools/dev/jobs/evidence.sh; raw page %s)" % os.path.basename(corr_csv),
+    rec = {"source": "ncu --set full --clock-control none, the correlation kernel at [32,256,48,64] (tools/dev/jobs/evidence.sh; raw page %s)" % os.path.basename(corr_csv),
            "kernel_sources": list(ft_build.CORR_SOURCES), "kernel_sources_sha256": ft_build.kernel_hash(ft_build.CORR_SOURCES), "launches": recs}
     json.dump(rec, open(out, "w"), indent=1)
     print(json.dumps(rec, indent=1))
