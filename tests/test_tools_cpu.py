@@ -48,3 +48,31 @@ def test_pose_main_options_and_npz_loader(tmp_path):
     batches = list(pm.NpzCrops(path, 2))
     assert [b[0].shape[0] for b in batches] == [2, 2, 1] and set(batches[0][3]) == {"center", "scale", "area", "score"}
     assert pm.num_joints == {"mpii": 16, "aic": 14, "coco": 17}
+
+
+def test_ncu_capture_is_tied_to_the_kernel_sources(tmp_path, monkeypatch):
+    """bench.read_traffic_capture: the committed conv capture is accepted only while the conv kernel's own sources (build.kernel_hash
+    over ft_conv.cu / ft_tc.cuh / ft_common.cuh + flags) are the ones it was taken with and the library was built from the tree."""
+    import json
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    from flowtrack.pytorch_b200 import build as ft_build
+    h = ft_build.kernel_hash(ft_build.CONV_SOURCES)
+    assert h == ft_build.kernel_hash(tuple(reversed(ft_build.CONV_SOURCES))) and h != ft_build.kernel_hash(ft_build.CORR_SOURCES)
+    with open(os.path.join(root, "profiles", "r02_conv_traffic.json")) as f:
+        tr = json.load(f)
+    assert tr["kernel_sources"] == list(ft_build.CONV_SOURCES) and tr["dram_bytes_per_launch"] > 0
+    monkeypatch.setattr(ft_build, "read_info", lambda: {"source_sha256": ft_build.source_hash()})
+    traffic, note = bench.read_traffic_capture(None)
+    if tr["kernel_sources_sha256"] == h:          # the committed capture belongs to the committed conv sources
+        assert traffic == tr["dram_bytes_per_launch"] and note["kernel_sources_sha256"] == h
+    else:
+        assert traffic is None and "other conv kernel sources" in note["refused"]
+    monkeypatch.setattr(ft_build, "kernel_hash", lambda names: "0" * 64)
+    traffic, note = bench.read_traffic_capture(None)
+    assert traffic is None and "other conv kernel sources" in note["refused"]
+    monkeypatch.setattr(ft_build, "read_info", lambda: {"source_sha256": "stale"})
+    traffic, note = bench.read_traffic_capture(None)
+    assert traffic is None and "not built from the sources" in note["refused"]
