@@ -34,9 +34,10 @@
 namespace ft {
 
 // "This thread has read its part of a TMEM accumulator stage": a pure signal -- the reads are complete when tcgen05.wait::ld
-// returns and no generic-proxy data is handed over -- so the arrive is RELAXED.  The default (.release) makes the thread wait until
-// every global store it has in flight (the previous rows of the band, 21-42 STG per warp) is performed; B200 boxes on driver
-// 580.178 take ~3 us for that, where the 580.159 boxes took ~0.4 us: the same binary went from 105 us to 255 us at [32,256,48,64].
+// returns and no generic-proxy data is handed over -- so the arrive is RELAXED: it does not have to order the global stores the
+// thread still has in flight (the previous rows of the band) before it.  (Same SASS and same time as the default .release.cta
+// arrive on the boxes measured; it was tried while looking for the cluster-launch store slowdown described at the variant choice
+// below, which it is not the cause of.)
 __device__ __forceinline__ void tmem_stage_release(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
